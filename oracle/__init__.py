@@ -1,0 +1,112 @@
+"""ctypes binding of the CPU oracle.  TEST INFRASTRUCTURE ONLY (see qpb_oracle.h):
+imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+from quadruped_control_b200.records import OUT_DTYPE, STATE_DTYPE, Params
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "_build", "libqpb_oracle.so")
+_lib = None
+
+
+def build(force=False):
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < max(
+        os.path.getmtime(os.path.join(_HERE, f)) for f in ("qpb_oracle.c", "qpb_oracle.h")
+    ):
+        subprocess.run(["make", "-C", _HERE, "-B"], check=True, capture_output=True)
+    return _LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = ctypes.CDLL(_LIB_PATH)
+        dp = ctypes.POINTER(ctypes.c_double)
+        vp = ctypes.c_void_p
+        L.orc_default_params.argtypes = [vp]
+        L.orc_forward_kinematics.argtypes = [vp, ctypes.c_int, dp, dp]
+        L.orc_leg_jacobian.argtypes = [vp, ctypes.c_int, dp, dp]
+        L.orc_angle_axis_total.argtypes = [dp, dp]
+        L.orc_assemble.argtypes = [vp, vp, dp, dp, dp, dp, dp, dp, dp]
+        L.orc_qp_solve.argtypes = [ctypes.c_int, ctypes.c_int, dp, dp, dp, dp, dp, ctypes.c_int, dp, dp,
+                                   ctypes.POINTER(ctypes.c_int)]
+        L.orc_qp_solve.restype = ctypes.c_int
+        L.orc_control.argtypes = [vp, vp, vp, dp]
+        L.orc_control.restype = ctypes.c_int
+        L.orc_control_batch.argtypes = [vp, vp, ctypes.c_int64, vp, ctypes.c_int]
+        _lib = L
+    return _lib
+
+
+def _dp(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+
+
+def default_params():
+    p = Params()  # same byte layout as orc_params
+    lib().orc_default_params(ctypes.byref(p))
+    return p
+
+
+def forward_kinematics(params, leg, q):
+    q = np.ascontiguousarray(q, dtype=np.float64)
+    out = np.empty(3)
+    lib().orc_forward_kinematics(ctypes.byref(params), leg, _dp(q), _dp(out))
+    return out
+
+
+def leg_jacobian(params, leg, q):
+    q = np.ascontiguousarray(q, dtype=np.float64)
+    out = np.empty(9)
+    lib().orc_leg_jacobian(ctypes.byref(params), leg, _dp(q), _dp(out))
+    return out.reshape(3, 3)
+
+
+def angle_axis_total(R):
+    R = np.ascontiguousarray(R, dtype=np.float64).reshape(9)
+    out = np.empty(3)
+    lib().orc_angle_axis_total(_dp(R), _dp(out))
+    return out
+
+
+def assemble(params, state):
+    """QP of one STATE_DTYPE record in the reference's qpOASES form -> dict(Q,c,C,lb,ub,A,b)."""
+    state = np.ascontiguousarray(state).reshape(1)
+    assert state.dtype == STATE_DTYPE
+    Q, c, C = np.empty(144), np.empty(12), np.empty(240)
+    lb, ub, A, b = np.empty(20), np.empty(20), np.empty(72), np.empty(6)
+    lib().orc_assemble(ctypes.byref(params), state.ctypes.data, _dp(Q), _dp(c), _dp(C), _dp(lb), _dp(ub), _dp(A), _dp(b))
+    return dict(Q=Q.reshape(12, 12), c=c, C=C.reshape(20, 12), lb=lb, ub=ub, A=A.reshape(6, 12), b=b)
+
+
+def qp_solve(Q, c, C, lb, ub, max_iter=200):
+    Q = np.ascontiguousarray(Q, dtype=np.float64)
+    C = np.ascontiguousarray(C, dtype=np.float64)
+    c, lb, ub = (np.ascontiguousarray(v, dtype=np.float64) for v in (c, lb, ub))
+    n, m = Q.shape[0], C.shape[0]
+    x, lam = np.empty(n), np.empty(m)
+    it = ctypes.c_int(0)
+    st = lib().orc_qp_solve(n, m, _dp(Q), _dp(c), _dp(C), _dp(lb), _dp(ub), max_iter, _dp(x), _dp(lam), ctypes.byref(it))
+    return st, x, lam, it.value
+
+
+def control(params, state):
+    """One record -> (OUT_DTYPE scalar array of 1, world-frame QP solution fw)."""
+    state = np.ascontiguousarray(state).reshape(1)
+    out = np.zeros(1, dtype=OUT_DTYPE)
+    fw = np.zeros(12)
+    lib().orc_control(ctypes.byref(params), state.ctypes.data, out.ctypes.data, _dp(fw))
+    return out, fw
+
+
+def control_batch(params, states, nthreads=1):
+    states = np.ascontiguousarray(states)
+    assert states.dtype == STATE_DTYPE
+    out = np.zeros(states.shape[0], dtype=OUT_DTYPE)
+    lib().orc_control_batch(ctypes.byref(params), states.ctypes.data, states.shape[0], out.ctypes.data, int(nthreads))
+    return out

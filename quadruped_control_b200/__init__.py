@@ -1,0 +1,12 @@
+"""qpb200: Blackwell-native batched balance-controller QP solver."""
+from .records import (  # noqa: F401
+    ALGO_BYTES_PER_QP,
+    LEG_NAMES,
+    OUT_DTYPE,
+    QPB_BAD_INPUT,
+    QPB_MAX_ITER,
+    QPB_OK,
+    STATE_DTYPE,
+    Params,
+    default_params,
+)

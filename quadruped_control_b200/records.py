@@ -1,0 +1,110 @@
+"""Flat record layouts of the batched balance-controller boundary.
+
+These mirror ``include/qpb200.h`` byte for byte.  One ``STATE_DTYPE`` item is the argument
+list of ``BalanceController::control`` (reference balance_controller.hpp:104-107) plus the joint
+angles consumed by ``QuadrupedKinematics::jacobianTransposeControl`` (kinematics.hpp:106-107);
+one ``OUT_DTYPE`` item is the ``ForceMap`` + ``TorqueMap`` those two calls return, flattened in
+the reference's leg order RL, FL, RR, FR (commander_node.cpp:61).
+"""
+import ctypes
+
+import numpy as np
+
+LEG_NAMES = ("RL", "FL", "RR", "FR")
+
+STATE_DTYPE = np.dtype(
+    [
+        ("Rwb", "<f8", (9,)),
+        ("Rwb_d", "<f8", (9,)),
+        ("x", "<f8", (3,)),
+        ("xdot", "<f8", (3,)),
+        ("w", "<f8", (3,)),
+        ("x_d", "<f8", (3,)),
+        ("xdot_d", "<f8", (3,)),
+        ("w_d", "<f8", (3,)),
+        ("feet", "<f8", (12,)),
+        ("q", "<f8", (12,)),
+        ("contact", "u1", (4,)),
+        ("pad", "u1", (28,)),
+    ]
+)
+assert STATE_DTYPE.itemsize == 512
+
+OUT_DTYPE = np.dtype(
+    [
+        ("grf_body", "<f8", (12,)),
+        ("tau", "<f8", (12,)),
+        ("status", "<i4"),
+        ("iters", "<i4"),
+        ("pad", "u1", (56,)),
+    ]
+)
+assert OUT_DTYPE.itemsize == 256
+
+# per-QP status (qpb200.h)
+QPB_OK, QPB_MAX_ITER, QPB_BAD_INPUT = 0, 1, 2
+
+# Algorithmic bytes per QP: 60 doubles + 4 contact bytes in, 24 doubles + status out.
+ALGO_BYTES_PER_QP = 60 * 8 + 4 + 24 * 8 + 4
+
+
+class Params(ctypes.Structure):
+    """``qpb_params``: constructor arguments of BalanceController (balance_controller.hpp:85-88),
+    the kinematic constants of QuadrupedKinematics (kinematics.cpp:23-47) and the caller's torque
+    clamp (commander_node.cpp:324-325, 526).  Matrices are row-major."""
+
+    _fields_ = [
+        ("mu", ctypes.c_double),
+        ("mass", ctypes.c_double),
+        ("fzmin", ctypes.c_double),
+        ("fzmax", ctypes.c_double),
+        ("Ib", ctypes.c_double * 9),
+        ("S", ctypes.c_double * 36),
+        ("W", ctypes.c_double * 144),
+        ("kff", ctypes.c_double * 6),
+        ("kp_p", ctypes.c_double * 3),
+        ("kd_p", ctypes.c_double * 3),
+        ("kp_w", ctypes.c_double * 3),
+        ("kd_w", ctypes.c_double * 3),
+        ("hip_offset", ctypes.c_double * 12),
+        ("link", ctypes.c_double * 12),
+        ("tau_min", ctypes.c_double),
+        ("tau_max", ctypes.c_double),
+        ("clamp_tau", ctypes.c_int32),
+        ("max_iter", ctypes.c_int32),
+    ]
+
+    def copy(self):
+        other = Params()
+        ctypes.memmove(ctypes.byref(other), ctypes.byref(self), ctypes.sizeof(self))
+        return other
+
+
+def default_params(mu=0.8):
+    """Values of quadruped_simulation/config/mit_cheetah_config.yaml:66-99 with W = 1e-5*I
+    (commander_node.cpp:289, 305) and the geometry of kinematics.cpp:23-47."""
+    p = Params()
+    p.mu, p.mass, p.fzmin, p.fzmax = mu, 11.0, 10.0, 120.0
+    Ib = np.diag([0.011253, 0.036203, 0.042673])
+    S = np.diag([1.0, 1.0, 1.0, 10.0, 10.0, 5.0])
+    W = 1e-5 * np.eye(12)
+    p.Ib[:] = Ib.ravel().tolist()
+    p.S[:] = S.ravel().tolist()
+    p.W[:] = W.ravel().tolist()
+    p.kff[:] = [0.0, 0.0, 0.15, 0.0, 0.0, 0.0]
+    p.kp_p[:] = [100.0] * 3
+    p.kd_p[:] = [50.0] * 3
+    p.kp_w[:] = [5000.0] * 3
+    p.kd_w[:] = [500.0] * 3
+    xbh, ybh, zbh = 0.196, 0.050, 0.0
+    l1, l2, l3 = 0.077, 0.211, 0.230
+    sx = (-1.0, 1.0, -1.0, 1.0)  # RL FL RR FR
+    sy = (1.0, 1.0, -1.0, -1.0)
+    hip, link = [], []
+    for leg in range(4):
+        hip += [sx[leg] * xbh, sy[leg] * ybh, zbh]
+        link += [sy[leg] * l1, -l2, -l3]
+    p.hip_offset[:] = hip
+    p.link[:] = link
+    p.tau_min, p.tau_max, p.clamp_tau, p.max_iter = -20.0, 20.0, 0, 200
+    return p

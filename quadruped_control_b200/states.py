@@ -1,0 +1,149 @@
+"""Synthetic batched robot states, index-addressable.
+
+Record ``i`` of a stream depends only on ``(seed, i)``: every record consumes exactly
+``DRAWS_PER_RECORD`` 64-bit Philox outputs, so a rank that owns ``[lo, hi)`` advances the
+counter to ``lo`` and generates its shard without touching the rest.  The same function feeds
+the CUDA path, the parity tests and the CPU baseline, so all three see identical bytes.
+
+Foot positions come from the reference's own forward kinematics (kinematics.cpp:81-103), which is
+how the caller produces ``foot_map`` (commander_node.cpp:383-384).
+"""
+import numpy as np
+
+from .records import STATE_DTYPE, Params, default_params
+
+DRAWS_PER_RECORD = 64  # 16 Philox4x64 blocks
+
+# stance pose, quadruped_controller/config/gait_visualizer.yaml:47-50 (RL FL RR FR)
+STANCE_Q = np.array([0.056, 0.90, -1.94, 0.056, 0.90, -1.94, -0.056, 0.90, -1.94, -0.056, 0.90, -1.94])
+
+PROFILES = {
+    # attitude error bound (rad), position box (m), velocity sigmas, angular-velocity sigmas
+    "default": dict(att=0.05, pos=0.05, vel=0.3, vel_d=0.3, w=0.5, w_d=0.2),
+    "light": dict(att=0.002, pos=0.01, vel=0.02, vel_d=0.02, w=0.01, w_d=0.01),
+    "stress": dict(att=0.3, pos=0.05, vel=0.3, vel_d=0.3, w=0.5, w_d=0.2),
+}
+
+# the 11 contact masks with >= 2 stance feet (bit i = leg i in RL FL RR FR order)
+MIXED_MASKS = np.array([m for m in range(16) if bin(m).count("1") >= 2], dtype=np.uint8)
+assert len(MIXED_MASKS) == 11
+
+
+def forward_kinematics(q, params: Params = None):
+    """Body-frame foot positions, (..., 12) joint angles -> (..., 12); kinematics.cpp:96-100."""
+    params = params or default_params()
+    q = np.asarray(q, dtype=np.float64)
+    hip = np.array(params.hip_offset[:]).reshape(4, 3)
+    link = np.array(params.link[:]).reshape(4, 3)
+    qq = q.reshape(q.shape[:-1] + (4, 3))
+    t1, t2, t3 = qq[..., 0], qq[..., 1], qq[..., 2]
+    l1, l2, l3 = link[:, 0], link[:, 1], link[:, 2]
+    out = np.empty_like(qq)
+    out[..., 0] = l2 * np.sin(t2) + l3 * np.sin(t2 + t3) + hip[:, 0]
+    out[..., 1] = l1 * np.cos(t1) - l2 * np.sin(t1) * np.cos(t2) - l3 * np.sin(t1) * np.cos(t2 + t3) + hip[:, 1]
+    out[..., 2] = l1 * np.sin(t1) + l2 * np.cos(t1) * np.cos(t2) + l3 * np.cos(t1) * np.cos(t2 + t3) + hip[:, 2]
+    return out.reshape(q.shape)
+
+
+def _rpy_matrix(roll, pitch, yaw):
+    """R = Rz(yaw) Ry(pitch) Rx(roll), batched -> (n, 3, 3)."""
+    cr, sr, cp, sp, cy, sy = np.cos(roll), np.sin(roll), np.cos(pitch), np.sin(pitch), np.cos(yaw), np.sin(yaw)
+    R = np.empty(roll.shape + (3, 3))
+    R[:, 0, 0] = cy * cp
+    R[:, 0, 1] = cy * sp * sr - sy * cr
+    R[:, 0, 2] = cy * sp * cr + sy * sr
+    R[:, 1, 0] = sy * cp
+    R[:, 1, 1] = sy * sp * sr + cy * cr
+    R[:, 1, 2] = sy * sp * cr - cy * sr
+    R[:, 2, 0] = -sp
+    R[:, 2, 1] = cp * sr
+    R[:, 2, 2] = cp * cr
+    return R
+
+
+def _exp_so3(v):
+    """Rodrigues, (n,3) -> (n,3,3)."""
+    th = np.linalg.norm(v, axis=1)
+    small = th < 1e-12
+    ths = np.where(small, 1.0, th)
+    k = v / ths[:, None]
+    K = np.zeros(v.shape[:1] + (3, 3))
+    K[:, 0, 1], K[:, 0, 2] = -k[:, 2], k[:, 1]
+    K[:, 1, 0], K[:, 1, 2] = k[:, 2], -k[:, 0]
+    K[:, 2, 0], K[:, 2, 1] = -k[:, 1], k[:, 0]
+    s, c = np.sin(th)[:, None, None], np.cos(th)[:, None, None]
+    E = np.eye(3)[None] + s * K + (1.0 - c) * (K @ K)
+    E[small] = np.eye(3)
+    return E
+
+
+def stance_state(params: Params = None):
+    """BASELINE config 1: one robot, 4-foot stance pose."""
+    params = params or default_params()
+    s = np.zeros(1, dtype=STATE_DTYPE)
+    s["Rwb"][0] = np.eye(3).ravel()
+    s["Rwb_d"][0] = np.eye(3).ravel()
+    s["x"][0] = (0.0, 0.0, 0.2429)
+    s["x_d"][0] = (0.0, 0.0, 0.26)  # commander_node.cpp:354
+    s["q"][0] = STANCE_Q
+    s["feet"][0] = forward_kinematics(STANCE_Q, params)
+    s["contact"][0] = 1
+    return s
+
+
+def generate_states(n, seed, lo=0, profile="default", masks="all4", params: Params = None):
+    """Records [lo, lo+n) of stream ``seed`` as a STATE_DTYPE array."""
+    params = params or default_params()
+    prof = PROFILES[profile] if isinstance(profile, str) else profile
+    bg = np.random.Philox(key=int(seed))
+    bg.advance(int(lo) * (DRAWS_PER_RECORD // 4))
+    raw = bg.random_raw(int(n) * DRAWS_PER_RECORD).reshape(int(n), DRAWS_PER_RECORD)
+    u = (raw >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)  # [0,1)
+    del raw
+    uni = u[:, :32]
+    # Box-Muller on the upper half: 16 pairs -> 32 standard normals
+    rad = np.sqrt(-2.0 * np.log(1.0 - u[:, 32:48]))
+    ang = 2.0 * np.pi * u[:, 48:64]
+    nrm = np.concatenate([rad * np.cos(ang), rad * np.sin(ang)], axis=1)
+
+    def sym(col, half):  # U(-half, half)
+        return (2.0 * uni[:, col] - 1.0) * half
+
+    s = np.zeros(int(n), dtype=STATE_DTYPE)
+    R = _rpy_matrix(sym(0, 0.3), sym(1, 0.3), sym(2, np.pi))
+    direction = nrm[:, 0:3]
+    dn = np.linalg.norm(direction, axis=1, keepdims=True)
+    direction = direction / np.where(dn > 0, dn, 1.0)
+    delta = direction * (uni[:, 3:4] * prof["att"])
+    Rd = _exp_so3(delta) @ R
+    s["Rwb"] = R.reshape(-1, 9)
+    s["Rwb_d"] = Rd.reshape(-1, 9)
+    x = np.array([0.0, 0.0, 0.26]) + (2.0 * uni[:, 4:7] - 1.0) * prof["pos"]
+    s["x"] = x
+    s["x_d"] = x + (2.0 * uni[:, 7:10] - 1.0) * prof["pos"]
+    xdot = nrm[:, 3:6] * prof["vel"]
+    s["xdot"] = xdot
+    s["xdot_d"] = xdot + nrm[:, 6:9] * prof["vel_d"]
+    w = nrm[:, 9:12] * prof["w"]
+    s["w"] = w
+    s["w_d"] = w + nrm[:, 12:15] * prof["w_d"]
+    q = STANCE_Q + (2.0 * uni[:, 10:22] - 1.0) * 0.3
+    s["q"] = q
+    s["feet"] = forward_kinematics(q, params)
+    if masks == "all4":
+        s["contact"] = 1
+    elif masks == "mixed":
+        m = MIXED_MASKS[np.minimum((uni[:, 22] * 11).astype(np.int64), 10)]
+        s["contact"] = (m[:, None] >> np.arange(4, dtype=np.uint8)) & 1
+    else:
+        raise ValueError(masks)
+    return s
+
+
+# BASELINE.json configs
+CONFIGS = {
+    "cfg1_stance": dict(n=1, seed=None, mu=0.8, masks="all4"),
+    "cfg2_all4_65536": dict(n=65536, seed=20260102, mu=0.6, masks="all4"),
+    "cfg3_mixed_1m": dict(n=1048576, seed=20260103, mu=0.6, masks="mixed"),
+    "cfg5_mixed_8m": dict(n=8388608, seed=20260105, mu=0.6, masks="mixed"),
+}
