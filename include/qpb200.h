@@ -1,0 +1,134 @@
+/*
+ * qpb200.h -- C ABI of libqpb200.so: the batched, B200-native replacement of the reference's
+ * balance-controller hot path.
+ *
+ * The reference (bostoncleek/quadruped_control) has no FFI layer; the boundary a maintainer binds is
+ * the C++ class API below (paths relative to quadruped_controller/):
+ *   BalanceController::BalanceController(...)               include/quadruped_controller/balance_controller.hpp:85-88
+ *   ForceMap BalanceController::control(...) const          include/quadruped_controller/balance_controller.hpp:104-107
+ *   TorqueMap QuadrupedKinematics::jacobianTransposeControl include/quadruped_controller/kinematics.hpp:106-107
+ *   FootholdMap QuadrupedKinematics::forwardKinematics      include/quadruped_controller/kinematics.hpp:58-60
+ * called once per control tick at src/commander_node.cpp:337-338 (ctor), 383-384 (FK) and 507-512.
+ * quadruped_control_b200/cpp/balance_controller.hpp keeps those C++ signatures on top of this ABI.
+ *
+ * Conventions: plain pointers and sizes, no exceptions, every call returns 0 or a negative
+ * qpb_error; all arithmetic FP64; matrices row-major; legs in the reference's order RL, FL, RR, FR
+ * (commander_node.cpp:61); contact 1 = stance, 0 = swing (types.hpp:91-95).  There is NO CPU
+ * fallback: without a CUDA device every compute entry point fails with QPB_ERR_CUDA.
+ */
+#ifndef QPB200_H
+#define QPB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QPB_VERSION 100
+
+typedef enum qpb_error {
+  QPB_SUCCESS = 0,
+  QPB_ERR_INVALID_ARG = -1, /* null pointer, negative n, misaligned record pointer */
+  QPB_ERR_BAD_PARAMS = -2,  /* parameters outside what the solver proves correct (see qpb_create) */
+  QPB_ERR_CUDA = -3,        /* CUDA runtime error; text in qpb_last_error() */
+  QPB_ERR_NO_MEMORY = -4
+} qpb_error;
+
+/* per-QP status written next to each result */
+enum { QPB_OK = 0, QPB_MAX_ITER = 1, QPB_BAD_INPUT = 2 };
+
+/* Constructor arguments of BalanceController (balance_controller.hpp:85-88; stored at
+ * balance_controller.cpp:70-96), the kinematic constants QuadrupedKinematics hard-codes
+ * (kinematics.cpp:23-47) and the caller's torque clamp (commander_node.cpp:324-325, 526). */
+typedef struct qpb_params {
+  double mu, mass, fzmin, fzmax;
+  double Ib[9];   /* body inertia, 3x3 */
+  double S[36];   /* least-squares weight, 6x6 symmetric positive definite */
+  double W[144];  /* force regulariser, 12x12 symmetric positive definite */
+  double kff[6], kp_p[3], kd_p[3], kp_w[3], kd_w[3];
+  double hip_offset[12]; /* base->hip translation per leg */
+  double link[12];       /* signed (l1, l2, l3) per leg: +l1 left legs, -l1 right legs, -l2, -l3 */
+  double tau_min, tau_max;
+  int32_t clamp_tau; /* 0 (default): return J^T f unclamped, as jacobianTransposeControl does */
+  int32_t max_iter;  /* working-set changes allowed per QP; nWSR_ = 200, balance_controller.cpp:85 */
+} qpb_params;
+
+/* One robot state = the argument list of control() + the joint angles of
+ * jacobianTransposeControl().  512 bytes, 16-byte aligned: one coalesced load per warp. */
+typedef struct qpb_state_rec {
+  double Rwb[9], Rwb_d[9];
+  double x[3], xdot[3], w[3], x_d[3], xdot_d[3], w_d[3];
+  double feet[12]; /* body-frame foot positions (FootholdMap), leg-major */
+  double q[12];    /* joint angles (JointStatesMap.q), leg-major: hip, thigh, calf */
+  uint8_t contact[4];
+  uint8_t pad[28];
+} qpb_state_rec;
+
+/* ForceMap + TorqueMap flattened.  Swing legs (absent from the reference's maps,
+ * balance_controller.cpp:223-228) are zero.  When status != QPB_OK every force and torque is
+ * zero, which is the reference's "empty map" failure return (balance_controller.cpp:182-216). */
+typedef struct qpb_out_rec {
+  double grf_body[12];
+  double tau[12];
+  int32_t status;
+  int32_t iters; /* working-set changes used */
+  uint8_t pad[56];
+} qpb_out_rec;
+
+typedef struct qpb_handle qpb_handle;
+
+int qpb_version(void);
+/* Text of the last error raised on the calling thread ("" if none). */
+const char* qpb_last_error(void);
+
+/* mit_cheetah_config.yaml:66-99 with W = 1e-5*I (commander_node.cpp:289, 305). */
+int qpb_default_params(qpb_params* out);
+
+/* Replaces the BalanceController + QuadrupedKinematics constructors (commander_node.cpp:337-338, 358).
+ * Rejects (QPB_ERR_BAD_PARAMS): non-finite values, mu <= 0, fzmin > fzmax, fzmax < 0,
+ * S or W not symmetric positive definite, max_iter < 1, and 2*mu*fzmax > 1e6 (the reference's
+ * finite "far" bounds of +-1e6, balance_controller.cpp:296-297, are provably inactive below that
+ * and the solver does not carry them). */
+int qpb_create(const qpb_params* params, int device, qpb_handle** out);
+int qpb_destroy(qpb_handle* h);
+
+/* control() + jacobianTransposeControl() for n robots; packed records resident on the device.
+ * stream is a cudaStream_t (NULL = default stream).  Asynchronous. */
+int qpb_control_batch_packed(qpb_handle* h, int64_t n, const qpb_state_rec* d_states, qpb_out_rec* d_out,
+                             void* stream);
+
+/* Same, argument-per-array (device pointers), mirroring the control() parameter list
+ * (balance_controller.hpp:104-107): Rwb, Rwb_d [n*9]; x, xdot, w, x_d, xdot_d, w_d [n*3];
+ * feet_body [n*12]; contact [n*4]; q [n*12] -> grf_body [n*12], tau [n*12], status [n].
+ * tau and status may be NULL. */
+int qpb_control_batch(qpb_handle* h, int64_t n, const double* Rwb, const double* Rwb_d, const double* x,
+                      const double* xdot, const double* w, const double* x_d, const double* xdot_d,
+                      const double* w_d, const double* feet_body, const uint8_t* contact, const double* q,
+                      double* grf_body, double* tau, int32_t* status, void* stream);
+
+/* Host-buffer entry point: copies records to the device in chunks, solves, copies results back,
+ * overlapping the three on internal streams; returns when h_out is complete.  Buffers may be
+ * pageable; pinned ones (qpb_host_alloc) reach PCIe speed. */
+int qpb_control_batch_host(qpb_handle* h, int64_t n, const qpb_state_rec* h_states, qpb_out_rec* h_out);
+
+/* jacobianTransposeControl() alone (kinematics.cpp:218-231): tau = J(q)^T f for stance legs,
+ * 0 for swing legs.  Device pointers: q [n*12], grf_body [n*12], contact [n*4] (NULL = all stance). */
+int qpb_jt_batch(qpb_handle* h, int64_t n, const double* q, const double* grf_body, const uint8_t* contact,
+                 double* tau, void* stream);
+
+/* forwardKinematics() (kinematics.cpp:81-103): q [n*12] -> feet_body [n*12]; device pointers. */
+int qpb_fk_batch(qpb_handle* h, int64_t n, const double* q, double* feet_body, void* stream);
+
+/* Pinned host memory for qpb_control_batch_host callers. */
+int qpb_host_alloc(void** ptr, size_t bytes);
+int qpb_host_free(void* ptr);
+
+/* Number of CUDA kernels this handle has launched so far (for the benchmark's gpu_launches). */
+int64_t qpb_launch_count(const qpb_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QPB200_H */

@@ -280,11 +280,17 @@ int orc_qp_solve(int n, int m, const double* Q, const double* c, const double* C
   int status = 0, it = 0;
   /* one-sided list */
   int mc = 0;
-  int* crow = (int*)malloc(sizeof(int) * 2 * m);
-  double* csgn = (double*)malloc(sizeof(double) * 2 * m);
-  double* cb = (double*)malloc(sizeof(double) * 2 * m);
-  int* ceq = (int*)malloc(sizeof(int) * 2 * m);
-  int* cact = (int*)calloc(2 * m, sizeof(int));
+  /* stack workspace for the balance QP sizes; heap only for larger problems */
+  enum { NS = 16, MS = 32 };
+  int crow_s[2 * MS], ceq_s[2 * MS], cact_s[2 * MS], A_s[NS + 1];
+  double csgn_s[2 * MS], cb_s[2 * MS], ws_s[3 * NS * NS + 6 * NS + 8];
+  const int small = (n <= NS && m <= MS);
+  int* crow = small ? crow_s : (int*)malloc(sizeof(int) * 2 * m);
+  double* csgn = small ? csgn_s : (double*)malloc(sizeof(double) * 2 * m);
+  double* cb = small ? cb_s : (double*)malloc(sizeof(double) * 2 * m);
+  int* ceq = small ? ceq_s : (int*)malloc(sizeof(int) * 2 * m);
+  int* cact = small ? cact_s : (int*)malloc(sizeof(int) * 2 * m);
+  memset(cact, 0, sizeof(int) * 2 * m);
   for (int pass = 0; pass < 2; pass++) /* equalities first */
     for (int i = 0; i < m; i++) {
       const int eq = (lb[i] == ub[i]);
@@ -295,10 +301,12 @@ int orc_qp_solve(int n, int m, const double* Q, const double* c, const double* C
         if (ub[i] < INF) { crow[mc] = i; csgn[mc] = -1.0; cb[mc] = -ub[i]; ceq[mc] = 0; mc++; }
       }
     }
-  double* ws = (double*)calloc((size_t)(3 * n * n + 6 * n + 8), sizeof(double));
+  const size_t wsn = (size_t)(3 * n * n + 6 * n + 8);
+  double* ws = small ? ws_s : (double*)malloc(wsn * sizeof(double));
+  memset(ws, 0, wsn * sizeof(double));
   double *L = ws, *J = L + n * n, *R = J + n * n;
   double *d = R + n * n, *z = d + n, *r = z + n, *u = r + n, *nv = u + n + 1;
-  int* A = (int*)malloc(sizeof(int) * (n + 1));
+  int* A = small ? A_s : (int*)malloc(sizeof(int) * (n + 1));
   gi_fact f = { n, J, R, 0 };
   if (lam) memset(lam, 0, sizeof(double) * m);
 
@@ -435,7 +443,7 @@ int orc_qp_solve(int n, int m, const double* Q, const double* c, const double* C
     for (int j = 0; j < f.q; j++) lam[crow[A[j]]] += csgn[A[j]] * u[j];
 done:
   if (iters) *iters = it;
-  free(A); free(ws); free(cact); free(ceq); free(cb); free(csgn); free(crow);
+  if (!small) { free(A); free(ws); free(cact); free(ceq); free(cb); free(csgn); free(crow); }
   return status;
 }
 

@@ -1,0 +1,294 @@
+// qpb_api.cu -- C ABI of libqpb200.so (include/qpb200.h) on top of the kernels in qpb_kernel.cuh.
+// Host side of the drop-in boundary: plain pointers in, plain pointers out, no exceptions.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "qpb_kernel.cuh"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+
+#define QPB_CUDA(expr)                                                                         \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess) {                                                                   \
+      return fail(QPB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));           \
+    }                                                                                          \
+  } while (0)
+
+// dense Cholesky test for "symmetric positive definite"
+bool is_sympd(const double* A, int n) {
+  double L[144];
+  for (int i = 0; i < n; i++)
+    for (int j = 0; j < n; j++) {
+      const double a = A[i * n + j], b = A[j * n + i];
+      if (std::fabs(a - b) > 1e-12 * (std::fabs(a) + std::fabs(b))) return false;
+    }
+  for (int j = 0; j < n; j++) {
+    double s = A[j * n + j];
+    for (int k = 0; k < j; k++) s -= L[j * n + k] * L[j * n + k];
+    if (!(s > 0.0)) return false;
+    L[j * n + j] = std::sqrt(s);
+    for (int i = j + 1; i < n; i++) {
+      double t = A[i * n + j];
+      for (int k = 0; k < j; k++) t -= L[i * n + k] * L[j * n + k];
+      L[i * n + j] = t / L[j * n + j];
+    }
+  }
+  return true;
+}
+
+constexpr int kHostSlots = 3;          // streams / staging slots of the host-buffer pipeline
+constexpr int64_t kHostChunk = 16384;  // records per pipeline stage (8 MiB in, 4 MiB out)
+
+}  // namespace
+
+struct qpb_handle {
+  int device = 0;
+  int num_sms = 0;
+  int ctas_per_sm_packed = 0, ctas_per_sm_split = 0;
+  qpb_params params;
+  qpb_params* d_params = nullptr;
+  cudaStream_t streams[kHostSlots] = { nullptr, nullptr, nullptr };
+  qpb_state_rec* d_in[kHostSlots] = { nullptr, nullptr, nullptr };
+  qpb_out_rec* d_out[kHostSlots] = { nullptr, nullptr, nullptr };
+  std::atomic<int64_t> launches{ 0 };
+};
+
+namespace {
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+    if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+template <class IO>
+int launch_balance(qpb_handle* h, const IO& io, int64_t n, int ctas_per_sm, cudaStream_t stream) {
+  if (n == 0) return QPB_SUCCESS;
+  const int64_t want = (n + qpb::WARPS_PER_CTA - 1) / qpb::WARPS_PER_CTA;
+  const int64_t cap = (int64_t)h->num_sms * ctas_per_sm;
+  const int grid = (int)(want < cap ? want : cap);
+  qpb::balance_qp_kernel<IO><<<grid, qpb::WARPS_PER_CTA * 32, 0, stream>>>(h->d_params, io, n);
+  h->launches.fetch_add(1, std::memory_order_relaxed);
+  QPB_CUDA(cudaGetLastError());
+  return QPB_SUCCESS;
+}
+
+}  // namespace
+
+extern "C" {
+
+int qpb_version(void) { return QPB_VERSION; }
+
+const char* qpb_last_error(void) { return g_last_error.c_str(); }
+
+int qpb_default_params(qpb_params* p) {
+  if (!p) return fail(QPB_ERR_INVALID_ARG, "qpb_default_params: null pointer");
+  std::memset(p, 0, sizeof(*p));
+  p->mu = 0.8;
+  p->mass = 11.0;
+  p->fzmin = 10.0;
+  p->fzmax = 120.0;
+  p->Ib[0] = 0.011253;
+  p->Ib[4] = 0.036203;
+  p->Ib[8] = 0.042673;
+  const double sd[6] = { 1.0, 1.0, 1.0, 10.0, 10.0, 5.0 };
+  for (int i = 0; i < 6; i++) p->S[7 * i] = sd[i];
+  for (int i = 0; i < 12; i++) p->W[13 * i] = 1e-5;
+  p->kff[2] = 0.15;
+  for (int i = 0; i < 3; i++) {
+    p->kp_p[i] = 100.0;
+    p->kd_p[i] = 50.0;
+    p->kp_w[i] = 5000.0;
+    p->kd_w[i] = 500.0;
+  }
+  const double sx[4] = { -1.0, 1.0, -1.0, 1.0 }, sy[4] = { 1.0, 1.0, -1.0, -1.0 };  // RL FL RR FR
+  for (int leg = 0; leg < 4; leg++) {
+    p->hip_offset[3 * leg] = sx[leg] * 0.196;
+    p->hip_offset[3 * leg + 1] = sy[leg] * 0.050;
+    p->hip_offset[3 * leg + 2] = 0.0;
+    p->link[3 * leg] = sy[leg] * 0.077;
+    p->link[3 * leg + 1] = -0.211;
+    p->link[3 * leg + 2] = -0.230;
+  }
+  p->tau_min = -20.0;
+  p->tau_max = 20.0;
+  p->clamp_tau = 0;
+  p->max_iter = 200;
+  return QPB_SUCCESS;
+}
+
+int qpb_create(const qpb_params* params, int device, qpb_handle** out) {
+  if (!params || !out) return fail(QPB_ERR_INVALID_ARG, "qpb_create: null pointer");
+  *out = nullptr;
+  const double* pd = reinterpret_cast<const double*>(params);
+  const size_t nd = offsetof(qpb_params, clamp_tau) / sizeof(double);
+  for (size_t i = 0; i < nd; i++)
+    if (!std::isfinite(pd[i])) return fail(QPB_ERR_BAD_PARAMS, "qpb_create: non-finite parameter");
+  if (!(params->mu > 0.0)) return fail(QPB_ERR_BAD_PARAMS, "qpb_create: mu must be > 0");
+  if (!(params->fzmin <= params->fzmax)) return fail(QPB_ERR_BAD_PARAMS, "qpb_create: fzmin > fzmax");
+  if (!(params->fzmax >= 0.0)) return fail(QPB_ERR_BAD_PARAMS, "qpb_create: fzmax < 0 leaves the friction pyramid empty");
+  if (!(2.0 * params->mu * params->fzmax <= 1.0e6))
+    return fail(QPB_ERR_BAD_PARAMS, "qpb_create: 2*mu*fzmax > 1e6: the reference's far bounds could become active");
+  if (params->max_iter < 1) return fail(QPB_ERR_BAD_PARAMS, "qpb_create: max_iter < 1");
+  if (!is_sympd(params->S, 6)) return fail(QPB_ERR_BAD_PARAMS, "qpb_create: S is not symmetric positive definite");
+  if (!is_sympd(params->W, 12)) return fail(QPB_ERR_BAD_PARAMS, "qpb_create: W is not symmetric positive definite");
+
+  int ndev = 0;
+  QPB_CUDA(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(QPB_ERR_INVALID_ARG, "qpb_create: no such CUDA device");
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(QPB_ERR_CUDA, "qpb_create: cudaSetDevice failed");
+  qpb_handle* h = new (std::nothrow) qpb_handle;
+  if (!h) return fail(QPB_ERR_NO_MEMORY, "qpb_create: out of host memory");
+  h->device = device;
+  h->params = *params;
+  cudaDeviceProp prop;
+  cudaError_t e = cudaGetDeviceProperties(&prop, device);
+  if (e == cudaSuccess) e = cudaMalloc(&h->d_params, sizeof(qpb_params));
+  if (e == cudaSuccess) e = cudaMemcpy(h->d_params, params, sizeof(qpb_params), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess)
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->ctas_per_sm_packed, qpb::balance_qp_kernel<qpb::PackedIO>,
+                                                      qpb::WARPS_PER_CTA * 32, 0);
+  if (e == cudaSuccess)
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->ctas_per_sm_split, qpb::balance_qp_kernel<qpb::SplitIO>,
+                                                      qpb::WARPS_PER_CTA * 32, 0);
+  if (e != cudaSuccess || h->ctas_per_sm_packed < 1 || h->ctas_per_sm_split < 1) {
+    const std::string msg = std::string("qpb_create: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "kernel does not fit");
+    if (h->d_params) cudaFree(h->d_params);
+    delete h;
+    return fail(QPB_ERR_CUDA, msg);
+  }
+  h->num_sms = prop.multiProcessorCount;
+  *out = h;
+  return QPB_SUCCESS;
+}
+
+int qpb_destroy(qpb_handle* h) {
+  if (!h) return QPB_SUCCESS;
+  DeviceGuard guard(h->device);
+  for (int s = 0; s < kHostSlots; s++) {
+    if (h->streams[s]) cudaStreamDestroy(h->streams[s]);
+    if (h->d_in[s]) cudaFree(h->d_in[s]);
+    if (h->d_out[s]) cudaFree(h->d_out[s]);
+  }
+  if (h->d_params) cudaFree(h->d_params);
+  delete h;
+  return QPB_SUCCESS;
+}
+
+int qpb_control_batch_packed(qpb_handle* h, int64_t n, const qpb_state_rec* d_states, qpb_out_rec* d_out,
+                             void* stream) {
+  if (!h || n < 0 || (n > 0 && (!d_states || !d_out)))
+    return fail(QPB_ERR_INVALID_ARG, "qpb_control_batch_packed: bad argument");
+  if ((reinterpret_cast<uintptr_t>(d_states) & 15u) || (reinterpret_cast<uintptr_t>(d_out) & 15u))
+    return fail(QPB_ERR_INVALID_ARG, "qpb_control_batch_packed: records must be 16-byte aligned");
+  DeviceGuard guard(h->device);
+  if (!guard.ok) return fail(QPB_ERR_CUDA, "cudaSetDevice failed");
+  qpb::PackedIO io{ d_states, d_out };
+  return launch_balance(h, io, n, h->ctas_per_sm_packed, static_cast<cudaStream_t>(stream));
+}
+
+int qpb_control_batch(qpb_handle* h, int64_t n, const double* Rwb, const double* Rwb_d, const double* x,
+                      const double* xdot, const double* w, const double* x_d, const double* xdot_d,
+                      const double* w_d, const double* feet_body, const uint8_t* contact, const double* q,
+                      double* grf_body, double* tau, int32_t* status, void* stream) {
+  if (!h || n < 0) return fail(QPB_ERR_INVALID_ARG, "qpb_control_batch: bad argument");
+  if (n > 0 && (!Rwb || !Rwb_d || !x || !xdot || !w || !x_d || !xdot_d || !w_d || !feet_body || !contact || !q ||
+                !grf_body))
+    return fail(QPB_ERR_INVALID_ARG, "qpb_control_batch: null array");
+  DeviceGuard guard(h->device);
+  if (!guard.ok) return fail(QPB_ERR_CUDA, "cudaSetDevice failed");
+  qpb::SplitIO io{ Rwb, Rwb_d, x, xdot, w, x_d, xdot_d, w_d, feet_body, q, contact, grf_body, tau, status };
+  return launch_balance(h, io, n, h->ctas_per_sm_split, static_cast<cudaStream_t>(stream));
+}
+
+int qpb_control_batch_host(qpb_handle* h, int64_t n, const qpb_state_rec* h_states, qpb_out_rec* h_out) {
+  if (!h || n < 0 || (n > 0 && (!h_states || !h_out)))
+    return fail(QPB_ERR_INVALID_ARG, "qpb_control_batch_host: bad argument");
+  if (n == 0) return QPB_SUCCESS;
+  DeviceGuard guard(h->device);
+  if (!guard.ok) return fail(QPB_ERR_CUDA, "cudaSetDevice failed");
+  for (int s = 0; s < kHostSlots; s++) {  // lazily create the pipeline
+    if (!h->streams[s]) QPB_CUDA(cudaStreamCreateWithFlags(&h->streams[s], cudaStreamNonBlocking));
+    if (!h->d_in[s]) QPB_CUDA(cudaMalloc(&h->d_in[s], kHostChunk * sizeof(qpb_state_rec)));
+    if (!h->d_out[s]) QPB_CUDA(cudaMalloc(&h->d_out[s], kHostChunk * sizeof(qpb_out_rec)));
+  }
+  int slot = 0;
+  for (int64_t lo = 0; lo < n; lo += kHostChunk, slot = (slot + 1) % kHostSlots) {
+    const int64_t m = (n - lo < kHostChunk) ? (n - lo) : kHostChunk;
+    cudaStream_t st = h->streams[slot];
+    QPB_CUDA(cudaMemcpyAsync(h->d_in[slot], h_states + lo, m * sizeof(qpb_state_rec), cudaMemcpyHostToDevice, st));
+    qpb::PackedIO io{ h->d_in[slot], h->d_out[slot] };
+    const int rc = launch_balance(h, io, m, h->ctas_per_sm_packed, st);
+    if (rc != QPB_SUCCESS) return rc;
+    QPB_CUDA(cudaMemcpyAsync(h_out + lo, h->d_out[slot], m * sizeof(qpb_out_rec), cudaMemcpyDeviceToHost, st));
+  }
+  for (int s = 0; s < kHostSlots; s++) QPB_CUDA(cudaStreamSynchronize(h->streams[s]));
+  return QPB_SUCCESS;
+}
+
+int qpb_jt_batch(qpb_handle* h, int64_t n, const double* q, const double* grf_body, const uint8_t* contact,
+                 double* tau, void* stream) {
+  if (!h || n < 0 || (n > 0 && (!q || !grf_body || !tau))) return fail(QPB_ERR_INVALID_ARG, "qpb_jt_batch: bad argument");
+  if (n == 0) return QPB_SUCCESS;
+  DeviceGuard guard(h->device);
+  if (!guard.ok) return fail(QPB_ERR_CUDA, "cudaSetDevice failed");
+  const int64_t nlegs = 4 * n;
+  const int threads = 128;
+  const int64_t blocks = (nlegs + threads - 1) / threads;
+  qpb::jt_kernel<<<(unsigned)blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(h->d_params, q, grf_body, contact,
+                                                                                     tau, nlegs);
+  h->launches.fetch_add(1, std::memory_order_relaxed);
+  QPB_CUDA(cudaGetLastError());
+  return QPB_SUCCESS;
+}
+
+int qpb_fk_batch(qpb_handle* h, int64_t n, const double* q, double* feet_body, void* stream) {
+  if (!h || n < 0 || (n > 0 && (!q || !feet_body))) return fail(QPB_ERR_INVALID_ARG, "qpb_fk_batch: bad argument");
+  if (n == 0) return QPB_SUCCESS;
+  DeviceGuard guard(h->device);
+  if (!guard.ok) return fail(QPB_ERR_CUDA, "cudaSetDevice failed");
+  const int64_t nlegs = 4 * n;
+  const int threads = 128;
+  const int64_t blocks = (nlegs + threads - 1) / threads;
+  qpb::fk_kernel<<<(unsigned)blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(h->d_params, q, feet_body, nlegs);
+  h->launches.fetch_add(1, std::memory_order_relaxed);
+  QPB_CUDA(cudaGetLastError());
+  return QPB_SUCCESS;
+}
+
+int qpb_host_alloc(void** ptr, size_t bytes) {
+  if (!ptr) return fail(QPB_ERR_INVALID_ARG, "qpb_host_alloc: null pointer");
+  QPB_CUDA(cudaHostAlloc(ptr, bytes, cudaHostAllocDefault));
+  return QPB_SUCCESS;
+}
+
+int qpb_host_free(void* ptr) {
+  if (!ptr) return QPB_SUCCESS;
+  QPB_CUDA(cudaFreeHost(ptr));
+  return QPB_SUCCESS;
+}
+
+int64_t qpb_launch_count(const qpb_handle* h) { return h ? h->launches.load(std::memory_order_relaxed) : 0; }
+
+}  // extern "C"

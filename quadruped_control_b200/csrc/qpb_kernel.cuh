@@ -1,0 +1,585 @@
+// qpb_kernel.cuh -- the balance-controller hot path as one sm_100a kernel family.
+//
+// One warp solves one robot's QP end to end (north_star): load the 512-B state record with one
+// coalesced 16-B load per lane, assemble the 12-variable QP of
+// BalanceController::control (reference balance_controller.cpp:98-330), solve it with a dual
+// active-set method, then apply the world->body epilogue (balance_controller.cpp:218-232) and
+// the Jacobian-transpose torque map (kinematics.cpp:162-188, 218-231), and store 256 B.
+//
+// Solver (DESIGN.md "Algorithm"): Goldfarb-Idnani dual active set in the WHITENED space
+// y = L^T f (Q = L L^T), where the Hessian is the identity.  State per warp:
+//   lanes 0..11  : f_i (world-frame force component), row i of the projector P = I - N~ (N~^T N~)^-1 N~^T
+//   lanes 16..27 : working-set slot k: constraint id, multiplier u_k, row k of N~* = (N~^T N~)^-1 N~^T
+// P and N~* rows live in the same register array M[12], so one DFMA stream updates both.  The
+// whitened normal n~ = L^-1 n is a 2-row combination of J0 = L^-T (friction-pyramid rows have two
+// non-zeros).  Working in the whitened space keeps the error at ~sqrt(cond(Q)) * eps instead of
+// cond(Q) * eps (cond(Q) ~ 7e5 for W = 1e-5 I), see DESIGN.md.
+//
+// No tensor cores: there is no dense contraction here (12x12 FP64 per problem).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/qpb200.h"
+
+namespace qpb {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int WARPS_PER_CTA = 4;
+constexpr int LSTRIDE = 14;  // row stride (doubles) of the Cholesky factor in shared memory
+
+// Per-warp shared memory.  L (setup) and J0 (main loop) share storage.
+struct __align__(16) WarpSmem {
+  double rec[64];            // staged input record
+  double LJ[12 * LSTRIDE];   // L rows during factorisation, then J0 rows (stride 12)
+  double bc[3][12];          // broadcast vectors
+};
+
+__device__ __forceinline__ double rcp_fast(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  return y;
+}
+
+__device__ __forceinline__ double rsqrt_fast(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+#pragma unroll
+  for (int it = 0; it < 2; it++) {
+    const double xy = x * y;
+    const double e = fma(-xy, y, 1.0);              // 1 - x y^2
+    y = fma(y * fma(0.375, e, 0.5), e, y);          // y (1 + e/2 + 3e^2/8)
+  }
+  return y;
+}
+
+__device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(FULL, v, src); }
+
+// read 12 doubles (16-B aligned) from shared memory as six 128-bit loads
+__device__ __forceinline__ void lds12(const double* p, double (&v)[12]) {
+  const double2* p2 = reinterpret_cast<const double2*>(p);
+#pragma unroll
+  for (int j = 0; j < 6; j++) {
+    const double2 t = p2[j];
+    v[2 * j] = t.x;
+    v[2 * j + 1] = t.y;
+  }
+}
+__device__ __forceinline__ void sts12(double* p, const double (&v)[12]) {
+  double2* p2 = reinterpret_cast<double2*>(p);
+#pragma unroll
+  for (int j = 0; j < 6; j++) p2[j] = make_double2(v[2 * j], v[2 * j + 1]);
+}
+
+// SO(3) log map exactly as Eigen::AngleAxisd(Matrix3d) does it (reference rigid3d.cpp:198-203 ->
+// drake RotationMatrix::ToAngleAxis -> Eigen quaternion-from-matrix + angle-axis-from-quaternion).
+__device__ __forceinline__ void angle_axis_total(const double (&R)[9], double (&out)[3]) {
+  double qw, qv[3];
+  double t = R[0] + R[4] + R[8];
+  if (t > 0.0) {
+    t = sqrt(t + 1.0);
+    qw = 0.5 * t;
+    t = 0.5 / t;
+    qv[0] = (R[7] - R[5]) * t;
+    qv[1] = (R[2] - R[6]) * t;
+    qv[2] = (R[3] - R[1]) * t;
+  } else if (R[0] >= R[4] && R[0] >= R[8]) {  // i = 0 (Eigen picks the first largest diagonal)
+    t = sqrt(R[0] - R[4] - R[8] + 1.0);
+    qv[0] = 0.5 * t;
+    t = 0.5 / t;
+    qw = (R[7] - R[5]) * t;
+    qv[1] = (R[3] + R[1]) * t;
+    qv[2] = (R[6] + R[2]) * t;
+  } else if (R[4] > R[0] && R[4] >= R[8]) {  // i = 1
+    t = sqrt(R[4] - R[8] - R[0] + 1.0);
+    qv[1] = 0.5 * t;
+    t = 0.5 / t;
+    qw = (R[2] - R[6]) * t;
+    qv[2] = (R[7] + R[5]) * t;
+    qv[0] = (R[1] + R[3]) * t;
+  } else {  // i = 2
+    t = sqrt(R[8] - R[0] - R[4] + 1.0);
+    qv[2] = 0.5 * t;
+    t = 0.5 / t;
+    qw = (R[3] - R[1]) * t;
+    qv[0] = (R[2] + R[6]) * t;
+    qv[1] = (R[5] + R[7]) * t;
+  }
+  double n = sqrt(qv[0] * qv[0] + qv[1] * qv[1] + qv[2] * qv[2]);
+  if (n != 0.0) {
+    const double angle = 2.0 * atan2(n, fabs(qw));
+    if (qw < 0.0) n = -n;
+    const double s = angle / n;
+    out[0] = qv[0] * s;
+    out[1] = qv[1] * s;
+    out[2] = qv[2] * s;
+  } else {
+    out[0] = out[1] = out[2] = 0.0;
+  }
+}
+
+// Where a record's 64 double slots come from.
+struct PackedIO {
+  const qpb_state_rec* __restrict__ in;
+  qpb_out_rec* __restrict__ out;
+};
+struct SplitIO {
+  const double *Rwb, *Rwb_d, *x, *xdot, *w, *x_d, *xdot_d, *w_d, *feet, *q;
+  const uint8_t* contact;
+  double *grf, *tau;
+  int32_t* status;
+};
+
+__device__ __forceinline__ double split_slot(const SplitIO& io, int64_t idx, int m) {
+  if (m < 9) return __ldg(io.Rwb + idx * 9 + m);
+  if (m < 18) return __ldg(io.Rwb_d + idx * 9 + (m - 9));
+  if (m < 21) return __ldg(io.x + idx * 3 + (m - 18));
+  if (m < 24) return __ldg(io.xdot + idx * 3 + (m - 21));
+  if (m < 27) return __ldg(io.w + idx * 3 + (m - 24));
+  if (m < 30) return __ldg(io.x_d + idx * 3 + (m - 27));
+  if (m < 33) return __ldg(io.xdot_d + idx * 3 + (m - 30));
+  if (m < 36) return __ldg(io.w_d + idx * 3 + (m - 33));
+  if (m < 48) return __ldg(io.feet + idx * 12 + (m - 36));
+  if (m < 60) return __ldg(io.q + idx * 12 + (m - 48));
+  return 0.0;
+}
+
+__device__ __forceinline__ double2 load_rec(const PackedIO& io, int64_t idx, int lane) {
+  return __ldg(reinterpret_cast<const double2*>(io.in) + idx * 32 + lane);
+}
+__device__ __forceinline__ double2 load_rec(const SplitIO& io, int64_t idx, int lane) {
+  double2 v;
+  v.x = split_slot(io, idx, 2 * lane);
+  v.y = split_slot(io, idx, 2 * lane + 1);
+  if (lane == 30) {
+    const uint32_t c = io.contact[idx * 4] | (io.contact[idx * 4 + 1] << 8) | (io.contact[idx * 4 + 2] << 16) |
+                       ((uint32_t)io.contact[idx * 4 + 3] << 24);
+    v.x = __hiloint2double(0, (int)c);  // little-endian: bytes 480..483 of the packed record
+  }
+  return v;
+}
+
+__device__ __forceinline__ void store_rec(const PackedIO& io, int64_t idx, int lane, double grf, double tau,
+                                          int status, int iters) {
+  double* o = reinterpret_cast<double*>(io.out + idx);
+  if (lane < 12) {
+    o[lane] = grf;
+    o[12 + lane] = tau;
+  } else if (lane < 16) {
+    // bytes 192..255: status, iters, zero padding -- the whole 256-B record is written
+    int4 v = make_int4(0, 0, 0, 0);
+    if (lane == 12) { v.x = status; v.y = iters; }
+    reinterpret_cast<int4*>(o + 24)[lane - 12] = v;
+  }
+}
+__device__ __forceinline__ void store_rec(const SplitIO& io, int64_t idx, int lane, double grf, double tau,
+                                          int status, int /*iters*/) {
+  if (lane < 12) {
+    io.grf[idx * 12 + lane] = grf;
+    if (io.tau) io.tau[idx * 12 + lane] = tau;
+  } else if (lane == 12 && io.status) {
+    io.status[idx] = status;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// The kernel.  Persistent: each warp strides over the batch.
+// ------------------------------------------------------------------------------------------------
+template <class IO>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+balance_qp_kernel(const qpb_params* __restrict__ gparams, IO io, int64_t n) {
+  __shared__ qpb_params P;
+  __shared__ WarpSmem wsm[WARPS_PER_CTA];
+
+  {  // stage the controller parameters once per CTA
+    const int nw = sizeof(qpb_params) / 8;
+    const double* src = reinterpret_cast<const double*>(gparams);
+    double* dst = reinterpret_cast<double*>(&P);
+    for (int i = threadIdx.x; i < nw; i += blockDim.x) dst[i] = src[i];
+  }
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  WarpSmem& ws = wsm[wib];
+  const int64_t gw = (int64_t)blockIdx.x * WARPS_PER_CTA + wib;
+  const int64_t nwarps = (int64_t)gridDim.x * WARPS_PER_CTA;
+
+  // lane roles
+  const bool isP = lane < 12;                 // variable / projector row
+  const bool isN = lane >= 16 && lane < 28;   // working-set slot
+  const int vi = isP ? lane : 0;
+  const int leg = vi / 3, ax = vi - 3 * leg;
+  const int axp1 = (ax + 1) % 3, axp2 = (ax + 2) % 3;
+  const double mu = P.mu;
+  // the two inequality rows this lane watches (DESIGN.md constraint table)
+  const int idA = 6 * leg + (ax < 2 ? ax : 4);
+  const int idB = 6 * leg + (ax < 2 ? 3 - ax : 5);
+  const double tolA = ax < 2 ? 1e-9 : 1e-9 * (1.0 + fabs(P.fzmin));
+  const double tolB = ax < 2 ? 1e-9 : 1e-9 * (1.0 + fabs(P.fzmax));
+  const int max_iter = P.max_iter;
+
+  for (int64_t idx = gw; idx < n; idx += nwarps) {
+    // ---- load + stage ---------------------------------------------------------------------------
+    const double2 v = load_rec(io, idx, lane);
+    bool ok = (lane >= 30) || (isfinite(v.x) && isfinite(v.y));
+    __syncwarp();
+    reinterpret_cast<double2*>(ws.rec)[lane] = v;
+    __syncwarp();
+    ok = __all_sync(FULL, ok);
+    const uint32_t cbytes = reinterpret_cast<const uint32_t*>(ws.rec + 60)[0];
+    const uint32_t smask = ((cbytes & 0xffu) ? 1u : 0u) | ((cbytes & 0xff00u) ? 2u : 0u) |
+                           ((cbytes & 0xff0000u) ? 4u : 0u) | ((cbytes & 0xff000000u) ? 8u : 0u);
+    const bool stance = isP && ((smask >> leg) & 1u);
+
+    int status = QPB_OK, iters = 0;
+    double x = 0.0;  // f_w component (lanes 0..11)
+
+    if (ok) {
+      const double* R = ws.rec;
+      // ---- PD target, balance_controller.cpp:126-139 (uniform across lanes) ---------------------
+      double b6[6];
+      {
+        double acc[3];
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+          acc[i] = P.kp_p[i] * (ws.rec[27 + i] - ws.rec[18 + i]) + P.kd_p[i] * (ws.rec[30 + i] - ws.rec[21 + i]);
+        acc[0] += P.kff[0] * ws.rec[30];
+        acc[1] += P.kff[1] * ws.rec[31];
+        acc[2] += P.kff[2] * P.mass * 9.81;
+        const double g[3] = { 0.0, 0.0, -9.81 };
+#pragma unroll
+        for (int i = 0; i < 3; i++) b6[i] = P.mass * (acc[i] + g[i]);  // :265
+        double Re[9], aa[3], wd[3];
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+          for (int j = 0; j < 3; j++)  // R_d * R^T, :133
+            Re[3 * i + j] = ws.rec[9 + 3 * i] * R[3 * j] + ws.rec[9 + 3 * i + 1] * R[3 * j + 1] +
+                            ws.rec[9 + 3 * i + 2] * R[3 * j + 2];
+        angle_axis_total(Re, aa);
+#pragma unroll
+        for (int i = 0; i < 3; i++) wd[i] = P.kp_w[i] * aa[i] + P.kd_w[i] * (ws.rec[33 + i] - ws.rec[24 + i]);
+        wd[0] += P.kff[3] * ws.rec[33];
+        wd[1] += P.kff[4] * ws.rec[34];
+        wd[1] += P.kff[5] * ws.rec[35];  // index 1 twice: reference quirk, :139
+        // Iw = R Ib R^T, :251
+        double RI[9], Iw[9];
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+          for (int j = 0; j < 3; j++)
+            RI[3 * i + j] = R[3 * i] * P.Ib[j] + R[3 * i + 1] * P.Ib[3 + j] + R[3 * i + 2] * P.Ib[6 + j];
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+          for (int j = 0; j < 3; j++)
+            Iw[3 * i + j] = RI[3 * i] * R[3 * j] + RI[3 * i + 1] * R[3 * j + 1] + RI[3 * i + 2] * R[3 * j + 2];
+        const double w0 = ws.rec[33], w1 = ws.rec[34], w2 = ws.rec[35];  // desired omega, :269
+        double Iwd[3], Iww[3];
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+          Iwd[i] = Iw[3 * i] * wd[0] + Iw[3 * i + 1] * wd[1] + Iw[3 * i + 2] * wd[2];
+          Iww[i] = Iw[3 * i] * w0 + Iw[3 * i + 1] * w1 + Iw[3 * i + 2] * w2;
+        }
+        b6[3] = Iwd[0] + (w1 * Iww[2] - w2 * Iww[1]);
+        b6[4] = Iwd[1] + (w2 * Iww[0] - w0 * Iww[2]);
+        b6[5] = Iwd[2] + (w0 * Iww[1] - w1 * Iww[0]);
+      }
+
+      // ---- lever arms r_leg = R p_leg (:245-248); lane i holds component ax of leg ----------------
+      const double ri = R[3 * ax] * ws.rec[36 + 3 * leg] + R[3 * ax + 1] * ws.rec[37 + 3 * leg] +
+                        R[3 * ax + 2] * ws.rec[38 + 3 * leg];
+      if (isP) ws.bc[0][lane] = ri;
+      __syncwarp();
+      double rr[12];
+      lds12(ws.bc[0], rr);
+      // column i of A = [e_ax ; column ax of skew(r_leg)], rigid3d.cpp:61-74
+      const double g_up = ws.bc[0][3 * leg + axp2];
+      const double g_dn = -ws.bc[0][3 * leg + axp1];
+      double ang[3];
+#pragma unroll
+      for (int k = 0; k < 3; k++) ang[k] = (k == axp1) ? g_up : ((k == axp2) ? g_dn : 0.0);
+      // v = S a_i
+      double sv[6];
+#pragma unroll
+      for (int m = 0; m < 6; m++)
+        sv[m] = P.S[6 * m + ax] + P.S[6 * m + 3] * ang[0] + P.S[6 * m + 4] * ang[1] + P.S[6 * m + 5] * ang[2];
+      // c_i = -2 a_i^T S b, :153
+      double ci = 0.0;
+#pragma unroll
+      for (int m = 0; m < 6; m++) ci = fma(sv[m], b6[m], ci);
+      ci = stance ? -2.0 * ci : 0.0;
+      // row i of Q = 2 (A^T S A + W), :152; swing variables are decoupled (identity row)
+      double Qr[12];
+#pragma unroll
+      for (int j = 0; j < 12; j++) {
+        const int lj = j / 3, aj = j % 3, aj1 = (aj + 1) % 3, aj2 = (aj + 2) % 3;
+        double val = sv[aj] + sv[3 + aj1] * rr[3 * lj + aj2] - sv[3 + aj2] * rr[3 * lj + aj1];
+        val = 2.0 * (val + P.W[12 * vi + j]);
+        const bool both = stance && ((smask >> lj) & 1u);
+        Qr[j] = both ? val : ((j == vi) ? 1.0 : 0.0);
+      }
+
+      // ---- Cholesky Q = L L^T, left-looking; row k of L is published to shared memory ------------
+      double rsd[12];
+#pragma unroll
+      for (int k = 0; k < 12; k++) {
+        double acc = Qr[k];
+#pragma unroll
+        for (int l = 0; l < k; l++) acc = fma(-Qr[l], ws.LJ[k * LSTRIDE + l], acc);
+        const double d = shfl_d(acc, k);
+        ok = ok && (d > 0.0) && (d < 1e300);
+        const double rs = rsqrt_fast(d);
+        rsd[k] = rs;
+        Qr[k] = (lane >= k) ? acc * rs : 0.0;  // Qr now holds row i of L
+        if (isP) ws.LJ[lane * LSTRIDE + k] = Qr[k];
+        __syncwarp();
+      }
+      // ---- T = L^-1 column by column per lane (lane j holds column j = row j of J0 = L^-T);
+      //      lane 12 carries the extra right-hand side -c, giving y0 = -L^-1 c --------------------
+      if (isP) ws.bc[1][lane] = ci;
+      __syncwarp();
+      double J0r[12];
+#pragma unroll
+      for (int m = 0; m < 12; m++) {
+        double t = (lane == 12) ? -ws.bc[1][m] : ((lane == m) ? 1.0 : 0.0);
+#pragma unroll
+        for (int l = 0; l < m; l++) t = fma(-ws.LJ[m * LSTRIDE + l], J0r[l], t);
+        J0r[m] = t * rsd[m];
+      }
+      __syncwarp();  // everyone is done reading L
+      if (lane == 12) sts12(ws.bc[0], J0r);
+      if (isP) sts12(ws.LJ + 12 * lane, J0r);  // J0 rows, stride 12
+      __syncwarp();
+      {
+        double y0[12];
+        lds12(ws.bc[0], y0);
+        double acc = 0.0;
+#pragma unroll
+        for (int m = 0; m < 12; m++) acc = fma(J0r[m], y0[m], acc);
+        x = isP ? acc : 0.0;  // unconstrained minimiser f0 = J0 y0
+      }
+
+      // ---- dual active set ---------------------------------------------------------------------
+      double M[12];
+#pragma unroll
+      for (int j = 0; j < 12; j++) M[j] = (isP && j == lane) ? 1.0 : 0.0;
+      double u = 0.0;
+      int cons = -1;
+      uint32_t active = 0;
+      int p = -1;
+      double up = 0.0;
+      const double INF = __longlong_as_double(0x7ff0000000000000LL);
+
+      if (ok) {
+        for (;;) {
+          // (1) slacks of the two rows this lane watches
+          const double xz = shfl_d(x, 3 * leg + 2);
+          double sA, sB;
+          if (ax < 2) {
+            sA = fma(mu, xz, -x);  // -f + mu fz >= 0
+            sB = fma(mu, xz, x);   //  f + mu fz >= 0
+          } else {
+            sA = x - P.fzmin;
+            sB = P.fzmax - x;
+          }
+          const bool vA = stance && !((active >> idA) & 1u) && (sA < -tolA);
+          const bool vB = stance && !((active >> idB) & 1u) && (sB < -tolB);
+          uint32_t key = 0;
+          if (vA && (!vB || sA <= sB)) key = ((uint32_t)__double2hiint(sA) & ~31u) | (uint32_t)idA;
+          else if (vB) key = ((uint32_t)__double2hiint(sB) & ~31u) | (uint32_t)idB;
+          const uint32_t kmax = __reduce_max_sync(FULL, key);
+          if (p < 0) {
+            if (kmax == 0) break;  // primal feasible: optimal
+            p = (int)(kmax & 31u);
+            up = 0.0;
+          }
+          if (iters >= max_iter) { status = QPB_MAX_ITER; break; }
+          iters++;
+          // decode the row: f_ia * ca + f_ib * cb >= bound
+          const int pl = p / 6, pt = p - 6 * pl;
+          const int ib = 3 * pl + 2;
+          const int ia = (pt < 4) ? 3 * pl + ((pt == 1 || pt == 2) ? 1 : 0) : ib;
+          const double ca = (pt == 0 || pt == 1 || pt == 5) ? -1.0 : 1.0;
+          const double cb = (pt < 4) ? mu : 0.0;
+          const bool pIsA = (pt == 0 || pt == 1 || pt == 4);
+          const double sp = shfl_d(pIsA ? sA : sB, (pt < 4) ? ia : ib);
+
+          // (2) whitened normal n~ = J0^T n
+          if (isP) ws.bc[0][lane] = ca * ws.LJ[12 * ia + lane] + cb * ws.LJ[12 * ib + lane];
+          __syncwarp();
+          double nt[12];
+          lds12(ws.bc[0], nt);
+          // (3) z~ = P n~ (lanes 0..11), r = N~* n~ (lanes 16..27)
+          double mv = 0.0, nn = 0.0;
+#pragma unroll
+          for (int j = 0; j < 12; j++) {
+            mv = fma(M[j], nt[j], mv);
+            nn = fma(nt[j], nt[j], nn);
+          }
+          if (isP) ws.bc[1][lane] = mv;
+          __syncwarp();
+          double zt[12];
+          lds12(ws.bc[1], zt);
+          double zeta = 0.0;
+#pragma unroll
+          for (int j = 0; j < 12; j++) zeta = fma(nt[j], zt[j], zeta);
+          const bool dep = !(zeta > 1e-13 * nn);  // n~ in the span of the working set
+          const double izeta = rcp_fast(zeta);
+          const double t2 = dep ? INF : fmax(0.0, -sp * izeta);
+          // (4) dual step bound: min u_k / r_k over r_k > 0 (exact argmin via two integer reductions)
+          const bool cand = isN && cons >= 0 && mv > 0.0;
+          const double ratio = cand ? fmax(u, 0.0) * rcp_fast(mv) : INF;
+          const uint32_t rhi = (uint32_t)__double2hiint(ratio);
+          const uint32_t mhi = __reduce_min_sync(FULL, rhi);
+          const bool c2 = cand && rhi == mhi;
+          const uint32_t rlo = c2 ? (uint32_t)__double2loint(ratio) : 0xffffffffu;
+          const uint32_t mlo = __reduce_min_sync(FULL, rlo);
+          const uint32_t wb = __ballot_sync(FULL, c2 && rlo == mlo);
+          const int kl = wb ? (__ffs(wb) - 1) : 0;
+          const double t1 = wb ? shfl_d(ratio, kl) : INF;
+          const double t = fmin(t1, t2);
+          if (!(t < INF)) { status = QPB_BAD_INPUT; break; }  // infeasible
+          // (5) step
+          if (!dep) {
+            double dx = 0.0;
+#pragma unroll
+            for (int m = 0; m < 12; m++) dx = fma(J0r[m], zt[m], dx);
+            if (isP) x = fma(t, dx, x);
+          }
+          if (isN && cons >= 0) u = fma(-t, mv, u);
+          up += t;
+          if (t2 <= t1) {
+            // (6a) full step: row p enters the working set
+            const uint32_t fb = __ballot_sync(FULL, isN && cons < 0);
+            const int ql = __ffs(fb) - 1;
+            double coef = (isP || (isN && cons >= 0)) ? mv * izeta : 0.0;
+            if (lane == ql) coef = -izeta;
+#pragma unroll
+            for (int j = 0; j < 12; j++) M[j] = fma(-coef, zt[j], M[j]);
+            if (lane == ql) { cons = p; u = up; }
+            active |= 1u << p;
+            p = -1;
+          } else {
+            // (6b) partial step: the blocking row (slot kl) leaves the working set
+            __syncwarp();
+            if (lane == kl) sts12(ws.bc[2], M);
+            __syncwarp();
+            double nu[12];
+            lds12(ws.bc[2], nu);
+            double delta = 0.0, gam = 0.0;
+#pragma unroll
+            for (int j = 0; j < 12; j++) {
+              delta = fma(nu[j], nu[j], delta);
+              gam = fma(M[j], nu[j], gam);
+            }
+            const double idelta = rcp_fast(delta);
+            const int cdrop = __shfl_sync(FULL, cons, kl);
+            double coef = 0.0;
+            if (isP) coef = -ws.bc[2][lane] * idelta;
+            else if (isN && cons >= 0) coef = gam * idelta;
+            if (lane == kl) coef = 1.0;
+#pragma unroll
+            for (int j = 0; j < 12; j++) M[j] = fma(-coef, nu[j], M[j]);
+            if (lane == kl) { cons = -1; u = 0.0; }
+            active &= ~(1u << cdrop);
+          }
+        }
+      } else {
+        status = QPB_BAD_INPUT;
+      }
+    } else {
+      status = QPB_BAD_INPUT;
+    }
+
+    // ---- epilogue: body-frame GRF (:218-232) and tau = J^T f (kinematics.cpp:162-188, 218-231) ---
+    const bool good = (status == QPB_OK);
+    const double fw = (good && stance) ? x : 0.0;
+    const double f0 = shfl_d(fw, 3 * leg), f1 = shfl_d(fw, 3 * leg + 1), f2 = shfl_d(fw, 3 * leg + 2);
+    double fb = -1.0 * (ws.rec[ax] * f0 + ws.rec[3 + ax] * f1 + ws.rec[6 + ax] * f2);  // -(R^T f)_ax
+    if (!(good && stance)) fb = 0.0;
+    // angle handled by this lane: t1, t2, t2+t3
+    const double qa = ws.rec[48 + 3 * leg + ax] + ((ax == 2) ? ws.rec[48 + 3 * leg + 1] : 0.0);
+    double sn, cs;
+    sincos(qa, &sn, &cs);
+    const double s1 = shfl_d(sn, 3 * leg), c1 = shfl_d(cs, 3 * leg);
+    const double s2 = shfl_d(sn, 3 * leg + 1), c2 = shfl_d(cs, 3 * leg + 1);
+    const double s23 = shfl_d(sn, 3 * leg + 2), c23 = shfl_d(cs, 3 * leg + 2);
+    const double fbx = shfl_d(fb, 3 * leg), fby = shfl_d(fb, 3 * leg + 1), fbz = shfl_d(fb, 3 * leg + 2);
+    const double l1 = P.link[3 * leg], l2 = P.link[3 * leg + 1], l3 = P.link[3 * leg + 2];
+    double Jx, Jy, Jz;  // column ax of the leg Jacobian
+    if (ax == 0) {
+      Jx = 0.0;
+      Jy = -l1 * s1 - l2 * c1 * c2 - l3 * c1 * c23;
+      Jz = l1 * c1 - l2 * s1 * c2 - l3 * s1 * c23;
+    } else if (ax == 1) {
+      const double h = l2 * s2 + l3 * s23;
+      Jx = l2 * c2 + l3 * c23;
+      Jy = h * s1;
+      Jz = -h * c1;
+    } else {
+      Jx = l3 * c23;
+      Jy = l3 * s1 * s23;
+      Jz = -l3 * s23 * c1;
+    }
+    double tau = Jx * fbx + Jy * fby + Jz * fbz;
+    if (P.clamp_tau) tau = fmin(fmax(tau, P.tau_min), P.tau_max);  // commander_node.cpp:526
+    if (!(good && stance)) tau = 0.0;
+    store_rec(io, idx, lane, fb, tau, status, iters);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stand-alone kinematics kernels (one thread per leg).
+// ------------------------------------------------------------------------------------------------
+__global__ void jt_kernel(const qpb_params* __restrict__ P, const double* __restrict__ q,
+                          const double* __restrict__ f, const uint8_t* __restrict__ contact,
+                          double* __restrict__ tau, int64_t nlegs) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nlegs) return;
+  const int leg = (int)(i & 3);
+  const double l1 = P->link[3 * leg], l2 = P->link[3 * leg + 1], l3 = P->link[3 * leg + 2];
+  const double t1 = q[3 * i], t2 = q[3 * i + 1], t3 = q[3 * i + 2];
+  double s1, c1, s2, c2, s23, c23;
+  sincos(t1, &s1, &c1);
+  sincos(t2, &s2, &c2);
+  sincos(t2 + t3, &s23, &c23);
+  const bool st = contact ? (contact[i] != 0) : true;
+  const double fx = f[3 * i], fy = f[3 * i + 1], fz = f[3 * i + 2];
+  const double h = l2 * s2 + l3 * s23;
+  double o0 = (-l1 * s1 - l2 * c1 * c2 - l3 * c1 * c23) * fy + (l1 * c1 - l2 * s1 * c2 - l3 * s1 * c23) * fz;
+  double o1 = (l2 * c2 + l3 * c23) * fx + h * s1 * fy - h * c1 * fz;
+  double o2 = l3 * c23 * fx + l3 * s1 * s23 * fy - l3 * s23 * c1 * fz;
+  if (P->clamp_tau) {
+    o0 = fmin(fmax(o0, P->tau_min), P->tau_max);
+    o1 = fmin(fmax(o1, P->tau_min), P->tau_max);
+    o2 = fmin(fmax(o2, P->tau_min), P->tau_max);
+  }
+  tau[3 * i] = st ? o0 : 0.0;
+  tau[3 * i + 1] = st ? o1 : 0.0;
+  tau[3 * i + 2] = st ? o2 : 0.0;
+}
+
+__global__ void fk_kernel(const qpb_params* __restrict__ P, const double* __restrict__ q,
+                          double* __restrict__ feet, int64_t nlegs) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nlegs) return;
+  const int leg = (int)(i & 3);
+  const double l1 = P->link[3 * leg], l2 = P->link[3 * leg + 1], l3 = P->link[3 * leg + 2];
+  const double t1 = q[3 * i], t2 = q[3 * i + 1], t3 = q[3 * i + 2];
+  double s1, c1, s2, c2, s23, c23;
+  sincos(t1, &s1, &c1);
+  sincos(t2, &s2, &c2);
+  sincos(t2 + t3, &s23, &c23);
+  feet[3 * i] = l2 * s2 + l3 * s23 + P->hip_offset[3 * leg];
+  feet[3 * i + 1] = l1 * c1 - l2 * s1 * c2 - l3 * s1 * c23 + P->hip_offset[3 * leg + 1];
+  feet[3 * i + 2] = l1 * s1 + l2 * c1 * c2 + l3 * c1 * c23 + P->hip_offset[3 * leg + 2];
+}
+
+}  // namespace qpb

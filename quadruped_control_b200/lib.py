@@ -1,0 +1,161 @@
+"""ctypes binding of libqpb200.so (include/qpb200.h).
+
+This is plumbing for the tests and the benchmark; the product boundary is the C ABI itself and the
+C++ shim in ``cpp/balance_controller.hpp``.  There is no CPU fallback: if the library is missing,
+or no CUDA device is present, every compute call raises.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+from .records import OUT_DTYPE, STATE_DTYPE, Params
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libqpb200.so")
+
+EXPORTS = (
+    "qpb_version",
+    "qpb_last_error",
+    "qpb_default_params",
+    "qpb_create",
+    "qpb_destroy",
+    "qpb_control_batch_packed",
+    "qpb_control_batch",
+    "qpb_control_batch_host",
+    "qpb_jt_batch",
+    "qpb_fk_batch",
+    "qpb_host_alloc",
+    "qpb_host_free",
+    "qpb_launch_count",
+)
+
+_lib = None
+
+
+class QpbError(RuntimeError):
+    pass
+
+
+def load():
+    """dlopen libqpb200.so and declare its prototypes.  Raises if the library is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise QpbError(f"{LIB_PATH} not built: run `python -c 'import __graft_entry__ as g; g.build()'` (no CPU fallback)")
+    L = ctypes.CDLL(LIB_PATH)
+    vp, i64, dp = ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p
+    L.qpb_version.restype = ctypes.c_int
+    L.qpb_last_error.restype = ctypes.c_char_p
+    L.qpb_default_params.argtypes = [ctypes.POINTER(Params)]
+    L.qpb_create.argtypes = [ctypes.POINTER(Params), ctypes.c_int, ctypes.POINTER(vp)]
+    L.qpb_destroy.argtypes = [vp]
+    L.qpb_control_batch_packed.argtypes = [vp, i64, vp, vp, vp]
+    L.qpb_control_batch.argtypes = [vp, i64] + [dp] * 14 + [vp]
+    L.qpb_control_batch_host.argtypes = [vp, i64, vp, vp]
+    L.qpb_jt_batch.argtypes = [vp, i64, dp, dp, dp, dp, vp]
+    L.qpb_fk_batch.argtypes = [vp, i64, dp, dp, vp]
+    L.qpb_host_alloc.argtypes = [ctypes.POINTER(vp), ctypes.c_size_t]
+    L.qpb_host_free.argtypes = [vp]
+    L.qpb_launch_count.argtypes = [vp]
+    L.qpb_launch_count.restype = i64
+    for name in EXPORTS:
+        getattr(L, name)
+    _lib = L
+    return L
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise QpbError(f"{what} failed ({rc}): {load().qpb_last_error().decode()}")
+
+
+def default_params():
+    p = Params()
+    _check(load().qpb_default_params(ctypes.byref(p)), "qpb_default_params")
+    return p
+
+
+def _ptr(t):
+    """Device/host address of a torch tensor, numpy array, or raw int."""
+    if t is None:
+        return None
+    if isinstance(t, int):
+        return t
+    if isinstance(t, np.ndarray):
+        return t.ctypes.data
+    return t.data_ptr()
+
+
+class PinnedBuffer:
+    """Pinned host memory from qpb_host_alloc, viewed as a numpy array of ``dtype``."""
+
+    def __init__(self, n, dtype):
+        self.dtype = np.dtype(dtype)
+        self.nbytes = int(n) * self.dtype.itemsize
+        p = ctypes.c_void_p()
+        _check(load().qpb_host_alloc(ctypes.byref(p), max(self.nbytes, 1)), "qpb_host_alloc")
+        self.ptr = p.value
+        buf = (ctypes.c_char * max(self.nbytes, 1)).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=self.dtype, count=int(n))
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            load().qpb_host_free(self.ptr)
+            self.ptr = None
+
+
+class BalanceSolver:
+    """Owns one ``qpb_handle`` (replaces the BalanceController + QuadrupedKinematics pair the
+    reference constructs at commander_node.cpp:337-338, 358) on one CUDA device."""
+
+    def __init__(self, params: Params = None, device: int = 0):
+        L = load()
+        self.params = params.copy() if params is not None else default_params()
+        h = ctypes.c_void_p()
+        _check(L.qpb_create(ctypes.byref(self.params), int(device), ctypes.byref(h)), "qpb_create")
+        self._h = h
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load().qpb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launches(self):
+        return int(load().qpb_launch_count(self._h))
+
+    # -- device-resident packed records (torch uint8 tensors or raw device pointers) ---------------
+    def control_packed(self, d_states, d_out, n, stream=None):
+        _check(load().qpb_control_batch_packed(self._h, int(n), _ptr(d_states), _ptr(d_out), stream), "qpb_control_batch_packed")
+
+    # -- device-resident argument-per-array form ----------------------------------------------------
+    def control_split(self, n, Rwb, Rwb_d, x, xdot, w, x_d, xdot_d, w_d, feet, contact, q, grf, tau=None, status=None,
+                      stream=None):
+        args = [_ptr(a) for a in (Rwb, Rwb_d, x, xdot, w, x_d, xdot_d, w_d, feet, contact, q, grf, tau, status)]
+        _check(load().qpb_control_batch(self._h, int(n), *args, stream), "qpb_control_batch")
+
+    # -- host buffers: the call a reference-side binding makes --------------------------------------
+    def control_host(self, states: np.ndarray, out: np.ndarray = None):
+        states = np.ascontiguousarray(states)
+        assert states.dtype == STATE_DTYPE
+        if out is None:
+            out = np.empty(states.shape[0], dtype=OUT_DTYPE)
+        assert out.dtype == OUT_DTYPE and out.shape[0] == states.shape[0] and out.flags.c_contiguous
+        _check(load().qpb_control_batch_host(self._h, states.shape[0], states.ctypes.data, out.ctypes.data), "qpb_control_batch_host")
+        return out
+
+    def jt(self, n, q, grf, contact, tau, stream=None):
+        _check(load().qpb_jt_batch(self._h, int(n), _ptr(q), _ptr(grf), _ptr(contact), _ptr(tau), stream), "qpb_jt_batch")
+
+    def fk(self, n, q, feet, stream=None):
+        _check(load().qpb_fk_batch(self._h, int(n), _ptr(q), _ptr(feet), stream), "qpb_fk_batch")
