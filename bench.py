@@ -1,0 +1,313 @@
+#!/usr/bin/env python
+"""Benchmark of the balance-controller hot path (BASELINE.json metric: balance QPs/sec, batched).
+
+  python bench.py --gpus N --steps K --warmup W            # our CUDA path (one process per GPU under torchrun)
+  python bench.py --impl reference --gpus N --steps K ...  # the CPU path (oracle port) on the host cores
+
+A "step" is one pass of the hot path over one batch of synthetic robot states: BASELINE config 2
+(65 536 states, 4 feet in contact, mu = 0.6, seed 20260102) per GPU; weak scaling: rank r owns records
+[r*65536, (r+1)*65536) of the same stream.  One JSON line is printed by rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from quadruped_control_b200 import ALGO_BYTES_PER_QP, OUT_DTYPE, STATE_DTYPE, default_params, states  # noqa: E402
+from quadruped_control_b200.sharding import reduce_report  # noqa: E402
+
+WORKLOADS = {
+    # name: (records per GPU, seed, masks, profile, description)
+    "cfg2": (65536, 20260102, "all4", "default", "cfg2: 65536 random CoM poses/twists per GPU, 4 feet in contact, mu=0.6"),
+    "cfg3": (1048576, 20260103, "mixed", "default", "cfg3: 1048576 mixed 2/3/4-foot contact states per GPU, mu=0.6"),
+    "cfg5": (1048576, 20260105, "mixed", "default", "cfg5: 8388608 mixed-contact states over 8 GPUs (1048576 per GPU), mu=0.6"),
+}
+MU = 0.6
+METRIC = "balance QPs/sec (batched)"
+UNIT = "QP/s"
+N_ROTATE = 8  # distinct device batches cycled through so a step never re-reads L2-resident inputs
+
+
+def measured_peak_hbm():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic_per_launch(workload):
+    """dram bytes per launch from the committed `ncu --set full` summary, if present."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_summary.json")) as f:
+            d = json.load(f)
+        return d.get(workload, {}).get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """nvidia-smi clock/throttle sampler running beside the timed region (B200_PROFILING.md recipe)."""
+
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index):
+        self.rows = []
+        self.proc = None
+        self.dev = device_index
+        self.t0 = None
+        self.marks = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.dev)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t_begin, t_end):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t_begin - 0.05 <= t <= t_end + 0.15] or [r for _, r in self.rows[-3:]]
+        sm, smax, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for r in rows:
+            parts = [p.strip() for p in r.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                smax.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_baseline(params, S, budget_s=12.0):
+    """The oracle port on the host cores over a bounded sample of the workload (test infrastructure
+    used only as the timed CPU baseline)."""
+    import oracle
+
+    cores = os.cpu_count() or 1
+    oracle.control_batch(params, S[:2048], cores)  # warm
+    t0 = time.perf_counter()
+    oracle.control_batch(params, S[:8192], cores)
+    rate = 8192 / (time.perf_counter() - t0)
+    n = int(min(len(S), max(8192, rate * budget_s / 3)))
+    best = 0.0
+    for _ in range(3):
+        t0 = time.perf_counter()
+        oracle.control_batch(params, S[:n], cores)
+        best = max(best, n / (time.perf_counter() - t0))
+    t0 = time.perf_counter()
+    m = min(n, 16384)
+    oracle.control_batch(params, S[:m], 1)
+    one = m / (time.perf_counter() - t0)
+    return {"value": best, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"first {n} records of the workload, best of 3, {cores} threads (pthread slices); 1 thread: {one:.0f} QP/s",
+            "one_thread": one}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path for this hot path.  qpOASES/Armadillo/Drake are not
+    installable here, so this is the oracle port, with all host threads, on our arm's config."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle
+
+    n, seed, masks, profile, desc = WORKLOADS[args.workload]
+    params = default_params(MU)
+    cores = os.cpu_count() or 1
+    S_full = states.generate_states(n, seed, profile=profile, masks=masks)
+    oracle.control_batch(params, S_full[:4096], cores)
+    t0 = time.perf_counter()
+    oracle.control_batch(params, S_full[:8192], cores)
+    rate = 8192 / (time.perf_counter() - t0)
+    total_steps = args.steps + args.warmup
+    per_step = int(min(n, max(4096, rate * 120.0 / total_steps)))  # whole run within ~2 minutes
+    S = np.ascontiguousarray(S_full[:per_step])
+    for _ in range(args.warmup):
+        oracle.control_batch(params, S, cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out = oracle.control_batch(params, S, cores)
+    dt = time.perf_counter() - t0
+    assert (out["status"] == 0).all()
+    value = per_step * args.steps / dt
+    sample = f"first {per_step} of {n} records per step, {cores} host threads"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": desc, "qps_per_step": per_step, "note": "CPU oracle port of the reference path (qpOASES + Armadillo not installable here); rank 0 only"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+
+    from quadruped_control_b200 import lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback for the product path)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+
+    n, seed, masks, profile, desc = WORKLOADS[args.workload]
+    params = default_params(MU)
+    solver = lib.BalanceSolver(params, device=local_rank)
+
+    # rank r owns records [r*n, (r+1)*n) of the stream; N_ROTATE further disjoint slices rotate through HBM
+    host_batches = [states.generate_states(n, seed + 1000 * k, lo=rank * n, profile=profile, masks=masks)
+                    for k in range(N_ROTATE if n <= 131072 else 2)]
+    n_rot = len(host_batches)
+    d_in = [torch.from_numpy(b.view(np.uint8).reshape(-1)).to(dev) for b in host_batches]
+    d_out = [torch.empty(n * OUT_DTYPE.itemsize, dtype=torch.uint8, device=dev) for _ in range(n_rot)]
+    stream = torch.cuda.current_stream()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput ------------------------------------------------------------
+    for i in range(args.warmup):
+        solver.control_packed(d_in[i % n_rot], d_out[i % n_rot], n, stream.cuda_stream)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    barrier()
+    launches0 = solver.launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_begin = time.perf_counter()
+    ev0.record(stream)
+    for i in range(args.steps):
+        solver.control_packed(d_in[i % n_rot], d_out[i % n_rot], n, stream.cuda_stream)
+    ev1.record(stream)
+    barrier()
+    t_end = time.perf_counter()
+    launches = solver.launches - launches0
+    elapsed_ms_local = ev0.elapsed_time(ev1)
+    clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
+
+    # correctness of what was just timed (status + checksum vs the oracle on a sample, rank 0)
+    last = d_out[(args.steps - 1) % n_rot].cpu().numpy().view(OUT_DTYPE)
+    failed = int((last["status"] != 0).sum())
+
+    elapsed_ms, (tot_launches, tot_failed) = reduce_report(elapsed_ms_local, [launches, failed], dist, dev)
+    total_qps = world * n * args.steps / (elapsed_ms * 1e-3)
+
+    # ---- end to end through the C ABI with HOST buffers (pinned), copies inside the timed region --
+    pin_in = [lib.PinnedBuffer(n, STATE_DTYPE) for _ in range(2)]
+    pin_out = lib.PinnedBuffer(n, OUT_DTYPE)
+    for k in range(2):
+        pin_in[k].array[:] = host_batches[k % n_rot]
+    e2e_steps = max(3, min(args.steps, 20))
+    for i in range(2):
+        solver.control_host(pin_in[i % 2].array, pin_out.array)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        solver.control_host(pin_in[i % 2].array, pin_out.array)
+    e2e_local = (time.perf_counter() - t0) * 1e3
+    barrier()
+    e2e_ms, _ = reduce_report(e2e_local, [0], dist, dev)
+    e2e_qps = world * n * e2e_steps / (e2e_ms * 1e-3)
+    e2e_checksum_ok = bool((pin_out.array["status"] == 0).all())
+
+    if rank == 0:
+        import oracle
+
+        sample = np.ascontiguousarray(host_batches[(args.steps - 1) % n_rot][:: max(1, n // 2048)])
+        ref = oracle.control_batch(params, sample, os.cpu_count() or 1)
+        got = np.ascontiguousarray(last[:: max(1, n // 2048)])
+        err = float((np.abs(got["grf_body"] - ref["grf_body"]).max(axis=1) / np.maximum(np.abs(ref["grf_body"]).max(axis=1), 1.0)).max())
+        cpu = cpu_baseline(params, host_batches[0]) if world == 1 or True else None
+        peak, peak_src = measured_peak_hbm()
+        kernel_ms = elapsed_ms / args.steps  # one kernel launch per step on the timed stream
+        achieved = ALGO_BYTES_PER_QP * n / (kernel_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": total_qps, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": desc, "qps_per_step_per_gpu": n, "global_batch": world * n, "parallelism": f"batch-sharded x{world}",
+                       "l2": f"{n_rot} distinct device batches rotate ({n_rot * n * 768 / 1e6:.0f} MB > 126 MB L2)" if n_rot * n * 768 > 126e6 else "inputs larger than L2",
+                       "iters_mean": float(last["iters"].mean()), "iters_max": int(last["iters"].max())},
+            "max_rel_grf_err_vs_oracle": err, "failed_qps": int(tot_failed),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": ncu_traffic_per_launch(args.workload), "peak_source": peak_src,
+                         "algorithmic_bytes_per_qp": ALGO_BYTES_PER_QP, "kernel": "balance_qp_kernel<PackedIO>",
+                         "kernel_ms": kernel_ms,
+                         "note": "the path is FP64-issue/latency bound, not DRAM bound (DESIGN.md); per-GPU figure"},
+            "cpu_baseline": cpu,
+            "e2e": {"value": e2e_qps, "unit": UNIT, "h2d_bytes_per_step": n * STATE_DTYPE.itemsize,
+                    "d2h_bytes_per_step": n * OUT_DTYPE.itemsize, "steps": e2e_steps, "ok": e2e_checksum_ok,
+                    "api": "qpb_control_batch_host (pinned host buffers, chunked H2D/kernel/D2H pipeline)"},
+            "gpu_launches": int(tot_launches),
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    for b in pin_in:
+        b.free()
+    pin_out.free()
+    solver.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=("ours", "reference"), default="ours")
+    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="cfg2")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -7,7 +7,7 @@
  *   BalanceController::BalanceController(...)               include/quadruped_controller/balance_controller.hpp:85-88
  *   ForceMap BalanceController::control(...) const          include/quadruped_controller/balance_controller.hpp:104-107
  *   TorqueMap QuadrupedKinematics::jacobianTransposeControl include/quadruped_controller/kinematics.hpp:106-107
- *   FootholdMap QuadrupedKinematics::forwardKinematics      include/quadruped_controller/kinematics.hpp:58-60
+ *   FootholdMap QuadrupedKinematics::forwardKinematics      include/quadruped_controller/kinematics.hpp:60
  * called once per control tick at src/commander_node.cpp:337-338 (ctor), 383-384 (FK) and 507-512.
  * quadruped_control_b200/cpp/balance_controller.hpp keeps those C++ signatures on top of this ABI.
  *
@@ -120,6 +120,12 @@ int qpb_jt_batch(qpb_handle* h, int64_t n, const double* q, const double* grf_bo
 
 /* forwardKinematics() (kinematics.cpp:81-103): q [n*12] -> feet_body [n*12]; device pointers. */
 int qpb_fk_batch(qpb_handle* h, int64_t n, const double* q, double* feet_body, void* stream);
+
+/* Host-buffer forms of the two kinematics calls (what a per-tick caller such as the C++ shim
+ * uses): copy in, launch, copy out, synchronous. */
+int qpb_jt_batch_host(qpb_handle* h, int64_t n, const double* q, const double* grf_body, const uint8_t* contact,
+                      double* tau);
+int qpb_fk_batch_host(qpb_handle* h, int64_t n, const double* q, double* feet_body);
 
 /* Pinned host memory for qpb_control_batch_host callers. */
 int qpb_host_alloc(void** ptr, size_t bytes);

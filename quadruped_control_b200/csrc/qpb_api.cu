@@ -277,6 +277,44 @@ int qpb_fk_batch(qpb_handle* h, int64_t n, const double* q, double* feet_body, v
   return QPB_SUCCESS;
 }
 
+int qpb_jt_batch_host(qpb_handle* h, int64_t n, const double* q, const double* grf_body, const uint8_t* contact,
+                      double* tau) {
+  if (!h || n < 0 || (n > 0 && (!q || !grf_body || !tau))) return fail(QPB_ERR_INVALID_ARG, "qpb_jt_batch_host: bad argument");
+  if (n == 0) return QPB_SUCCESS;
+  DeviceGuard guard(h->device);
+  if (!guard.ok) return fail(QPB_ERR_CUDA, "cudaSetDevice failed");
+  const size_t nb = (size_t)n * 12 * sizeof(double);
+  double* d = nullptr;  // [q | f | tau | contact]
+  QPB_CUDA(cudaMalloc(&d, 3 * nb + (size_t)n * 4));
+  uint8_t* dc = reinterpret_cast<uint8_t*>(d + 3 * (size_t)n * 12);
+  cudaError_t e = cudaMemcpy(d, q, nb, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(d + (size_t)n * 12, grf_body, nb, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && contact) e = cudaMemcpy(dc, contact, (size_t)n * 4, cudaMemcpyHostToDevice);
+  int rc = QPB_SUCCESS;
+  if (e == cudaSuccess) rc = qpb_jt_batch(h, n, d, d + (size_t)n * 12, contact ? dc : nullptr, d + 2 * (size_t)n * 12, nullptr);
+  if (e == cudaSuccess && rc == QPB_SUCCESS) e = cudaMemcpy(tau, d + 2 * (size_t)n * 12, nb, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  if (e != cudaSuccess) return fail(QPB_ERR_CUDA, std::string("qpb_jt_batch_host: ") + cudaGetErrorString(e));
+  return rc;
+}
+
+int qpb_fk_batch_host(qpb_handle* h, int64_t n, const double* q, double* feet_body) {
+  if (!h || n < 0 || (n > 0 && (!q || !feet_body))) return fail(QPB_ERR_INVALID_ARG, "qpb_fk_batch_host: bad argument");
+  if (n == 0) return QPB_SUCCESS;
+  DeviceGuard guard(h->device);
+  if (!guard.ok) return fail(QPB_ERR_CUDA, "cudaSetDevice failed");
+  const size_t nb = (size_t)n * 12 * sizeof(double);
+  double* d = nullptr;
+  QPB_CUDA(cudaMalloc(&d, 2 * nb));
+  cudaError_t e = cudaMemcpy(d, q, nb, cudaMemcpyHostToDevice);
+  int rc = QPB_SUCCESS;
+  if (e == cudaSuccess) rc = qpb_fk_batch(h, n, d, d + (size_t)n * 12, nullptr);
+  if (e == cudaSuccess && rc == QPB_SUCCESS) e = cudaMemcpy(feet_body, d + (size_t)n * 12, nb, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  if (e != cudaSuccess) return fail(QPB_ERR_CUDA, std::string("qpb_fk_batch_host: ") + cudaGetErrorString(e));
+  return rc;
+}
+
 int qpb_host_alloc(void** ptr, size_t bytes) {
   if (!ptr) return fail(QPB_ERR_INVALID_ARG, "qpb_host_alloc: null pointer");
   QPB_CUDA(cudaHostAlloc(ptr, bytes, cudaHostAllocDefault));

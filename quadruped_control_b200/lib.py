@@ -25,6 +25,8 @@ EXPORTS = (
     "qpb_control_batch_host",
     "qpb_jt_batch",
     "qpb_fk_batch",
+    "qpb_jt_batch_host",
+    "qpb_fk_batch_host",
     "qpb_host_alloc",
     "qpb_host_free",
     "qpb_launch_count",
@@ -56,6 +58,8 @@ def load():
     L.qpb_control_batch_host.argtypes = [vp, i64, vp, vp]
     L.qpb_jt_batch.argtypes = [vp, i64, dp, dp, dp, dp, vp]
     L.qpb_fk_batch.argtypes = [vp, i64, dp, dp, vp]
+    L.qpb_jt_batch_host.argtypes = [vp, i64, dp, dp, dp, dp]
+    L.qpb_fk_batch_host.argtypes = [vp, i64, dp, dp]
     L.qpb_host_alloc.argtypes = [ctypes.POINTER(vp), ctypes.c_size_t]
     L.qpb_host_free.argtypes = [vp]
     L.qpb_launch_count.argtypes = [vp]
@@ -156,6 +160,21 @@ class BalanceSolver:
 
     def jt(self, n, q, grf, contact, tau, stream=None):
         _check(load().qpb_jt_batch(self._h, int(n), _ptr(q), _ptr(grf), _ptr(contact), _ptr(tau), stream), "qpb_jt_batch")
+
+    def jt_host(self, q, grf, contact=None):
+        q = np.ascontiguousarray(q, dtype=np.float64).reshape(-1, 12)
+        grf = np.ascontiguousarray(grf, dtype=np.float64).reshape(-1, 12)
+        if contact is not None:
+            contact = np.ascontiguousarray(contact, dtype=np.uint8).reshape(-1, 4)
+        tau = np.empty_like(q)
+        _check(load().qpb_jt_batch_host(self._h, q.shape[0], _ptr(q), _ptr(grf), _ptr(contact), _ptr(tau)), "qpb_jt_batch_host")
+        return tau
+
+    def fk_host(self, q):
+        q = np.ascontiguousarray(q, dtype=np.float64).reshape(-1, 12)
+        feet = np.empty_like(q)
+        _check(load().qpb_fk_batch_host(self._h, q.shape[0], _ptr(q), _ptr(feet)), "qpb_fk_batch_host")
+        return feet
 
     def fk(self, n, q, feet, stream=None):
         _check(load().qpb_fk_batch(self._h, int(n), _ptr(q), _ptr(feet), stream), "qpb_fk_batch")
