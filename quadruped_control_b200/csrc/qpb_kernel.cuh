@@ -10,10 +10,17 @@
 // y = L^T f (Q = L L^T), where the Hessian is the identity.  State per warp:
 //   lanes 0..11  : f_i (world-frame force component), row i of the projector P = I - N~ (N~^T N~)^-1 N~^T
 //   lanes 16..27 : working-set slot k: constraint id, multiplier u_k, row k of N~* = (N~^T N~)^-1 N~^T
-// P and N~* rows live in the same register array M[12], so one DFMA stream updates both.  The
-// whitened normal n~ = L^-1 n is a 2-row combination of J0 = L^-T (friction-pyramid rows have two
-// non-zeros).  Working in the whitened space keeps the error at ~sqrt(cond(Q)) * eps instead of
-// cond(Q) * eps (cond(Q) ~ 7e5 for W = 1e-5 I), see DESIGN.md.
+// P and N~* rows live in the same register array M[12], so one DFMA stream updates both.  The 24
+// whitened normals n~_j = L^-1 n_j (2-row combinations of J0 = L^-T, friction-pyramid rows have two
+// non-zeros) are tabulated in shared memory once per QP.  Working in the whitened space keeps the
+// error at ~sqrt(cond(Q)) * eps instead of cond(Q) * eps (cond(Q) ~ 7e5 for W = 1e-5 I).
+//
+// Inequality rows: variable lane v (leg l = v/3, axis a = v%3) watches rows 2v ("A") and 2v+1 ("B"):
+//   a = 0: A: -fx + mu fz >= 0   B:  fx + mu fz >= 0      (rows 0 and 3 of Cf, balance_controller.cpp:278-282)
+//   a = 1: A: -fy + mu fz >= 0   B:  fy + mu fz >= 0      (rows 1 and 2)
+//   a = 2: A:  fz >= fzmin       B: -fz >= -fzmax         (row 4, both sides)
+// The reference's +-1e6 "far" sides (balance_controller.cpp:296-297) are provably inactive when
+// 2 mu fzmax <= 1e6, which qpb_create enforces.
 //
 // No tensor cores: there is no dense contraction here (12x12 FP64 per problem).
 #pragma once
@@ -27,13 +34,19 @@ namespace qpb {
 
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int WARPS_PER_CTA = 4;
-constexpr int LSTRIDE = 14;  // row stride (doubles) of the Cholesky factor in shared memory
+#ifndef QPB_MIN_CTAS_PER_SM
+#define QPB_MIN_CTAS_PER_SM 4
+#endif
+constexpr int LS = 14;  // row stride (doubles) of 12x12 matrices in shared memory: conflict-free 128-bit rows
 
-// Per-warp shared memory.  L (setup) and J0 (main loop) share storage.
+// Per-warp shared memory.
 struct __align__(16) WarpSmem {
-  double rec[64];            // staged input record
-  double LJ[12 * LSTRIDE];   // L rows during factorisation, then J0 rows (stride 12)
-  double bc[3][12];          // broadcast vectors
+  double rec[64];        // staged input record
+  double LJ[12 * LS];    // columns of L during factorisation, then rows of J0 = L^-T
+  double Nt[24 * 12];    // whitened normals n~_j
+  double nn[24];         // |n~_j|^2
+  double bz[32];         // broadcast buffer (one slot per lane)
+  double bv[16];         // second broadcast buffer
 };
 
 __device__ __forceinline__ double rcp_fast(double x) {
@@ -74,6 +87,17 @@ __device__ __forceinline__ void sts12(double* p, const double (&v)[12]) {
   double2* p2 = reinterpret_cast<double2*>(p);
 #pragma unroll
   for (int j = 0; j < 6; j++) p2[j] = make_double2(v[2 * j], v[2 * j + 1]);
+}
+// 12-term dot product with three independent accumulators (short dependency chains)
+__device__ __forceinline__ double dot12(const double (&a)[12], const double (&b)[12]) {
+  double s0 = a[0] * b[0], s1 = a[1] * b[1], s2 = a[2] * b[2];
+#pragma unroll
+  for (int j = 3; j < 12; j += 3) {
+    s0 = fma(a[j], b[j], s0);
+    s1 = fma(a[j + 1], b[j + 1], s1);
+    s2 = fma(a[j + 2], b[j + 2], s2);
+  }
+  return (s0 + s1) + s2;
 }
 
 // SO(3) log map exactly as Eigen::AngleAxisd(Matrix3d) does it (reference rigid3d.cpp:198-203 ->
@@ -191,7 +215,7 @@ __device__ __forceinline__ void store_rec(const SplitIO& io, int64_t idx, int la
 // The kernel.  Persistent: each warp strides over the batch.
 // ------------------------------------------------------------------------------------------------
 template <class IO>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, QPB_MIN_CTAS_PER_SM)
 balance_qp_kernel(const qpb_params* __restrict__ gparams, IO io, int64_t n) {
   __shared__ qpb_params P;
   __shared__ WarpSmem wsm[WARPS_PER_CTA];
@@ -215,14 +239,19 @@ balance_qp_kernel(const qpb_params* __restrict__ gparams, IO io, int64_t n) {
   const bool isN = lane >= 16 && lane < 28;   // working-set slot
   const int vi = isP ? lane : 0;
   const int leg = vi / 3, ax = vi - 3 * leg;
+  const int zl = 3 * leg + 2;  // lane of this leg's fz
   const int axp1 = (ax + 1) % 3, axp2 = (ax + 2) % 3;
   const double mu = P.mu;
-  // the two inequality rows this lane watches (DESIGN.md constraint table)
-  const int idA = 6 * leg + (ax < 2 ? ax : 4);
-  const int idB = 6 * leg + (ax < 2 ? 3 - ax : 5);
   const double tolA = ax < 2 ? 1e-9 : 1e-9 * (1.0 + fabs(P.fzmin));
   const double tolB = ax < 2 ? 1e-9 : 1e-9 * (1.0 + fabs(P.fzmax));
   const int max_iter = P.max_iter;
+  // the inequality row this lane tabulates (lanes 0..23): row j = 2*ov + side on variable ov
+  const int cj = lane < 24 ? lane : 0;
+  const int c_ov = cj >> 1, c_leg = c_ov / 3, c_ax = c_ov - 3 * c_leg;
+  const int c_ib = 3 * c_leg + 2;
+  const double c_ca = (((cj & 1) == 0) == (c_ax < 2)) ? -1.0 : 1.0;
+  const double c_cb = (c_ax < 2) ? mu : 0.0;
+  const double INF = __longlong_as_double(0x7ff0000000000000LL);
 
   for (int64_t idx = gw; idx < n; idx += nwarps) {
     // ---- load + stage ---------------------------------------------------------------------------
@@ -295,13 +324,13 @@ balance_qp_kernel(const qpb_params* __restrict__ gparams, IO io, int64_t n) {
       // ---- lever arms r_leg = R p_leg (:245-248); lane i holds component ax of leg ----------------
       const double ri = R[3 * ax] * ws.rec[36 + 3 * leg] + R[3 * ax + 1] * ws.rec[37 + 3 * leg] +
                         R[3 * ax + 2] * ws.rec[38 + 3 * leg];
-      if (isP) ws.bc[0][lane] = ri;
+      ws.bz[lane] = ri;
       __syncwarp();
       double rr[12];
-      lds12(ws.bc[0], rr);
+      lds12(ws.bz, rr);
       // column i of A = [e_ax ; column ax of skew(r_leg)], rigid3d.cpp:61-74
-      const double g_up = ws.bc[0][3 * leg + axp2];
-      const double g_dn = -ws.bc[0][3 * leg + axp1];
+      const double g_up = ws.bz[3 * leg + axp2];
+      const double g_dn = -ws.bz[3 * leg + axp1];
       double ang[3];
 #pragma unroll
       for (int k = 0; k < 3; k++) ang[k] = (k == axp1) ? g_up : ((k == axp2) ? g_dn : 0.0);
@@ -325,46 +354,57 @@ balance_qp_kernel(const qpb_params* __restrict__ gparams, IO io, int64_t n) {
         const bool both = stance && ((smask >> lj) & 1u);
         Qr[j] = both ? val : ((j == vi) ? 1.0 : 0.0);
       }
+      __syncwarp();  // bz is reused below
 
-      // ---- Cholesky Q = L L^T, left-looking; row k of L is published to shared memory ------------
+      // ---- Cholesky Q = L L^T, right-looking; column k of L is published to shared memory --------
       double rsd[12];
 #pragma unroll
       for (int k = 0; k < 12; k++) {
-        double acc = Qr[k];
-#pragma unroll
-        for (int l = 0; l < k; l++) acc = fma(-Qr[l], ws.LJ[k * LSTRIDE + l], acc);
-        const double d = shfl_d(acc, k);
+        const double d = shfl_d(Qr[k], k);
         ok = ok && (d > 0.0) && (d < 1e300);
         const double rs = rsqrt_fast(d);
         rsd[k] = rs;
-        Qr[k] = (lane >= k) ? acc * rs : 0.0;  // Qr now holds row i of L
-        if (isP) ws.LJ[lane * LSTRIDE + k] = Qr[k];
+        const double lik = (lane >= k) ? Qr[k] * rs : 0.0;  // L[lane][k]
+        if (isP) ws.LJ[k * LS + lane] = lik;
         __syncwarp();
+#pragma unroll
+        for (int j = k + 1; j < 12; j++) Qr[j] = fma(-lik, ws.LJ[k * LS + j], Qr[j]);
       }
-      // ---- T = L^-1 column by column per lane (lane j holds column j = row j of J0 = L^-T);
-      //      lane 12 carries the extra right-hand side -c, giving y0 = -L^-1 c --------------------
-      if (isP) ws.bc[1][lane] = ci;
+      // ---- T = L^-1 by columns (lane j holds column j of T = row j of J0 = L^-T); lane 12 carries
+      //      the extra right-hand side -c, giving y0 = -L^-1 c ------------------------------------
+      ws.bz[lane] = ci;
       __syncwarp();
       double J0r[12];
 #pragma unroll
-      for (int m = 0; m < 12; m++) {
-        double t = (lane == 12) ? -ws.bc[1][m] : ((lane == m) ? 1.0 : 0.0);
+      for (int m = 0; m < 12; m++) J0r[m] = (lane == 12) ? -ws.bz[m] : ((lane == m) ? 1.0 : 0.0);
 #pragma unroll
-        for (int l = 0; l < m; l++) t = fma(-ws.LJ[m * LSTRIDE + l], J0r[l], t);
-        J0r[m] = t * rsd[m];
+      for (int l = 0; l < 12; l++) {
+        J0r[l] *= rsd[l];
+#pragma unroll
+        for (int m = l + 1; m < 12; m++) J0r[m] = fma(-ws.LJ[l * LS + m], J0r[l], J0r[m]);
       }
-      __syncwarp();  // everyone is done reading L
-      if (lane == 12) sts12(ws.bc[0], J0r);
-      if (isP) sts12(ws.LJ + 12 * lane, J0r);  // J0 rows, stride 12
+      __syncwarp();  // everyone is done reading L and bz
+      if (lane == 12) sts12(ws.bv, J0r);
+      if (isP) sts12(ws.LJ + LS * lane, J0r);  // J0 rows
       __syncwarp();
       {
         double y0[12];
-        lds12(ws.bc[0], y0);
-        double acc = 0.0;
-#pragma unroll
-        for (int m = 0; m < 12; m++) acc = fma(J0r[m], y0[m], acc);
-        x = isP ? acc : 0.0;  // unconstrained minimiser f0 = J0 y0
+        lds12(ws.bv, y0);
+        x = dot12(J0r, y0);  // unconstrained minimiser f0 = J0 y0 (lanes 0..11)
       }
+      // ---- whitened normals n~_j = J0^T n_j and their squared norms (lanes 0..23) ----------------
+      {
+        double ra[12], rb[12];
+        lds12(ws.LJ + LS * c_ov, ra);
+        lds12(ws.LJ + LS * c_ib, rb);
+#pragma unroll
+        for (int m = 0; m < 12; m++) ra[m] = fma(c_cb, rb[m], c_ca * ra[m]);
+        if (lane < 24) {
+          sts12(ws.Nt + 12 * lane, ra);
+          ws.nn[lane] = dot12(ra, ra);
+        }
+      }
+      __syncwarp();
 
       // ---- dual active set ---------------------------------------------------------------------
       double M[12];
@@ -375,25 +415,26 @@ balance_qp_kernel(const qpb_params* __restrict__ gparams, IO io, int64_t n) {
       uint32_t active = 0;
       int p = -1;
       double up = 0.0;
-      const double INF = __longlong_as_double(0x7ff0000000000000LL);
 
       if (ok) {
         for (;;) {
+          __syncwarp();
           // (1) slacks of the two rows this lane watches
-          const double xz = shfl_d(x, 3 * leg + 2);
+          const double xz = shfl_d(x, zl);
           double sA, sB;
           if (ax < 2) {
-            sA = fma(mu, xz, -x);  // -f + mu fz >= 0
-            sB = fma(mu, xz, x);   //  f + mu fz >= 0
+            sA = fma(mu, xz, -x);
+            sB = fma(mu, xz, x);
           } else {
             sA = x - P.fzmin;
             sB = P.fzmax - x;
           }
-          const bool vA = stance && !((active >> idA) & 1u) && (sA < -tolA);
-          const bool vB = stance && !((active >> idB) & 1u) && (sB < -tolB);
-          uint32_t key = 0;
-          if (vA && (!vB || sA <= sB)) key = ((uint32_t)__double2hiint(sA) & ~31u) | (uint32_t)idA;
-          else if (vB) key = ((uint32_t)__double2hiint(sB) & ~31u) | (uint32_t)idB;
+          const uint32_t act2 = active >> ((2 * lane) & 31);
+          const bool vA = stance && !(act2 & 1u) && (sA < -tolA);
+          const bool vB = stance && !(act2 & 2u) && (sB < -tolB);
+          const bool pickB = vB && (!vA || sB < sA);
+          const double sv2 = pickB ? sB : sA;
+          const uint32_t key = (vA || vB) ? (((uint32_t)__double2hiint(sv2) & ~31u) | (uint32_t)(2 * lane + (pickB ? 1 : 0))) : 0u;
           const uint32_t kmax = __reduce_max_sync(FULL, key);
           if (p < 0) {
             if (kmax == 0) break;  // primal feasible: optimal
@@ -402,34 +443,28 @@ balance_qp_kernel(const qpb_params* __restrict__ gparams, IO io, int64_t n) {
           }
           if (iters >= max_iter) { status = QPB_MAX_ITER; break; }
           iters++;
-          // decode the row: f_ia * ca + f_ib * cb >= bound
-          const int pl = p / 6, pt = p - 6 * pl;
-          const int ib = 3 * pl + 2;
-          const int ia = (pt < 4) ? 3 * pl + ((pt == 1 || pt == 2) ? 1 : 0) : ib;
-          const double ca = (pt == 0 || pt == 1 || pt == 5) ? -1.0 : 1.0;
-          const double cb = (pt < 4) ? mu : 0.0;
-          const bool pIsA = (pt == 0 || pt == 1 || pt == 4);
-          const double sp = shfl_d(pIsA ? sA : sB, (pt < 4) ? ia : ib);
+          const double sp = shfl_d((p & 1) ? sB : sA, p >> 1);
 
-          // (2) whitened normal n~ = J0^T n
-          if (isP) ws.bc[0][lane] = ca * ws.LJ[12 * ia + lane] + cb * ws.LJ[12 * ib + lane];
-          __syncwarp();
-          double nt[12];
-          lds12(ws.bc[0], nt);
-          // (3) z~ = P n~ (lanes 0..11), r = N~* n~ (lanes 16..27)
-          double mv = 0.0, nn = 0.0;
-#pragma unroll
-          for (int j = 0; j < 12; j++) {
-            mv = fma(M[j], nt[j], mv);
-            nn = fma(nt[j], nt[j], nn);
+          // (2) z~ = P n~ (lanes 0..11), r = N~* n~ (lanes 16..27)
+          double mv;
+          {
+            double nt[12];
+            lds12(ws.Nt + 12 * p, nt);
+            mv = dot12(M, nt);
           }
-          if (isP) ws.bc[1][lane] = mv;
+          const double nn = ws.nn[p];
+          ws.bz[lane] = mv;
           __syncwarp();
           double zt[12];
-          lds12(ws.bc[1], zt);
-          double zeta = 0.0;
-#pragma unroll
-          for (int j = 0; j < 12; j++) zeta = fma(nt[j], zt[j], zeta);
+          lds12(ws.bz, zt);
+          // (3) lanes 0..11: dx = J0 z~ ; other lanes: zeta = n~^T z~ (exactly annihilates n~ in the update)
+          double acc;
+          {
+            double a[12];
+            lds12(isP ? (ws.LJ + LS * lane) : (ws.Nt + 12 * p), a);
+            acc = dot12(a, zt);
+          }
+          const double zeta = shfl_d(acc, 16);
           const bool dep = !(zeta > 1e-13 * nn);  // n~ in the span of the working set
           const double izeta = rcp_fast(zeta);
           const double t2 = dep ? INF : fmax(0.0, -sp * izeta);
@@ -447,12 +482,7 @@ balance_qp_kernel(const qpb_params* __restrict__ gparams, IO io, int64_t n) {
           const double t = fmin(t1, t2);
           if (!(t < INF)) { status = QPB_BAD_INPUT; break; }  // infeasible
           // (5) step
-          if (!dep) {
-            double dx = 0.0;
-#pragma unroll
-            for (int m = 0; m < 12; m++) dx = fma(J0r[m], zt[m], dx);
-            if (isP) x = fma(t, dx, x);
-          }
+          x = fma(dep ? 0.0 : t, acc, x);  // meaningful on lanes 0..11
           if (isN && cons >= 0) u = fma(-t, mv, u);
           up += t;
           if (t2 <= t1) {
@@ -468,27 +498,23 @@ balance_qp_kernel(const qpb_params* __restrict__ gparams, IO io, int64_t n) {
             p = -1;
           } else {
             // (6b) partial step: the blocking row (slot kl) leaves the working set
-            __syncwarp();
-            if (lane == kl) sts12(ws.bc[2], M);
+            if (lane == kl) sts12(ws.bv, M);
             __syncwarp();
             double nu[12];
-            lds12(ws.bc[2], nu);
-            double delta = 0.0, gam = 0.0;
-#pragma unroll
-            for (int j = 0; j < 12; j++) {
-              delta = fma(nu[j], nu[j], delta);
-              gam = fma(M[j], nu[j], gam);
-            }
+            lds12(ws.bv, nu);
+            const double gam = dot12(M, nu);
+            const double delta = shfl_d(gam, kl);  // |nu|^2
             const double idelta = rcp_fast(delta);
             const int cdrop = __shfl_sync(FULL, cons, kl);
             double coef = 0.0;
-            if (isP) coef = -ws.bc[2][lane] * idelta;
+            if (isP) coef = -ws.bv[lane] * idelta;
             else if (isN && cons >= 0) coef = gam * idelta;
             if (lane == kl) coef = 1.0;
 #pragma unroll
             for (int j = 0; j < 12; j++) M[j] = fma(-coef, nu[j], M[j]);
             if (lane == kl) { cons = -1; u = 0.0; }
             active &= ~(1u << cdrop);
+            __syncwarp();
           }
         }
       } else {

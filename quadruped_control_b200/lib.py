@@ -12,7 +12,7 @@ import numpy as np
 from .records import OUT_DTYPE, STATE_DTYPE, Params
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libqpb200.so")
+LIB_PATH = os.environ.get("QPB_LIB") or os.path.join(_HERE, "libqpb200.so")  # QPB_LIB: experiment builds
 
 EXPORTS = (
     "qpb_version",
