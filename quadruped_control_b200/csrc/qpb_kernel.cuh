@@ -242,8 +242,13 @@ balance_qp_kernel(const qpb_params* __restrict__ gparams, IO io, int64_t n) {
   const int zl = 3 * leg + 2;  // lane of this leg's fz
   const int axp1 = (ax + 1) % 3, axp2 = (ax + 2) % 3;
   const double mu = P.mu;
-  const double tolA = ax < 2 ? 1e-9 : 1e-9 * (1.0 + fabs(P.fzmin));
-  const double tolB = ax < 2 ? 1e-9 : 1e-9 * (1.0 + fabs(P.fzmax));
+  // slack_A = kz fz + kA f - bA,  slack_B = kz fz - kA f - bB  (rows A/B of the table above)
+  const double kz = ax < 2 ? mu : 0.0;
+  const double kA = ax < 2 ? -1.0 : 1.0;
+  const double bA = ax < 2 ? 0.0 : P.fzmin;
+  const double bB = ax < 2 ? 0.0 : -P.fzmax;
+  const double ntolA = ax < 2 ? -1e-9 : -1e-9 * (1.0 + fabs(P.fzmin));
+  const double ntolB = ax < 2 ? -1e-9 : -1e-9 * (1.0 + fabs(P.fzmax));
   const int max_iter = P.max_iter;
   // the inequality row this lane tabulates (lanes 0..23): row j = 2*ov + side on variable ov
   const int cj = lane < 24 ? lane : 0;
@@ -419,19 +424,14 @@ balance_qp_kernel(const qpb_params* __restrict__ gparams, IO io, int64_t n) {
       if (ok) {
         for (;;) {
           __syncwarp();
-          // (1) slacks of the two rows this lane watches
+          // (1) slacks of the two rows this lane watches:  kz fz +- kA f - b
           const double xz = shfl_d(x, zl);
-          double sA, sB;
-          if (ax < 2) {
-            sA = fma(mu, xz, -x);
-            sB = fma(mu, xz, x);
-          } else {
-            sA = x - P.fzmin;
-            sB = P.fzmax - x;
-          }
+          const double base = kz * xz;
+          const double sA = fma(kA, x, base - bA);
+          const double sB = fma(-kA, x, base - bB);
           const uint32_t act2 = active >> ((2 * lane) & 31);
-          const bool vA = stance && !(act2 & 1u) && (sA < -tolA);
-          const bool vB = stance && !(act2 & 2u) && (sB < -tolB);
+          const bool vA = stance && !(act2 & 1u) && (sA < ntolA);
+          const bool vB = stance && !(act2 & 2u) && (sB < ntolB);
           const bool pickB = vB && (!vA || sB < sA);
           const double sv2 = pickB ? sB : sA;
           const uint32_t key = (vA || vB) ? (((uint32_t)__double2hiint(sv2) & ~31u) | (uint32_t)(2 * lane + (pickB ? 1 : 0))) : 0u;
@@ -467,55 +467,52 @@ balance_qp_kernel(const qpb_params* __restrict__ gparams, IO io, int64_t n) {
           const double zeta = shfl_d(acc, 16);
           const bool dep = !(zeta > 1e-13 * nn);  // n~ in the span of the working set
           const double izeta = rcp_fast(zeta);
-          const double t2 = dep ? INF : fmax(0.0, -sp * izeta);
+          const double t2 = -sp * izeta;  // > 0: row p is violated and zeta > 0
           // (4) dual step bound: min u_k / r_k over r_k > 0 (exact argmin via two integer reductions)
           const bool cand = isN && cons >= 0 && mv > 0.0;
-          const double ratio = cand ? fmax(u, 0.0) * rcp_fast(mv) : INF;
-          const uint32_t rhi = (uint32_t)__double2hiint(ratio);
+          const double uu = (__double2hiint(u) < 0) ? 0.0 : u;  // rounding can leave -1e-17
+          const double ratio = uu * rcp_fast(mv);
+          const uint32_t rhi = cand ? (uint32_t)__double2hiint(ratio) : 0x7ff00000u;
           const uint32_t mhi = __reduce_min_sync(FULL, rhi);
           const bool c2 = cand && rhi == mhi;
           const uint32_t rlo = c2 ? (uint32_t)__double2loint(ratio) : 0xffffffffu;
           const uint32_t mlo = __reduce_min_sync(FULL, rlo);
           const uint32_t wb = __ballot_sync(FULL, c2 && rlo == mlo);
-          const int kl = wb ? (__ffs(wb) - 1) : 0;
-          const double t1 = wb ? shfl_d(ratio, kl) : INF;
-          const double t = fmin(t1, t2);
-          if (!(t < INF)) { status = QPB_BAD_INPUT; break; }  // infeasible
+          const bool has1 = wb != 0u;
+          const int kl = __ffs(wb) - 1;  // -1: no blocking row
+          const double t1 = shfl_d(ratio, kl & 31);
+          if (dep && !has1) { status = QPB_BAD_INPUT; break; }  // infeasible
+          const bool full = !dep && (!has1 || t2 <= t1);
+          const double t = full ? t2 : t1;
           // (5) step
           x = fma(dep ? 0.0 : t, acc, x);  // meaningful on lanes 0..11
           if (isN && cons >= 0) u = fma(-t, mv, u);
           up += t;
-          if (t2 <= t1) {
-            // (6a) full step: row p enters the working set
+          double coef;
+          if (full) {
+            // (6a) full step: row p enters the working set;  M -= (M n~) z~^T / zeta
             const uint32_t fb = __ballot_sync(FULL, isN && cons < 0);
             const int ql = __ffs(fb) - 1;
-            double coef = (isP || (isN && cons >= 0)) ? mv * izeta : 0.0;
-            if (lane == ql) coef = -izeta;
-#pragma unroll
-            for (int j = 0; j < 12; j++) M[j] = fma(-coef, zt[j], M[j]);
-            if (lane == ql) { cons = p; u = up; }
+            coef = (isP || (isN && cons >= 0)) ? mv * izeta : 0.0;
+            if (lane == ql) { coef = -izeta; cons = p; u = up; }
             active |= 1u << p;
             p = -1;
           } else {
-            // (6b) partial step: the blocking row (slot kl) leaves the working set
+            // (6b) partial step: the blocking row (slot kl) leaves;  M += / -= (..) nu^T / |nu|^2
             if (lane == kl) sts12(ws.bv, M);
             __syncwarp();
-            double nu[12];
-            lds12(ws.bv, nu);
-            const double gam = dot12(M, nu);
-            const double delta = shfl_d(gam, kl);  // |nu|^2
-            const double idelta = rcp_fast(delta);
+            lds12(ws.bv, zt);  // zt now holds nu = row kl of N~*
+            const double gam = dot12(M, zt);
+            const double idelta = rcp_fast(shfl_d(gam, kl));  // 1 / |nu|^2
             const int cdrop = __shfl_sync(FULL, cons, kl);
-            double coef = 0.0;
+            coef = 0.0;
             if (isP) coef = -ws.bv[lane] * idelta;
             else if (isN && cons >= 0) coef = gam * idelta;
-            if (lane == kl) coef = 1.0;
-#pragma unroll
-            for (int j = 0; j < 12; j++) M[j] = fma(-coef, nu[j], M[j]);
-            if (lane == kl) { cons = -1; u = 0.0; }
+            if (lane == kl) { coef = 1.0; cons = -1; u = 0.0; }
             active &= ~(1u << cdrop);
-            __syncwarp();
           }
+#pragma unroll
+          for (int j = 0; j < 12; j++) M[j] = fma(-coef, zt[j], M[j]);
         }
       } else {
         status = QPB_BAD_INPUT;
