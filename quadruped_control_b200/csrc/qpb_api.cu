@@ -52,6 +52,7 @@ bool is_sympd(const double* A, int n) {
 
 constexpr int kHostSlots = 3;          // streams / staging slots of the host-buffer pipeline
 constexpr int64_t kHostChunk = 16384;  // records per pipeline stage (8 MiB in, 4 MiB out)
+constexpr uint32_t kTicketSlots = 256;  // launches that may be in flight on different streams at once
 
 }  // namespace
 
@@ -65,6 +66,9 @@ struct qpb_handle {
   qpb_state_rec* d_in[kHostSlots] = { nullptr, nullptr, nullptr };
   qpb_out_rec* d_out[kHostSlots] = { nullptr, nullptr, nullptr };
   std::atomic<int64_t> launches{ 0 };
+  // ring of work-ticket counters, one per in-flight launch of the balance kernel
+  unsigned long long* d_tickets = nullptr;
+  std::atomic<uint32_t> ticket_slot{ 0 };
 };
 
 namespace {
@@ -87,7 +91,9 @@ int launch_balance(qpb_handle* h, const IO& io, int64_t n, int ctas_per_sm, cuda
   const int64_t want = (n + qpb::WARPS_PER_CTA - 1) / qpb::WARPS_PER_CTA;
   const int64_t cap = (int64_t)h->num_sms * ctas_per_sm;
   const int grid = (int)(want < cap ? want : cap);
-  qpb::balance_qp_kernel<IO><<<grid, qpb::WARPS_PER_CTA * 32, 0, stream>>>(h->d_params, io, n);
+  unsigned long long* ticket = h->d_tickets + (h->ticket_slot.fetch_add(1, std::memory_order_relaxed) % kTicketSlots);
+  QPB_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned long long), stream));
+  qpb::balance_qp_kernel<IO><<<grid, qpb::WARPS_PER_CTA * 32, 0, stream>>>(h->d_params, io, n, ticket);
   h->launches.fetch_add(1, std::memory_order_relaxed);
   QPB_CUDA(cudaGetLastError());
   return QPB_SUCCESS;
@@ -166,6 +172,7 @@ int qpb_create(const qpb_params* params, int device, qpb_handle** out) {
   cudaError_t e = cudaGetDeviceProperties(&prop, device);
   if (e == cudaSuccess) e = cudaMalloc(&h->d_params, sizeof(qpb_params));
   if (e == cudaSuccess) e = cudaMemcpy(h->d_params, params, sizeof(qpb_params), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMalloc(&h->d_tickets, kTicketSlots * sizeof(unsigned long long));
   if (e == cudaSuccess)
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->ctas_per_sm_packed, qpb::balance_qp_kernel<qpb::PackedIO>,
                                                       qpb::WARPS_PER_CTA * 32, 0);
@@ -175,6 +182,7 @@ int qpb_create(const qpb_params* params, int device, qpb_handle** out) {
   if (e != cudaSuccess || h->ctas_per_sm_packed < 1 || h->ctas_per_sm_split < 1) {
     const std::string msg = std::string("qpb_create: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "kernel does not fit");
     if (h->d_params) cudaFree(h->d_params);
+    if (h->d_tickets) cudaFree(h->d_tickets);
     delete h;
     return fail(QPB_ERR_CUDA, msg);
   }
@@ -192,6 +200,7 @@ int qpb_destroy(qpb_handle* h) {
     if (h->d_out[s]) cudaFree(h->d_out[s]);
   }
   if (h->d_params) cudaFree(h->d_params);
+  if (h->d_tickets) cudaFree(h->d_tickets);
   delete h;
   return QPB_SUCCESS;
 }

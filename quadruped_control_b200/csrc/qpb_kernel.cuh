@@ -212,11 +212,11 @@ __device__ __forceinline__ void store_rec(const SplitIO& io, int64_t idx, int la
 }
 
 // ------------------------------------------------------------------------------------------------
-// The kernel.  Persistent: each warp strides over the batch.
+// The kernel.  Persistent: each warp claims records until the batch is exhausted.
 // ------------------------------------------------------------------------------------------------
 template <class IO>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, QPB_MIN_CTAS_PER_SM)
-balance_qp_kernel(const qpb_params* __restrict__ gparams, IO io, int64_t n) {
+balance_qp_kernel(const qpb_params* __restrict__ gparams, IO io, int64_t n, unsigned long long* __restrict__ ticket) {
   __shared__ qpb_params P;
   __shared__ WarpSmem wsm[WARPS_PER_CTA];
 
@@ -258,7 +258,13 @@ balance_qp_kernel(const qpb_params* __restrict__ gparams, IO io, int64_t n) {
   const double c_cb = (c_ax < 2) ? mu : 0.0;
   const double INF = __longlong_as_double(0x7ff0000000000000LL);
 
-  for (int64_t idx = gw; idx < n; idx += nwarps) {
+  // Work distribution: warp w starts on record w; further records are claimed from a global ticket
+  // counter (iteration counts vary a lot between QPs, so a static stride leaves a long tail).  The
+  // ticket for the next record is requested at the start of the current one, hiding the atomic.
+  int64_t idx = gw;
+  while (idx < n) {
+    unsigned long long next_ticket = 0;
+    if (lane == 0) next_ticket = atomicAdd(ticket, 1ULL);
     // ---- load + stage ---------------------------------------------------------------------------
     const double2 v = load_rec(io, idx, lane);
     bool ok = (lane >= 30) || (isfinite(v.x) && isfinite(v.y));
@@ -555,6 +561,7 @@ balance_qp_kernel(const qpb_params* __restrict__ gparams, IO io, int64_t n) {
     if (P.clamp_tau) tau = fmin(fmax(tau, P.tau_min), P.tau_max);  // commander_node.cpp:526
     if (!(good && stance)) tau = 0.0;
     store_rec(io, idx, lane, fb, tau, status, iters);
+    idx = nwarps + (int64_t)__shfl_sync(FULL, next_ticket, 0);
   }
 }
 
