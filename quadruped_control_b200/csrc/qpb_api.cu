@@ -5,6 +5,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -50,9 +51,9 @@ bool is_sympd(const double* A, int n) {
   return true;
 }
 
-constexpr int kHostSlots = 3;          // streams / staging slots of the host-buffer pipeline
-constexpr int64_t kHostChunk = 16384;  // records per pipeline stage (8 MiB in, 4 MiB out)
-constexpr uint32_t kTicketSlots = 256;  // launches that may be in flight on different streams at once
+constexpr int kHostSlots = 6;          // streams / staging slots of the host-buffer pipeline
+constexpr int64_t kHostChunkMax = 16384;  // capacity of a pipeline stage (8 MiB in, 4 MiB out)
+constexpr uint32_t kTicketSlots = 4096;  // ring of work counters; a launch re-zeroes the slot half a ring ahead
 
 }  // namespace
 
@@ -62,13 +63,14 @@ struct qpb_handle {
   int ctas_per_sm_packed = 0, ctas_per_sm_split = 0;
   qpb_params params;
   qpb_params* d_params = nullptr;
-  cudaStream_t streams[kHostSlots] = { nullptr, nullptr, nullptr };
-  qpb_state_rec* d_in[kHostSlots] = { nullptr, nullptr, nullptr };
-  qpb_out_rec* d_out[kHostSlots] = { nullptr, nullptr, nullptr };
+  cudaStream_t streams[kHostSlots] = {};
+  qpb_state_rec* d_in[kHostSlots] = {};
+  qpb_out_rec* d_out[kHostSlots] = {};
   std::atomic<int64_t> launches{ 0 };
   // ring of work-ticket counters, one per in-flight launch of the balance kernel
   unsigned long long* d_tickets = nullptr;
   std::atomic<uint32_t> ticket_slot{ 0 };
+  int64_t host_chunk = 8192;  // records per H2D/kernel/D2H pipeline stage (QPB_HOST_CHUNK overrides)
 };
 
 namespace {
@@ -91,9 +93,11 @@ int launch_balance(qpb_handle* h, const IO& io, int64_t n, int ctas_per_sm, cuda
   const int64_t want = (n + qpb::WARPS_PER_CTA - 1) / qpb::WARPS_PER_CTA;
   const int64_t cap = (int64_t)h->num_sms * ctas_per_sm;
   const int grid = (int)(want < cap ? want : cap);
-  unsigned long long* ticket = h->d_tickets + (h->ticket_slot.fetch_add(1, std::memory_order_relaxed) % kTicketSlots);
-  QPB_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned long long), stream));
-  qpb::balance_qp_kernel<IO><<<grid, qpb::WARPS_PER_CTA * 32, 0, stream>>>(h->d_params, io, n, ticket);
+  // Launch i draws tickets from slot i % R and zeroes slot (i + R/2) % R for a launch far in the future, so no
+  // memset sits on the critical path; this is safe while fewer than R/2 = 2048 launches of one handle are in flight.
+  const uint32_t slot = h->ticket_slot.fetch_add(1, std::memory_order_relaxed) % kTicketSlots;
+  qpb::balance_qp_kernel<IO><<<grid, qpb::WARPS_PER_CTA * 32, 0, stream>>>(
+      h->d_params, io, n, h->d_tickets + slot, h->d_tickets + (slot + kTicketSlots / 2) % kTicketSlots);
   h->launches.fetch_add(1, std::memory_order_relaxed);
   QPB_CUDA(cudaGetLastError());
   return QPB_SUCCESS;
@@ -173,6 +177,7 @@ int qpb_create(const qpb_params* params, int device, qpb_handle** out) {
   if (e == cudaSuccess) e = cudaMalloc(&h->d_params, sizeof(qpb_params));
   if (e == cudaSuccess) e = cudaMemcpy(h->d_params, params, sizeof(qpb_params), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMalloc(&h->d_tickets, kTicketSlots * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMemset(h->d_tickets, 0, kTicketSlots * sizeof(unsigned long long));
   if (e == cudaSuccess)
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->ctas_per_sm_packed, qpb::balance_qp_kernel<qpb::PackedIO>,
                                                       qpb::WARPS_PER_CTA * 32, 0);
@@ -187,6 +192,10 @@ int qpb_create(const qpb_params* params, int device, qpb_handle** out) {
     return fail(QPB_ERR_CUDA, msg);
   }
   h->num_sms = prop.multiProcessorCount;
+  if (const char* env = std::getenv("QPB_HOST_CHUNK")) {
+    const long long v = std::atoll(env);
+    if (v >= 256 && v <= kHostChunkMax) h->host_chunk = v;
+  }
   *out = h;
   return QPB_SUCCESS;
 }
@@ -239,12 +248,17 @@ int qpb_control_batch_host(qpb_handle* h, int64_t n, const qpb_state_rec* h_stat
   if (!guard.ok) return fail(QPB_ERR_CUDA, "cudaSetDevice failed");
   for (int s = 0; s < kHostSlots; s++) {  // lazily create the pipeline
     if (!h->streams[s]) QPB_CUDA(cudaStreamCreateWithFlags(&h->streams[s], cudaStreamNonBlocking));
-    if (!h->d_in[s]) QPB_CUDA(cudaMalloc(&h->d_in[s], kHostChunk * sizeof(qpb_state_rec)));
-    if (!h->d_out[s]) QPB_CUDA(cudaMalloc(&h->d_out[s], kHostChunk * sizeof(qpb_out_rec)));
+    if (!h->d_in[s]) QPB_CUDA(cudaMalloc(&h->d_in[s], kHostChunkMax * sizeof(qpb_state_rec)));
+    if (!h->d_out[s]) QPB_CUDA(cudaMalloc(&h->d_out[s], kHostChunkMax * sizeof(qpb_out_rec)));
   }
   int slot = 0;
-  for (int64_t lo = 0; lo < n; lo += kHostChunk, slot = (slot + 1) % kHostSlots) {
-    const int64_t m = (n - lo < kHostChunk) ? (n - lo) : kHostChunk;
+  // Stage sizes halve towards the end of the batch so the last kernel + download (the part of the pipeline that
+  // cannot overlap an upload) is short.
+  const int64_t chunk = h->host_chunk, min_chunk = 1024;
+  for (int64_t lo = 0, m = 0; lo < n; lo += m, slot = (slot + 1) % kHostSlots) {
+    const int64_t left = n - lo;
+    m = left / 2 > chunk ? chunk : (left / 2 > min_chunk ? left / 2 : (left < min_chunk * 2 ? left : min_chunk));
+    if (m > chunk) m = chunk;
     cudaStream_t st = h->streams[slot];
     QPB_CUDA(cudaMemcpyAsync(h->d_in[slot], h_states + lo, m * sizeof(qpb_state_rec), cudaMemcpyHostToDevice, st));
     qpb::PackedIO io{ h->d_in[slot], h->d_out[slot] };

@@ -43,32 +43,51 @@ constexpr int LS = 14;  // row stride (doubles) of 12x12 matrices in shared memo
 struct __align__(16) WarpSmem {
   double rec[64];        // staged input record
   double LJ[12 * LS];    // columns of L during factorisation, then rows of J0 = L^-T
-  double Nt[24 * 12];    // whitened normals n~_j
-  double nn[24];         // |n~_j|^2
+  double Nt[24 * LS];    // whitened normals n~_j (12 entries) + |n~_j|^2 in slot 12
   double bz[32];         // broadcast buffer (one slot per lane)
   double bv[16];         // second broadcast buffer
 };
 
+// MUFU seeds carry >= 20 good bits (e <= 2^-20); one third-order step leaves e^3 <= 2^-60.
 __device__ __forceinline__ double rcp_fast(double x) {
   double y;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-  double e = fma(-x, y, 1.0);
-  y = fma(y, e, y);
-  e = fma(-x, y, 1.0);
-  y = fma(y, e, y);
-  return y;
+  const double e = fma(-x, y, 1.0);
+  return fma(y, fma(e, e, e), y);  // y (1 + e + e^2)
 }
 
 __device__ __forceinline__ double rsqrt_fast(double x) {
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-#pragma unroll
-  for (int it = 0; it < 2; it++) {
-    const double xy = x * y;
-    const double e = fma(-xy, y, 1.0);              // 1 - x y^2
-    y = fma(y * fma(0.375, e, 0.5), e, y);          // y (1 + e/2 + 3e^2/8)
-  }
-  return y;
+  const double e = fma(-(x * y), y, 1.0);               // 1 - x y^2
+  return fma(y * fma(0.375, e, 0.5), e, y);             // y (1 + e/2 + 3e^2/8)
+}
+__device__ __forceinline__ double sqrt_fast(double x) { return x > 0.0 ? x * rsqrt_fast(x) : 0.0; }
+
+// atan on [0, inf) x [0, inf): first-quadrant atan2(n, w) (n, w >= 0, not both 0).  Octant reduction
+// to |x| <= tan(pi/8), then x + x s P(s) with a degree-11 fit (max relative error 2.2e-16).
+__device__ __forceinline__ double atan2_q1(double n, double w) {
+  const bool swap = n > w;
+  const double num = swap ? w : n, den = swap ? n : w;
+  double r = num * rcp_fast(den);                        // in [0, 1]
+  const bool hi = r > 0.41421356237309503;
+  if (hi) r = (r - 1.0) * rcp_fast(r + 1.0);             // atan(r) = pi/4 + atan((r-1)/(r+1))
+  const double s = r * r;
+  double q = 1.08884100212413085e-02;
+  q = fma(q, s, -2.97502137203377037e-02);
+  q = fma(q, s, 4.36598234771156321e-02);
+  q = fma(q, s, -5.19008551015063060e-02);
+  q = fma(q, s, 5.87346776764138684e-02);
+  q = fma(q, s, -6.66594734155613600e-02);
+  q = fma(q, s, 7.69226916464344074e-02);
+  q = fma(q, s, -9.09090775828966802e-02);
+  q = fma(q, s, 1.11111110828050572e-01);
+  q = fma(q, s, -1.42857142853820868e-01);
+  q = fma(q, s, 1.99999999999983052e-01);
+  q = fma(q, s, -3.33333333333333370e-01);
+  double a = fma(r * s, q, r);
+  if (hi) a += 0.78539816339744831;
+  return swap ? 1.5707963267948966 - a : a;
 }
 
 __device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(FULL, v, src); }
@@ -106,39 +125,39 @@ __device__ __forceinline__ void angle_axis_total(const double (&R)[9], double (&
   double qw, qv[3];
   double t = R[0] + R[4] + R[8];
   if (t > 0.0) {
-    t = sqrt(t + 1.0);
+    t = sqrt_fast(t + 1.0);
     qw = 0.5 * t;
-    t = 0.5 / t;
+    t = 0.5 * rcp_fast(t);
     qv[0] = (R[7] - R[5]) * t;
     qv[1] = (R[2] - R[6]) * t;
     qv[2] = (R[3] - R[1]) * t;
   } else if (R[0] >= R[4] && R[0] >= R[8]) {  // i = 0 (Eigen picks the first largest diagonal)
-    t = sqrt(R[0] - R[4] - R[8] + 1.0);
+    t = sqrt_fast(R[0] - R[4] - R[8] + 1.0);
     qv[0] = 0.5 * t;
-    t = 0.5 / t;
+    t = 0.5 * rcp_fast(t);
     qw = (R[7] - R[5]) * t;
     qv[1] = (R[3] + R[1]) * t;
     qv[2] = (R[6] + R[2]) * t;
   } else if (R[4] > R[0] && R[4] >= R[8]) {  // i = 1
-    t = sqrt(R[4] - R[8] - R[0] + 1.0);
+    t = sqrt_fast(R[4] - R[8] - R[0] + 1.0);
     qv[1] = 0.5 * t;
-    t = 0.5 / t;
+    t = 0.5 * rcp_fast(t);
     qw = (R[2] - R[6]) * t;
     qv[2] = (R[7] + R[5]) * t;
     qv[0] = (R[1] + R[3]) * t;
   } else {  // i = 2
-    t = sqrt(R[8] - R[0] - R[4] + 1.0);
+    t = sqrt_fast(R[8] - R[0] - R[4] + 1.0);
     qv[2] = 0.5 * t;
-    t = 0.5 / t;
+    t = 0.5 * rcp_fast(t);
     qw = (R[3] - R[1]) * t;
     qv[0] = (R[2] + R[6]) * t;
     qv[1] = (R[5] + R[7]) * t;
   }
-  double n = sqrt(qv[0] * qv[0] + qv[1] * qv[1] + qv[2] * qv[2]);
-  if (n != 0.0) {
-    const double angle = 2.0 * atan2(n, fabs(qw));
+  double n = sqrt_fast(qv[0] * qv[0] + qv[1] * qv[1] + qv[2] * qv[2]);
+  if (n > 1e-150) {
+    const double angle = 2.0 * atan2_q1(n, fabs(qw));
     if (qw < 0.0) n = -n;
-    const double s = angle / n;
+    const double s = angle * rcp_fast(n);
     out[0] = qv[0] * s;
     out[1] = qv[1] * s;
     out[2] = qv[2] * s;
@@ -216,7 +235,8 @@ __device__ __forceinline__ void store_rec(const SplitIO& io, int64_t idx, int la
 // ------------------------------------------------------------------------------------------------
 template <class IO>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, QPB_MIN_CTAS_PER_SM)
-balance_qp_kernel(const qpb_params* __restrict__ gparams, IO io, int64_t n, unsigned long long* __restrict__ ticket) {
+balance_qp_kernel(const qpb_params* __restrict__ gparams, IO io, int64_t n, unsigned long long* __restrict__ ticket,
+                  unsigned long long* __restrict__ ticket_to_clear) {
   __shared__ qpb_params P;
   __shared__ WarpSmem wsm[WARPS_PER_CTA];
 
@@ -226,6 +246,7 @@ balance_qp_kernel(const qpb_params* __restrict__ gparams, IO io, int64_t n, unsi
     double* dst = reinterpret_cast<double*>(&P);
     for (int i = threadIdx.x; i < nw; i += blockDim.x) dst[i] = src[i];
   }
+  if (blockIdx.x == 0 && threadIdx.x == 0) *ticket_to_clear = 0ULL;  // for a launch half a ring from now
   __syncthreads();
 
   const int lane = threadIdx.x & 31;
@@ -367,8 +388,10 @@ balance_qp_kernel(const qpb_params* __restrict__ gparams, IO io, int64_t n, unsi
       }
       __syncwarp();  // bz is reused below
 
-      // ---- Cholesky Q = L L^T, right-looking; column k of L is published to shared memory --------
+      // ---- Cholesky Q = L L^T, right-looking; column k of L is published to shared memory.  The
+      //      gradient rides along as an extra column, which yields y0 = -L^-1 c by forward substitution.
       double rsd[12];
+      double cy = -ci;
 #pragma unroll
       for (int k = 0; k < 12; k++) {
         const double d = shfl_d(Qr[k], k);
@@ -377,32 +400,34 @@ balance_qp_kernel(const qpb_params* __restrict__ gparams, IO io, int64_t n, unsi
         rsd[k] = rs;
         const double lik = (lane >= k) ? Qr[k] * rs : 0.0;  // L[lane][k]
         if (isP) ws.LJ[k * LS + lane] = lik;
+        if (lane == k) {
+          const double yk = cy * rs;
+          ws.LJ[k * LS + 12] = yk;
+          ws.bv[k] = yk;
+        }
         __syncwarp();
 #pragma unroll
         for (int j = k + 1; j < 12; j++) Qr[j] = fma(-lik, ws.LJ[k * LS + j], Qr[j]);
+        cy = fma(-lik, ws.LJ[k * LS + 12], cy);
       }
-      // ---- T = L^-1 by columns (lane j holds column j of T = row j of J0 = L^-T); lane 12 carries
-      //      the extra right-hand side -c, giving y0 = -L^-1 c ------------------------------------
-      ws.bz[lane] = ci;
-      __syncwarp();
+      // ---- T = L^-1 by columns: lane j holds column j of T = row j of J0 = L^-T -----------------
       double J0r[12];
 #pragma unroll
-      for (int m = 0; m < 12; m++) J0r[m] = (lane == 12) ? -ws.bz[m] : ((lane == m) ? 1.0 : 0.0);
+      for (int m = 0; m < 12; m++) J0r[m] = (lane == m) ? 1.0 : 0.0;
 #pragma unroll
       for (int l = 0; l < 12; l++) {
         J0r[l] *= rsd[l];
 #pragma unroll
         for (int m = l + 1; m < 12; m++) J0r[m] = fma(-ws.LJ[l * LS + m], J0r[l], J0r[m]);
       }
-      __syncwarp();  // everyone is done reading L and bz
-      if (lane == 12) sts12(ws.bv, J0r);
-      if (isP) sts12(ws.LJ + LS * lane, J0r);  // J0 rows
-      __syncwarp();
       {
         double y0[12];
         lds12(ws.bv, y0);
         x = dot12(J0r, y0);  // unconstrained minimiser f0 = J0 y0 (lanes 0..11)
       }
+      __syncwarp();  // everyone is done reading L
+      if (isP) sts12(ws.LJ + LS * lane, J0r);  // J0 rows
+      __syncwarp();
       // ---- whitened normals n~_j = J0^T n_j and their squared norms (lanes 0..23) ----------------
       {
         double ra[12], rb[12];
@@ -411,8 +436,8 @@ balance_qp_kernel(const qpb_params* __restrict__ gparams, IO io, int64_t n, unsi
 #pragma unroll
         for (int m = 0; m < 12; m++) ra[m] = fma(c_cb, rb[m], c_ca * ra[m]);
         if (lane < 24) {
-          sts12(ws.Nt + 12 * lane, ra);
-          ws.nn[lane] = dot12(ra, ra);
+          sts12(ws.Nt + LS * lane, ra);
+          ws.Nt[LS * lane + 12] = dot12(ra, ra);
         }
       }
       __syncwarp();
@@ -438,27 +463,31 @@ balance_qp_kernel(const qpb_params* __restrict__ gparams, IO io, int64_t n, unsi
           const uint32_t act2 = active >> ((2 * lane) & 31);
           const bool vA = stance && !(act2 & 1u) && (sA < ntolA);
           const bool vB = stance && !(act2 & 2u) && (sB < ntolB);
-          const bool pickB = vB && (!vA || sB < sA);
-          const double sv2 = pickB ? sB : sA;
-          const uint32_t key = (vA || vB) ? (((uint32_t)__double2hiint(sv2) & ~31u) | (uint32_t)(2 * lane + (pickB ? 1 : 0))) : 0u;
-          const uint32_t kmax = __reduce_max_sync(FULL, key);
-          if (p < 0) {
-            if (kmax == 0) break;  // primal feasible: optimal
+          // key: most negative slack wins (sign bit set => larger magnitude = larger unsigned); low 5 bits = row
+          const uint32_t keyA = vA ? (((uint32_t)__double2hiint(sA) & ~31u) | (uint32_t)(2 * lane)) : 0u;
+          const uint32_t keyB = vB ? (((uint32_t)__double2hiint(sB) & ~31u) | (uint32_t)(2 * lane + 1)) : 0u;
+          const uint32_t kmax = __reduce_max_sync(FULL, max(keyA, keyB));
+          const bool fresh = p < 0;
+          if ((fresh && kmax == 0u) || iters >= max_iter) {  // primal feasible (optimal) or out of iterations
+            if (!(fresh && kmax == 0u)) status = QPB_MAX_ITER;
+            break;
+          }
+          if (fresh) {
             p = (int)(kmax & 31u);
             up = 0.0;
           }
-          if (iters >= max_iter) { status = QPB_MAX_ITER; break; }
           iters++;
           const double sp = shfl_d((p & 1) ? sB : sA, p >> 1);
 
           // (2) z~ = P n~ (lanes 0..11), r = N~* n~ (lanes 16..27)
+          const double* ntp = ws.Nt + LS * p;
           double mv;
           {
             double nt[12];
-            lds12(ws.Nt + 12 * p, nt);
+            lds12(ntp, nt);
             mv = dot12(M, nt);
           }
-          const double nn = ws.nn[p];
+          const double nn = ntp[12];
           ws.bz[lane] = mv;
           __syncwarp();
           double zt[12];
@@ -467,7 +496,7 @@ balance_qp_kernel(const qpb_params* __restrict__ gparams, IO io, int64_t n, unsi
           double acc;
           {
             double a[12];
-            lds12(isP ? (ws.LJ + LS * lane) : (ws.Nt + 12 * p), a);
+            lds12(isP ? (ws.LJ + LS * lane) : ntp, a);
             acc = dot12(a, zt);
           }
           const double zeta = shfl_d(acc, 16);
@@ -475,7 +504,7 @@ balance_qp_kernel(const qpb_params* __restrict__ gparams, IO io, int64_t n, unsi
           const double izeta = rcp_fast(zeta);
           const double t2 = -sp * izeta;  // > 0: row p is violated and zeta > 0
           // (4) dual step bound: min u_k / r_k over r_k > 0 (exact argmin via two integer reductions)
-          const bool cand = isN && cons >= 0 && mv > 0.0;
+          const bool cand = cons >= 0 && mv > 0.0;  // cons >= 0 only on slot lanes
           const double uu = (__double2hiint(u) < 0) ? 0.0 : u;  // rounding can leave -1e-17
           const double ratio = uu * rcp_fast(mv);
           const uint32_t rhi = cand ? (uint32_t)__double2hiint(ratio) : 0x7ff00000u;
@@ -492,14 +521,14 @@ balance_qp_kernel(const qpb_params* __restrict__ gparams, IO io, int64_t n, unsi
           const double t = full ? t2 : t1;
           // (5) step
           x = fma(dep ? 0.0 : t, acc, x);  // meaningful on lanes 0..11
-          if (isN && cons >= 0) u = fma(-t, mv, u);
+          u = fma(-t, mv, u);  // free slots and idle lanes have M = 0, hence mv = 0
           up += t;
           double coef;
           if (full) {
             // (6a) full step: row p enters the working set;  M -= (M n~) z~^T / zeta
             const uint32_t fb = __ballot_sync(FULL, isN && cons < 0);
             const int ql = __ffs(fb) - 1;
-            coef = (isP || (isN && cons >= 0)) ? mv * izeta : 0.0;
+            coef = mv * izeta;  // zero on free slots / idle lanes (their M rows are zero)
             if (lane == ql) { coef = -izeta; cons = p; u = up; }
             active |= 1u << p;
             p = -1;
@@ -513,7 +542,7 @@ balance_qp_kernel(const qpb_params* __restrict__ gparams, IO io, int64_t n, unsi
             const int cdrop = __shfl_sync(FULL, cons, kl);
             coef = 0.0;
             if (isP) coef = -ws.bv[lane] * idelta;
-            else if (isN && cons >= 0) coef = gam * idelta;
+            else if (cons >= 0) coef = gam * idelta;
             if (lane == kl) { coef = 1.0; cons = -1; u = 0.0; }
             active &= ~(1u << cdrop);
           }
