@@ -2,7 +2,7 @@
 """Benchmark of the balance-controller hot path (BASELINE.json metric: balance QPs/sec, batched).
 
   python bench.py --gpus N --steps K --warmup W            # our CUDA path (one process per GPU under torchrun)
-  python bench.py --impl reference --gpus N --steps K ...  # the CPU path (oracle port) on the host cores
+  python bench.py --impl reference --gpus N --steps K ...  # the reference CPU path (oracle/_ref) on the host cores
 
 A "step" is one pass of the hot path over one batch of synthetic robot states: BASELINE config 2
 (65 536 states, 4 feet in contact, mu = 0.6, seed 20260102) per GPU; weak scaling: rank r owns records
@@ -107,65 +107,79 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_baseline(params, S, budget_s=12.0):
-    """The oracle port on the host cores over a bounded sample of the workload (test infrastructure
-    used only as the timed CPU baseline)."""
+def _cpu_arm():
+    """The CPU implementation that is timed: oracle/_ref (the reference's own balance_controller.cpp +
+    kinematics.cpp compiled against stand-in Armadillo/qpOASES headers) when it was
+    built, else the plain-C oracle port.  Test infrastructure, used here only as the timed baseline."""
     import oracle
 
+    if oracle.ref_available():
+        return "reference", oracle.ref_control_batch, ("oracle/_ref: reference sources balance_controller.cpp + kinematics.cpp, "
+                                                        "stand-in Armadillo/qpOASES (QP solved by the oracle's Goldfarb-Idnani)")
+    return "port", oracle.control_batch, "oracle port (plain C restatement)"
+
+
+def cpu_baseline(params, S, budget_s=12.0):
+    """The reference CPU path on the host cores over a bounded sample of the workload."""
+    import oracle
+
+    kind, fn, desc = _cpu_arm()
     cores = os.cpu_count() or 1
-    oracle.control_batch(params, S[:2048], cores)  # warm
+    fn(params, S[:2048], cores)  # warm
     t0 = time.perf_counter()
-    oracle.control_batch(params, S[:8192], cores)
+    fn(params, S[:8192], cores)
     rate = 8192 / (time.perf_counter() - t0)
     n = int(min(len(S), max(8192, rate * budget_s / 3)))
     best = 0.0
     for _ in range(3):
         t0 = time.perf_counter()
-        oracle.control_batch(params, S[:n], cores)
+        fn(params, S[:n], cores)
         best = max(best, n / (time.perf_counter() - t0))
     t0 = time.perf_counter()
-    m = min(n, 16384)
-    oracle.control_batch(params, S[:m], 1)
+    m = min(n, 8192)
+    fn(params, S[:m], 1)
     one = m / (time.perf_counter() - t0)
-    return {"value": best, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"first {n} records of the workload, best of 3, {cores} threads (pthread slices); 1 thread: {one:.0f} QP/s",
-            "one_thread": one}
+    t0 = time.perf_counter()
+    oracle.control_batch(params, S[:n], cores)
+    port = n / (time.perf_counter() - t0)
+    return {"value": best, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": f"first {n} records of the workload, best of 3, {cores} threads; {desc}; 1 thread: {one:.0f} QP/s",
+            "one_thread": one, "c_port_all_cores": port}
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU path for this hot path.  qpOASES/Armadillo/Drake are not
-    installable here, so this is the oracle port, with all host threads, on our arm's config."""
+    """--impl reference: the reference's CPU path for this hot path on the host cores (see _cpu_arm), with all
+    the host threads, on our arm's config.  Rank 0 only; other ranks exit without work."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import oracle
-
-    n, seed, masks, profile, desc = WORKLOADS[args.workload]
+    kind, fn, desc = _cpu_arm()
+    n, seed, masks, profile, wdesc = WORKLOADS[args.workload]
     params = default_params(MU)
     cores = os.cpu_count() or 1
     S_full = states.generate_states(n, seed, profile=profile, masks=masks)
-    oracle.control_batch(params, S_full[:4096], cores)
+    fn(params, S_full[:4096], cores)
     t0 = time.perf_counter()
-    oracle.control_batch(params, S_full[:8192], cores)
+    fn(params, S_full[:8192], cores)
     rate = 8192 / (time.perf_counter() - t0)
     total_steps = args.steps + args.warmup
     per_step = int(min(n, max(4096, rate * 120.0 / total_steps)))  # whole run within ~2 minutes
     S = np.ascontiguousarray(S_full[:per_step])
     for _ in range(args.warmup):
-        oracle.control_batch(params, S, cores)
+        fn(params, S, cores)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        out = oracle.control_batch(params, S, cores)
+        out = fn(params, S, cores)
     dt = time.perf_counter() - t0
     assert (out["status"] == 0).all()
     value = per_step * args.steps / dt
-    sample = f"first {per_step} of {n} records per step, {cores} host threads"
+    sample = f"first {per_step} of {n} records per step, {cores} host threads; {desc}"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": desc, "qps_per_step": per_step, "note": "CPU oracle port of the reference path (qpOASES + Armadillo not installable here); rank 0 only"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": wdesc, "qps_per_step": per_step, "note": "CPU path on the host cores, rank 0 only; qpOASES/Armadillo/Drake are not installable here (DESIGN.md section 5)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -260,7 +274,7 @@ def run_ours(args):
         ref = oracle.control_batch(params, sample, os.cpu_count() or 1)
         got = np.ascontiguousarray(last[:: max(1, n // 2048)])
         err = float((np.abs(got["grf_body"] - ref["grf_body"]).max(axis=1) / np.maximum(np.abs(ref["grf_body"]).max(axis=1), 1.0)).max())
-        cpu = cpu_baseline(params, host_batches[0]) if world == 1 or True else None
+        cpu = cpu_baseline(params, host_batches[0])
         peak, peak_src = measured_peak_hbm()
         kernel_ms = elapsed_ms / args.steps  # one kernel launch per step on the timed stream
         achieved = ALGO_BYTES_PER_QP * n / (kernel_ms * 1e-3) / 1e9

@@ -110,3 +110,59 @@ def control_batch(params, states, nthreads=1):
     out = np.zeros(states.shape[0], dtype=OUT_DTYPE)
     lib().orc_control_batch(ctypes.byref(params), states.ctypes.data, states.shape[0], out.ctypes.data, int(nthreads))
     return out
+
+
+# ---- oracle/_ref: the reference's own sources compiled against stand-in third-party headers ------
+_REF_PATH = os.path.join(_HERE, "_ref", "libqpb_ref.so")
+_ref = None
+
+
+def ref_build():
+    """(Re)build oracle/_ref when /root/reference is present; elsewhere the prebuilt library is used."""
+    subprocess.run(["bash", os.path.join(_HERE, "ref_build.sh")], check=True, capture_output=True)
+    return os.path.exists(_REF_PATH)
+
+
+def ref_available():
+    return os.path.exists(_REF_PATH) or (os.path.isdir("/root/reference") and ref_build())
+
+
+def ref_lib():
+    global _ref
+    if _ref is None:
+        if os.path.isdir("/root/reference"):
+            ref_build()
+        R = ctypes.CDLL(_REF_PATH)
+        dp = ctypes.POINTER(ctypes.c_double)
+        R.ref_control.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        R.ref_control.restype = ctypes.c_int
+        R.ref_control_batch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_int]
+        R.ref_forward_kinematics.argtypes = [dp, dp]
+        R.ref_leg_jacobian.argtypes = [ctypes.c_int, dp, dp]
+        R.ref_error_count.restype = ctypes.c_int
+        _ref = R
+    return _ref
+
+
+def ref_control_batch(params, states, nthreads=1):
+    """States through the reference's BalanceController::control + jacobianTransposeControl
+    (its own source, stand-in Armadillo/qpOASES/ROS/rigid3d; one controller instance per thread)."""
+    states = np.ascontiguousarray(states)
+    assert states.dtype == STATE_DTYPE
+    out = np.zeros(states.shape[0], dtype=OUT_DTYPE)
+    ref_lib().ref_control_batch(ctypes.byref(params), states.ctypes.data, states.shape[0], out.ctypes.data, int(nthreads))
+    return out
+
+
+def ref_forward_kinematics(q12):
+    q = np.ascontiguousarray(q12, dtype=np.float64).reshape(12)
+    out = np.empty(12)
+    ref_lib().ref_forward_kinematics(_dp(q), _dp(out))
+    return out
+
+
+def ref_leg_jacobian(leg, q):
+    q = np.ascontiguousarray(q, dtype=np.float64).reshape(3)
+    out = np.empty(9)
+    ref_lib().ref_leg_jacobian(int(leg), _dp(q), _dp(out))
+    return out.reshape(3, 3)
