@@ -11,6 +11,7 @@
 #include <string>
 
 #include "qpb_kernel.cuh"
+#include "qpb_kernel16.cuh"
 
 namespace {
 
@@ -60,7 +61,8 @@ constexpr uint32_t kTicketSlots = 4096;  // ring of work counters; a launch re-z
 struct qpb_handle {
   int device = 0;
   int num_sms = 0;
-  int ctas_per_sm_packed = 0, ctas_per_sm_split = 0;
+  int ctas_per_sm_packed = 0, ctas_per_sm_split = 0, ctas_per_sm_16 = 0;
+  int qps_per_warp = 1;  // kernel mapping: 1 = balance_qp_kernel, 2 = balance_qp_kernel16 (QPB_QPS_PER_WARP overrides)
   qpb_params params;
   qpb_params* d_params = nullptr;
   cudaStream_t streams[kHostSlots] = {};
@@ -90,14 +92,20 @@ struct DeviceGuard {
 template <class IO>
 int launch_balance(qpb_handle* h, const IO& io, int64_t n, int ctas_per_sm, cudaStream_t stream) {
   if (n == 0) return QPB_SUCCESS;
-  const int64_t want = (n + qpb::WARPS_PER_CTA - 1) / qpb::WARPS_PER_CTA;
-  const int64_t cap = (int64_t)h->num_sms * ctas_per_sm;
+  const int per_warp = h->qps_per_warp;  // 1: one warp per QP; 2: two QPs per warp (half-warp kernel)
+  const int64_t units = (n + per_warp - 1) / per_warp;
+  const int64_t want = (units + qpb::WARPS_PER_CTA - 1) / qpb::WARPS_PER_CTA;
+  const int64_t cap = (int64_t)h->num_sms * (per_warp == 2 ? h->ctas_per_sm_16 : ctas_per_sm);
   const int grid = (int)(want < cap ? want : cap);
   // Launch i draws tickets from slot i % R and zeroes slot (i + R/2) % R for a launch far in the future, so no
   // memset sits on the critical path; this is safe while fewer than R/2 = 2048 launches of one handle are in flight.
   const uint32_t slot = h->ticket_slot.fetch_add(1, std::memory_order_relaxed) % kTicketSlots;
-  qpb::balance_qp_kernel<IO><<<grid, qpb::WARPS_PER_CTA * 32, 0, stream>>>(
-      h->d_params, io, n, h->d_tickets + slot, h->d_tickets + (slot + kTicketSlots / 2) % kTicketSlots);
+  unsigned long long* t0 = h->d_tickets + slot;
+  unsigned long long* t1 = h->d_tickets + (slot + kTicketSlots / 2) % kTicketSlots;
+  if (per_warp == 2)
+    qpb::balance_qp_kernel16<IO><<<grid, qpb::WARPS_PER_CTA * 32, 0, stream>>>(h->d_params, io, n, t0, t1);
+  else
+    qpb::balance_qp_kernel<IO><<<grid, qpb::WARPS_PER_CTA * 32, 0, stream>>>(h->d_params, io, n, t0, t1);
   h->launches.fetch_add(1, std::memory_order_relaxed);
   QPB_CUDA(cudaGetLastError());
   return QPB_SUCCESS;
@@ -184,7 +192,14 @@ int qpb_create(const qpb_params* params, int device, qpb_handle** out) {
   if (e == cudaSuccess)
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->ctas_per_sm_split, qpb::balance_qp_kernel<qpb::SplitIO>,
                                                       qpb::WARPS_PER_CTA * 32, 0);
-  if (e != cudaSuccess || h->ctas_per_sm_packed < 1 || h->ctas_per_sm_split < 1) {
+  if (e == cudaSuccess) {
+    int a = 0, b = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, qpb::balance_qp_kernel16<qpb::PackedIO>, qpb::WARPS_PER_CTA * 32, 0);
+    if (e == cudaSuccess)
+      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, qpb::balance_qp_kernel16<qpb::SplitIO>, qpb::WARPS_PER_CTA * 32, 0);
+    h->ctas_per_sm_16 = a < b ? a : b;
+  }
+  if (e != cudaSuccess || h->ctas_per_sm_packed < 1 || h->ctas_per_sm_split < 1 || h->ctas_per_sm_16 < 1) {
     const std::string msg = std::string("qpb_create: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "kernel does not fit");
     if (h->d_params) cudaFree(h->d_params);
     if (h->d_tickets) cudaFree(h->d_tickets);
@@ -192,6 +207,10 @@ int qpb_create(const qpb_params* params, int device, qpb_handle** out) {
     return fail(QPB_ERR_CUDA, msg);
   }
   h->num_sms = prop.multiProcessorCount;
+  if (const char* env = std::getenv("QPB_QPS_PER_WARP")) {
+    const int v = std::atoi(env);
+    if (v == 1 || v == 2) h->qps_per_warp = v;
+  }
   if (const char* env = std::getenv("QPB_HOST_CHUNK")) {
     const long long v = std::atoll(env);
     if (v >= 256 && v <= kHostChunkMax) h->host_chunk = v;
