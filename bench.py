@@ -288,7 +288,7 @@ def run_ours(args):
             "max_rel_grf_err_vs_oracle": err, "failed_qps": int(tot_failed),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic_per_launch(args.workload), "peak_source": peak_src,
-                         "algorithmic_bytes_per_qp": ALGO_BYTES_PER_QP, "kernel": "balance_qp_kernel<PackedIO>",
+                         "algorithmic_bytes_per_qp": ALGO_BYTES_PER_QP, "kernel": "balance_qp_kernel<PackedIO>" if os.environ.get("QPB_QPS_PER_WARP") == "1" else "balance_qp_kernel16<PackedIO>",
                          "kernel_ms": kernel_ms,
                          "note": "the path is FP64-issue/latency bound, not DRAM bound (DESIGN.md); per-GPU figure"},
             "cpu_baseline": cpu,

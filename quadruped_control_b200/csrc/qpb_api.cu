@@ -62,7 +62,9 @@ struct qpb_handle {
   int device = 0;
   int num_sms = 0;
   int ctas_per_sm_packed = 0, ctas_per_sm_split = 0, ctas_per_sm_16 = 0;
-  int qps_per_warp = 1;  // kernel mapping: 1 = balance_qp_kernel, 2 = balance_qp_kernel16 (QPB_QPS_PER_WARP overrides)
+  // kernel mapping: 2 = balance_qp_kernel16 (two QPs per warp, default: 1.2x the throughput), 1 = balance_qp_kernel
+  // (one warp per QP).  QPB_QPS_PER_WARP=1|2 in the environment at qpb_create time overrides it.
+  int qps_per_warp = 2;
   qpb_params params;
   qpb_params* d_params = nullptr;
   cudaStream_t streams[kHostSlots] = {};

@@ -22,12 +22,14 @@ struct __align__(16) HalfSmem {
 
 __device__ __forceinline__ double shfl16(double v, int src) { return __shfl_sync(FULL, v, src, 16); }
 
-__device__ __forceinline__ uint32_t half_max_u32(uint32_t v) {
+// Per-half reductions as 4-step butterflies.  (REDUX with a half-warp member mask was measured 8 % slower:
+// the compiler serialises the two member masks.)
+__device__ __forceinline__ uint32_t half_max_u32(uint32_t v, uint32_t) {
 #pragma unroll
   for (int o = 8; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(FULL, v, o, 16));
   return v;
 }
-__device__ __forceinline__ double half_min_f64(double v) {
+__device__ __forceinline__ double half_min_f64(double v, uint32_t) {
 #pragma unroll
   for (int o = 8; o > 0; o >>= 1) {
     const double w = __shfl_xor_sync(FULL, v, o, 16);
@@ -74,6 +76,7 @@ balance_qp_kernel16(const qpb_params* __restrict__ gparams, IO io, int64_t n, un
   const int wib = threadIdx.x >> 5;
   const int l = lane & 15;         // lane within the half
   const int hb = lane & 16;        // first lane of this half
+  const uint32_t hmask = 0xffffu << hb;
   HalfSmem& hs = hsm[2 * wib + (lane >> 4)];
   const int64_t gw = (int64_t)blockIdx.x * WARPS_PER_CTA + wib;
   const int64_t nwarps = (int64_t)gridDim.x * WARPS_PER_CTA;
@@ -286,7 +289,7 @@ balance_qp_kernel16(const qpb_params* __restrict__ gparams, IO io, int64_t n, un
       const bool vB = stance && !(act2 & 2u) && (sB < ntolB);
       const uint32_t keyA = vA ? (((uint32_t)__double2hiint(sA) & ~31u) | (uint32_t)(2 * l)) : 0u;
       const uint32_t keyB = vB ? (((uint32_t)__double2hiint(sB) & ~31u) | (uint32_t)(2 * l + 1)) : 0u;
-      const uint32_t kmax = half_max_u32(max(keyA, keyB));
+      const uint32_t kmax = half_max_u32(max(keyA, keyB), hmask);
       const bool fresh = p < 0;
       if (!done && ((fresh && kmax == 0u) || iters >= max_iter)) {
         if (!(fresh && kmax == 0u)) status = QPB_MAX_ITER;
@@ -331,7 +334,7 @@ balance_qp_kernel16(const qpb_params* __restrict__ gparams, IO io, int64_t n, un
       const double uu = (__double2hiint(u) < 0) ? 0.0 : u;
       const double INF = __longlong_as_double(0x7ff0000000000000LL);
       const double ratio = cand ? uu * rcp_fast(mvN) : INF;
-      const double t1 = half_min_f64(ratio);
+      const double t1 = half_min_f64(ratio, hmask);
       const bool has1 = t1 < INF;
       const uint32_t wb = (__ballot_sync(FULL, cand && ratio == t1) >> hb) & 0xffffu;
       const int kl = __ffs(wb) - 1;  // lane (within the half) of the blocking slot, -1 if none
@@ -359,14 +362,11 @@ balance_qp_kernel16(const qpb_params* __restrict__ gparams, IO io, int64_t n, un
       if (__any_sync(FULL, drop)) {
         if (drop && l == kl) sts12(hs.bv, Mn);
         __syncwarp();
-        double nu[12];
-        lds12(hs.bv, nu);
-        const double gam = dot12(Mn, nu);
+        lds12(drop ? hs.bv : hs.bz, zt);  // dropping halves: zt <- nu = row kl of N~*; others keep z~
+        const double gam = dot12(Mn, zt);
         const double idelta = rcp_fast(shfl16(gam, kl & 15));
         const int cdrop = __shfl_sync(FULL, cons, kl & 15, 16);
         if (drop) {
-#pragma unroll
-          for (int j = 0; j < 12; j++) zt[j] = nu[j];
           coefP = isP ? -hs.bv[l] * idelta : 0.0;
           coefN = (cons >= 0) ? gam * idelta : 0.0;
           if (l == kl) { coefN = 1.0; cons = -1; u = 0.0; }

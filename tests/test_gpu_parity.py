@@ -305,3 +305,32 @@ def test_cpp_shim_reproduces_reference_call_sequence(built, params08):
     for leg, name in enumerate(("RL", "FL", "RR")):
         assert np.allclose(data["force_3stance"][name], ref3["grf_body"][0][3 * leg:3 * leg + 3], rtol=1e-7, atol=1e-7)
         assert np.allclose(data["torque_3stance"][name], ref3["tau"][0][3 * leg:3 * leg + 3], rtol=1e-7, atol=1e-7)
+
+
+@pytest.mark.parametrize("qps_per_warp", ["1", "2"])
+def test_both_kernel_mappings(built, params06, qps_per_warp, monkeypatch):
+    """balance_qp_kernel (one warp per QP) and balance_qp_kernel16 (two QPs per warp, lock-step halves) run the
+    same arithmetic; both must meet the parity bar on every contact mask, odd batch sizes and failure paths."""
+    monkeypatch.setenv("QPB_QPS_PER_WARP", qps_per_warp)
+    solver = lib.BalanceSolver(params06)
+    S = states.generate_states(8191, 606, profile="stress", masks="mixed")  # odd count: last pair is half empty
+    codes = np.arange(len(S)) % 16
+    S["contact"][:4096] = ((codes[:4096, None] >> np.arange(4)) & 1)
+    S["w"][77, 2] = np.nan
+    out = solver.control_host(S)
+    ref = oracle.control_batch(params06, S, NCPU)
+    assert out["status"][77] == 2
+    ef, et = _compare(out, ref)
+    assert ef <= 1e-7
+    one = solver.control_host(S[:1])
+    assert one.tobytes() == out[:1].tobytes()
+    solver.close()
+    p = params06.copy()
+    p.max_iter = 5
+    solver = lib.BalanceSolver(p)
+    out5 = solver.control_host(S)
+    over = out5["status"] == 1
+    assert over.any() and (out5["iters"][over] == 5).all() and not out5["grf_body"][over].any()
+    okk = out5["status"] == 0
+    assert rel_err(out5["grf_body"][okk], ref["grf_body"][okk]) <= TOL
+    solver.close()
