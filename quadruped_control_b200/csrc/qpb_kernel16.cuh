@@ -24,12 +24,12 @@ __device__ __forceinline__ double shfl16(double v, int src) { return __shfl_sync
 
 // Per-half reductions as 4-step butterflies.  (REDUX with a half-warp member mask was measured 8 % slower:
 // the compiler serialises the two member masks.)
-__device__ __forceinline__ uint32_t half_max_u32(uint32_t v, uint32_t) {
+__device__ __forceinline__ uint32_t half_max_u32(uint32_t v) {
 #pragma unroll
   for (int o = 8; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(FULL, v, o, 16));
   return v;
 }
-__device__ __forceinline__ double half_min_f64(double v, uint32_t) {
+__device__ __forceinline__ double half_min_f64(double v) {
 #pragma unroll
   for (int o = 8; o > 0; o >>= 1) {
     const double w = __shfl_xor_sync(FULL, v, o, 16);
@@ -76,7 +76,6 @@ balance_qp_kernel16(const qpb_params* __restrict__ gparams, IO io, int64_t n, un
   const int wib = threadIdx.x >> 5;
   const int l = lane & 15;         // lane within the half
   const int hb = lane & 16;        // first lane of this half
-  const uint32_t hmask = 0xffffu << hb;
   HalfSmem& hs = hsm[2 * wib + (lane >> 4)];
   const int64_t gw = (int64_t)blockIdx.x * WARPS_PER_CTA + wib;
   const int64_t nwarps = (int64_t)gridDim.x * WARPS_PER_CTA;
@@ -89,11 +88,10 @@ balance_qp_kernel16(const qpb_params* __restrict__ gparams, IO io, int64_t n, un
   const int axp1 = (ax + 1) % 3, axp2 = (ax + 2) % 3;
   const double mu = P.mu;
   const double kz = ax < 2 ? mu : 0.0;
-  const double kA = ax < 2 ? -1.0 : 1.0;
+  const int sgnA = ax < 2 ? (int)0x80000000 : 0;  // sign applied to f in row A (row B uses the opposite)
   const double bA = ax < 2 ? 0.0 : P.fzmin;
   const double bB = ax < 2 ? 0.0 : -P.fzmax;
-  const double ntolA = ax < 2 ? -1e-9 : -1e-9 * (1.0 + fabs(P.fzmin));
-  const double ntolB = ax < 2 ? -1e-9 : -1e-9 * (1.0 + fabs(P.fzmax));
+  constexpr double kViolTol = -2e-9;  // a row is violated when its slack is below this (N)
   const int max_iter = P.max_iter;
 
   int64_t pair = gw;
@@ -247,6 +245,7 @@ balance_qp_kernel16(const qpb_params* __restrict__ gparams, IO io, int64_t n, un
       lds12(hs.LJ + LS * zl, rb);
       double na[12], nb[12];
       // rows A/B:  -/+ J0[v] + mu J0[z]  (ax < 2);   +/- J0[z]  (ax == 2)
+      const double kA = ax < 2 ? -1.0 : 1.0;
 #pragma unroll
       for (int m = 0; m < 12; m++) {
         const double base = kz * rb[m];
@@ -282,14 +281,15 @@ balance_qp_kernel16(const qpb_params* __restrict__ gparams, IO io, int64_t n, un
       // (1) slacks of the two rows this lane watches
       const double xz = shfl16(x, zl);
       const double base = kz * xz;
-      const double sA = fma(kA, x, base - bA);
-      const double sB = fma(-kA, x, base - bB);
+      const double xs = __hiloint2double(__double2hiint(x) ^ sgnA, __double2loint(x));  // -x (pyramid rows) or +x (fz rows)
+      const double sA = (base - bA) + xs;
+      const double sB = (base - bB) - xs;
       const uint32_t act2 = active >> ((2 * l) & 31);
-      const bool vA = stance && !(act2 & 1u) && (sA < ntolA);
-      const bool vB = stance && !(act2 & 2u) && (sB < ntolB);
+      const bool vA = stance && !(act2 & 1u) && (sA < kViolTol);
+      const bool vB = stance && !(act2 & 2u) && (sB < kViolTol);
       const uint32_t keyA = vA ? (((uint32_t)__double2hiint(sA) & ~31u) | (uint32_t)(2 * l)) : 0u;
       const uint32_t keyB = vB ? (((uint32_t)__double2hiint(sB) & ~31u) | (uint32_t)(2 * l + 1)) : 0u;
-      const uint32_t kmax = half_max_u32(max(keyA, keyB), hmask);
+      const uint32_t kmax = half_max_u32(max(keyA, keyB));
       const bool fresh = p < 0;
       if (!done && ((fresh && kmax == 0u) || iters >= max_iter)) {
         if (!(fresh && kmax == 0u)) status = QPB_MAX_ITER;
@@ -334,7 +334,7 @@ balance_qp_kernel16(const qpb_params* __restrict__ gparams, IO io, int64_t n, un
       const double uu = (__double2hiint(u) < 0) ? 0.0 : u;
       const double INF = __longlong_as_double(0x7ff0000000000000LL);
       const double ratio = cand ? uu * rcp_fast(mvN) : INF;
-      const double t1 = half_min_f64(ratio, hmask);
+      const double t1 = half_min_f64(ratio);
       const bool has1 = t1 < INF;
       const uint32_t wb = (__ballot_sync(FULL, cand && ratio == t1) >> hb) & 0xffffu;
       const int kl = __ffs(wb) - 1;  // lane (within the half) of the blocking slot, -1 if none
