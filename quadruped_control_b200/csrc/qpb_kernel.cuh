@@ -448,7 +448,7 @@ balance_qp_kernel(const qpb_params* __restrict__ gparams, IO io, int64_t n, unsi
       for (int j = 0; j < 12; j++) M[j] = (isP && j == lane) ? 1.0 : 0.0;
       double u = 0.0;
       int cons = -1;
-      uint32_t active = 0;
+      uint32_t active = 0, ignore = 0;
       int p = -1;
       double up = 0.0;
 
@@ -460,7 +460,7 @@ balance_qp_kernel(const qpb_params* __restrict__ gparams, IO io, int64_t n, unsi
           const double base = kz * xz;
           const double sA = fma(kA, x, base - bA);
           const double sB = fma(-kA, x, base - bB);
-          const uint32_t act2 = active >> ((2 * lane) & 31);
+          const uint32_t act2 = (active | ignore) >> ((2 * lane) & 31);
           const bool vA = stance && !(act2 & 1u) && (sA < ntolA);
           const bool vB = stance && !(act2 & 2u) && (sB < ntolB);
           // key: most negative slack wins (sign bit set => larger magnitude = larger unsigned); low 5 bits = row
@@ -516,7 +516,14 @@ balance_qp_kernel(const qpb_params* __restrict__ gparams, IO io, int64_t n, unsi
           const bool has1 = wb != 0u;
           const int kl = __ffs(wb) - 1;  // -1: no blocking row
           const double t1 = shfl_d(ratio, kl & 31);
-          if (dep && !has1) { status = QPB_BAD_INPUT; break; }  // infeasible
+          if (dep && !has1) {
+            // Row p lies in the span of the working set and no multiplier can give way.  The feasible set is
+            // never empty (qpb_create), so this is rounding making the twin of an active row look violated
+            // (e.g. fzmin == fzmax): the row holds to rounding, set it aside.
+            ignore |= 1u << p;
+            p = -1;
+            continue;
+          }
           const bool full = !dep && (!has1 || t2 <= t1);
           const double t = full ? t2 : t1;
           // (5) step

@@ -91,7 +91,8 @@ balance_qp_kernel16(const qpb_params* __restrict__ gparams, IO io, int64_t n, un
   const int sgnA = ax < 2 ? (int)0x80000000 : 0;  // sign applied to f in row A (row B uses the opposite)
   const double bA = ax < 2 ? 0.0 : P.fzmin;
   const double bB = ax < 2 ? 0.0 : -P.fzmax;
-  constexpr double kViolTol = -2e-9;  // a row is violated when its slack is below this (N)
+  // a row is violated when its slack is below -1e-9 (1 + |bound|); one value per lane (the larger bound of its two rows)
+  const double ntol = ax < 2 ? -1e-9 : -1e-9 * (1.0 + fmax(fabs(P.fzmin), fabs(P.fzmax)));
   const int max_iter = P.max_iter;
 
   int64_t pair = gw;
@@ -270,7 +271,7 @@ balance_qp_kernel16(const qpb_params* __restrict__ gparams, IO io, int64_t n, un
     }
     double u = 0.0;
     int cons = -1;
-    uint32_t active = 0;
+    uint32_t active = 0, ignore = 0;
     int p = -1;
     double up = 0.0;
     bool done = !ok;
@@ -284,9 +285,9 @@ balance_qp_kernel16(const qpb_params* __restrict__ gparams, IO io, int64_t n, un
       const double xs = __hiloint2double(__double2hiint(x) ^ sgnA, __double2loint(x));  // -x (pyramid rows) or +x (fz rows)
       const double sA = (base - bA) + xs;
       const double sB = (base - bB) - xs;
-      const uint32_t act2 = active >> ((2 * l) & 31);
-      const bool vA = stance && !(act2 & 1u) && (sA < kViolTol);
-      const bool vB = stance && !(act2 & 2u) && (sB < kViolTol);
+      const uint32_t act2 = (active | ignore) >> ((2 * l) & 31);
+      const bool vA = stance && !(act2 & 1u) && (sA < ntol);
+      const bool vB = stance && !(act2 & 2u) && (sB < ntol);
       const uint32_t keyA = vA ? (((uint32_t)__double2hiint(sA) & ~31u) | (uint32_t)(2 * l)) : 0u;
       const uint32_t keyB = vB ? (((uint32_t)__double2hiint(sB) & ~31u) | (uint32_t)(2 * l + 1)) : 0u;
       const uint32_t kmax = half_max_u32(max(keyA, keyB));
@@ -338,12 +339,16 @@ balance_qp_kernel16(const qpb_params* __restrict__ gparams, IO io, int64_t n, un
       const bool has1 = t1 < INF;
       const uint32_t wb = (__ballot_sync(FULL, cand && ratio == t1) >> hb) & 0xffffu;
       const int kl = __ffs(wb) - 1;  // lane (within the half) of the blocking slot, -1 if none
-      if (!done && dep && !has1) {   // infeasible
-        status = QPB_BAD_INPUT;
-        done = true;
+      // Row p lies in the span of the working set and no multiplier can give way: with a non-empty feasible
+      // set (qpb_create guarantees one) this only happens when rounding makes the twin of an active row look
+      // violated (e.g. fzmin == fzmax).  The row is satisfied to rounding: set it aside instead of failing.
+      const bool skip = !done && dep && !has1;
+      if (skip) {
+        ignore |= 1u << pp;
+        p = -1;
       }
       const bool full = !done && !dep && (!has1 || t2 <= t1);
-      const bool drop = !done && !full;
+      const bool drop = !done && !full && !skip;
       const double t = full ? t2 : (drop ? t1 : 0.0);
       // (5) step
       x = fma(dep ? 0.0 : t, acc, x);

@@ -334,3 +334,29 @@ def test_both_kernel_mappings(built, params06, qps_per_warp, monkeypatch):
     okk = out5["status"] == 0
     assert rel_err(out5["grf_body"][okk], ref["grf_body"][okk]) <= TOL
     solver.close()
+
+
+def test_degenerate_and_extreme_parameter_regimes(built):
+    """Active-set corner cases: pyramid apex (fzmin = 0, many linearly dependent rows), fzmin == fzmax,
+    tiny and large friction, heavy robot saturating fzmax, strong regulariser."""
+    rng = np.random.default_rng(12)
+    S = states.generate_states(3000, 91, profile="stress", masks="mixed")
+    S["x_d"][:, 2] = S["x"][:, 2] - rng.uniform(0.0, 0.6, len(S))  # demand downward acceleration: forces collapse to 0
+    cases = []
+    p = default_params(0.6); p.fzmin = 0.0; cases.append(("apex", p, S))
+    p = default_params(0.6); p.fzmin = 35.0; p.fzmax = 35.0; cases.append(("fz fixed", p, S))
+    p = default_params(0.01); cases.append(("mu tiny", p, S))
+    p = default_params(5.0); cases.append(("mu large", p, S))
+    S2 = states.generate_states(3000, 92, profile="default", masks="mixed")
+    p = default_params(0.6); p.mass = 60.0; cases.append(("heavy", p, S2))
+    p = default_params(0.6); p.W[:] = (1e-1 * np.eye(12)).ravel().tolist(); cases.append(("W large", p, S2))
+    for name, p, Sin in cases:
+        solver = lib.BalanceSolver(p)
+        out = solver.control_host(Sin)
+        ref = oracle.control_batch(p, Sin, NCPU)
+        assert (ref["status"] == 0).all(), name
+        ef, et = _compare(out, ref)
+        assert ef <= 1e-6, (name, ef)
+        solver.close()
+    apex = oracle.control_batch(cases[0][1], S, NCPU)
+    assert (np.abs(apex["grf_body"]).max(axis=1) < 1e-9).sum() > 500  # the all-zero apex solution really occurs
