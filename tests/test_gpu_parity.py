@@ -360,3 +360,16 @@ def test_degenerate_and_extreme_parameter_regimes(built):
         solver.close()
     apex = oracle.control_batch(cases[0][1], S, NCPU)
     assert (np.abs(apex["grf_body"]).max(axis=1) < 1e-9).sum() > 500  # the all-zero apex solution really occurs
+
+
+def test_randomised_parameter_sets(built):
+    """tools/fuzz_gpu.py: random SPD S/W, inertia, gains, mu in [0.02, 3], mass, fz bounds (incl. fzmin = 0 and
+    fzmin == fzmax), every profile and mask family, both kernel mappings -- all against the oracle."""
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_gpu.py"), "10", "1024", "77"],
+                         capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, res.stderr[-2000:]
+    last = res.stdout.strip().splitlines()[-1]
+    assert "failures 0" in last, res.stdout[-3000:]
