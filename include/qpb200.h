@@ -127,6 +127,33 @@ int qpb_jt_batch_host(qpb_handle* h, int64_t n, const double* q, const double* g
                       double* tau);
 int qpb_fk_batch_host(qpb_handle* h, int64_t n, const double* q, double* feet_body);
 
+/* ---- Swing-leg half of the control tick (the caller code around the hot path) ------------------------------
+ * src/commander_node.cpp:482-505: reference foot state (world) -> body frame -> legInverseKinematics
+ * (kinematics.cpp:117-160) -> legJacobianInverse (kinematics.cpp:190-204: inv, then pinv, then J^T) * velocity;
+ * :503-504 + joint_controller.cpp:21-39: joint PD; :515: merged with the stance torques; :526: clamp. */
+typedef struct qpb_joint_gains {
+  double kff[3], kp[3], kd[3]; /* JointController(kff, kp, kd), joint_control/* in mit_cheetah_config.yaml:50-53 */
+} qpb_joint_gains;
+
+typedef struct qpb_swing_rec {
+  double foot_ref_pos[12]; /* FootTrajectoryManager::referenceState(...).position per leg, WORLD frame */
+  double foot_ref_vel[12]; /* ... .velocity per leg, world frame */
+  double qdot[12];         /* measured joint velocities (JointStatesMap.qdot) */
+} qpb_swing_rec;           /* 288 bytes; only the entries of legs in swing are read */
+
+/* Defaults: kff = 0, kp = (40, 40, 50), kd = 1 (mit_cheetah_config.yaml:50-53). */
+int qpb_set_joint_gains(qpb_handle* h, const qpb_joint_gains* gains);
+
+/* One whole control tick for n robots (commander_node.cpp:482-533): control() + jacobianTransposeControl()
+ * for the stance legs and the joint-space PD for the swing legs, merged into qpb_out_rec.tau (all 12 joints),
+ * clamped when qpb_params.clamp_tau is set.  If the balance QP fails (status 1) the swing torques are still
+ * returned, as the reference publishes them alone; a non-finite state (status 2) returns zeros.  Device pointers. */
+int qpb_tick_batch_packed(qpb_handle* h, int64_t n, const qpb_state_rec* d_states, const qpb_swing_rec* d_swing,
+                          qpb_out_rec* d_out, void* stream);
+/* Same with host buffers (pipelined like qpb_control_batch_host). */
+int qpb_tick_batch_host(qpb_handle* h, int64_t n, const qpb_state_rec* h_states, const qpb_swing_rec* h_swing,
+                        qpb_out_rec* h_out);
+
 /* Pinned host memory for qpb_control_batch_host callers. */
 int qpb_host_alloc(void** ptr, size_t bytes);
 int qpb_host_free(void* ptr);

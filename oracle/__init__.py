@@ -6,7 +6,7 @@ import subprocess
 
 import numpy as np
 
-from quadruped_control_b200.records import OUT_DTYPE, STATE_DTYPE, Params
+from quadruped_control_b200.records import OUT_DTYPE, STATE_DTYPE, SWING_DTYPE, JointGains, Params
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "_build", "libqpb_oracle.so")
@@ -39,6 +39,11 @@ def lib():
         L.orc_control.argtypes = [vp, vp, vp, dp]
         L.orc_control.restype = ctypes.c_int
         L.orc_control_batch.argtypes = [vp, vp, ctypes.c_int64, vp, ctypes.c_int]
+        L.orc_default_joint_gains.argtypes = [vp]
+        L.orc_leg_inverse_kinematics.argtypes = [vp, ctypes.c_int, dp, dp]
+        L.orc_leg_jacobian_inverse.argtypes = [vp, ctypes.c_int, dp, dp]
+        L.orc_leg_jacobian_inverse.restype = ctypes.c_int
+        L.orc_tick_batch.argtypes = [vp, vp, vp, vp, ctypes.c_int64, vp, ctypes.c_int]
         _lib = L
     return _lib
 
@@ -140,6 +145,9 @@ def ref_lib():
         R.ref_forward_kinematics.argtypes = [dp, dp]
         R.ref_leg_jacobian.argtypes = [ctypes.c_int, dp, dp]
         R.ref_error_count.restype = ctypes.c_int
+        R.ref_leg_inverse_kinematics.argtypes = [ctypes.c_int, dp, dp]
+        R.ref_leg_jacobian_inverse.argtypes = [ctypes.c_int, dp, dp]
+        R.ref_tick_batch.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_longlong, ctypes.c_void_p, ctypes.c_int]
         _ref = R
     return _ref
 
@@ -166,3 +174,57 @@ def ref_leg_jacobian(leg, q):
     out = np.empty(9)
     ref_lib().ref_leg_jacobian(int(leg), _dp(q), _dp(out))
     return out.reshape(3, 3)
+
+
+# ---- swing-leg half of the control tick -------------------------------------------
+def default_joint_gains():
+    g = JointGains()
+    lib().orc_default_joint_gains(ctypes.byref(g))
+    return g
+
+
+def leg_inverse_kinematics(params, leg, foothold):
+    f = np.ascontiguousarray(foothold, dtype=np.float64).reshape(3)
+    out = np.empty(3)
+    lib().orc_leg_inverse_kinematics(ctypes.byref(params), int(leg), _dp(f), _dp(out))
+    return out
+
+
+def leg_jacobian_inverse(params, leg, q):
+    q = np.ascontiguousarray(q, dtype=np.float64).reshape(3)
+    out = np.empty(9)
+    kind = lib().orc_leg_jacobian_inverse(ctypes.byref(params), int(leg), _dp(q), _dp(out))
+    return out.reshape(3, 3), kind
+
+
+def tick_batch(params, gains, states, swing, nthreads=1):
+    """control() + jacobianTransposeControl() + swing-leg joint PD, merged and clamped (commander_node.cpp:482-533)."""
+    states, swing = np.ascontiguousarray(states), np.ascontiguousarray(swing)
+    assert states.dtype == STATE_DTYPE and swing.dtype == SWING_DTYPE and len(states) == len(swing)
+    out = np.zeros(len(states), dtype=OUT_DTYPE)
+    lib().orc_tick_batch(ctypes.byref(params), ctypes.byref(gains), states.ctypes.data, swing.ctypes.data, len(states),
+                         out.ctypes.data, int(nthreads))
+    return out
+
+
+def ref_leg_inverse_kinematics(leg, foothold):
+    f = np.ascontiguousarray(foothold, dtype=np.float64).reshape(3)
+    out = np.empty(3)
+    ref_lib().ref_leg_inverse_kinematics(int(leg), _dp(f), _dp(out))
+    return out
+
+
+def ref_leg_jacobian_inverse(leg, q):
+    q = np.ascontiguousarray(q, dtype=np.float64).reshape(3)
+    out = np.empty(9)
+    ref_lib().ref_leg_jacobian_inverse(int(leg), _dp(q), _dp(out))
+    return out.reshape(3, 3)
+
+
+def ref_tick_batch(params, gains, states, swing, nthreads=1):
+    states, swing = np.ascontiguousarray(states), np.ascontiguousarray(swing)
+    assert states.dtype == STATE_DTYPE and swing.dtype == SWING_DTYPE and len(states) == len(swing)
+    out = np.zeros(len(states), dtype=OUT_DTYPE)
+    ref_lib().ref_tick_batch(ctypes.byref(params), ctypes.byref(gains), states.ctypes.data, swing.ctypes.data, len(states),
+                             out.ctypes.data, int(nthreads))
+    return out

@@ -510,3 +510,203 @@ void orc_control_batch(const orc_params* p, const orc_state* s, int64_t n, orc_o
   batch_worker(&jobs[0]);
   for (int t = 1; t < nthreads; t++) pthread_join(th[t], NULL);
 }
+
+/* ==========================================================================================
+ * Swing-leg half of the control tick.
+ * ======================================================================================== */
+void orc_default_joint_gains(orc_joint_gains* g) { /* mit_cheetah_config.yaml:50-53 */
+  const double kp[3] = { 40.0, 40.0, 50.0 };
+  for (int i = 0; i < 3; i++) { g->kff[i] = 0.0; g->kp[i] = kp[i]; g->kd[i] = 1.0; }
+}
+
+/* kinematics.cpp:117-160.  links_ holds the unsigned lengths (kinematics.cpp:28-31). */
+void orc_leg_inverse_kinematics(const orc_params* p, int leg, const double foothold[3], double q[3]) {
+  const double x = foothold[0] - p->hip_offset[3 * leg];
+  const double y = foothold[1] - p->hip_offset[3 * leg + 1];
+  const double z = foothold[2] - p->hip_offset[3 * leg + 2];
+  const double l1 = fabs(p->link[3 * leg]), l2 = fabs(p->link[3 * leg + 1]), l3 = fabs(p->link[3 * leg + 2]);
+  double d = (x * x + y * y + z * z - l1 * l1 - l2 * l2 - l3 * l3) / (2.0 * l2 * l3);
+  if (d > 1.0) d = 1.0;
+  double sc = y * y + z * z - l1 * l1;
+  if (sc < 0.0) sc = 0.0;
+  const int right = p->link[3 * leg] < 0.0; /* "FR" or "RR", :147 */
+  if (right) q[0] = atan2(z, y) + atan2(sqrt(sc), -l1);
+  else q[0] = -(atan2(z, -y) + atan2(sqrt(sc), -l1));
+  q[2] = atan2(-sqrt(1.0 - d * d), d);
+  q[1] = -atan2(x, sqrt(sc)) - atan2(l3 * sin(q[2]), l2 + l3 * cos(q[2]));
+}
+
+/* cyclic Jacobi eigen-decomposition of a symmetric 3x3 (B = V diag(w) V') */
+static void jacobi3(double B[9], double V[9], double w[3]) {
+  for (int i = 0; i < 9; i++) V[i] = (i % 4 == 0) ? 1.0 : 0.0;
+  for (int sweep = 0; sweep < 30; sweep++) {
+    const double off = fabs(B[1]) + fabs(B[2]) + fabs(B[5]);
+    if (off == 0.0) break;
+    for (int pi = 0; pi < 2; pi++)
+      for (int qi = pi + 1; qi < 3; qi++) {
+        const double apq = B[3 * pi + qi];
+        if (apq == 0.0) continue;
+        const double theta = (B[4 * qi] - B[4 * pi]) / (2.0 * apq);
+        const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+        const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
+        for (int k = 0; k < 3; k++) { /* B <- B G */
+          const double bkp = B[3 * k + pi], bkq = B[3 * k + qi];
+          B[3 * k + pi] = c * bkp - sn * bkq;
+          B[3 * k + qi] = sn * bkp + c * bkq;
+        }
+        for (int k = 0; k < 3; k++) { /* B <- G' B */
+          const double bpk = B[3 * pi + k], bqk = B[3 * qi + k];
+          B[3 * pi + k] = c * bpk - sn * bqk;
+          B[3 * qi + k] = sn * bpk + c * bqk;
+        }
+        for (int k = 0; k < 3; k++) {
+          const double vkp = V[3 * k + pi], vkq = V[3 * k + qi];
+          V[3 * k + pi] = c * vkp - sn * vkq;
+          V[3 * k + qi] = sn * vkp + c * vkq;
+        }
+      }
+  }
+  w[0] = B[0]; w[1] = B[4]; w[2] = B[8];
+}
+
+/* Moore-Penrose pseudo-inverse of a 3x3 (arma::pinv: SVD, tolerance max(m,n) * sigma_max * eps) */
+static void pinv3(const double J[9], double out[9]) {
+  double B[9], V[9], w[3];
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) B[3 * i + j] = J[i] * J[j] + J[3 + i] * J[3 + j] + J[6 + i] * J[6 + j]; /* J'J */
+  jacobi3(B, V, w);
+  double smax = 0.0;
+  for (int i = 0; i < 3; i++) { if (w[i] < 0.0) w[i] = 0.0; if (sqrt(w[i]) > smax) smax = sqrt(w[i]); }
+  const double tol = 3.0 * smax * 2.220446049250313e-16;
+  double M[9]; /* V diag(1/sigma^2) V' */
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) {
+      double acc = 0.0;
+      for (int k = 0; k < 3; k++)
+        if (sqrt(w[k]) > tol) acc += V[3 * i + k] * V[3 * j + k] / w[k];
+      M[3 * i + j] = acc;
+    }
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) out[3 * i + j] = M[3 * i] * J[3 * j] + M[3 * i + 1] * J[3 * j + 1] + M[3 * i + 2] * J[3 * j + 2]; /* M J' */
+}
+
+/* kinematics.cpp:190-204: arma::inv, then arma::pinv, then the transpose.  Armadillo's inv ends in LAPACK
+ * getrf/getri, which fails only on an exactly zero pivot; pinv (SVD) then always succeeds. */
+int orc_leg_jacobian_inverse(const orc_params* p, int leg, const double q[3], double Jinv[9]) {
+  double J[9], a[9], b[9] = { 1, 0, 0, 0, 1, 0, 0, 0, 1 };
+  orc_leg_jacobian(p, leg, q, J);
+  memcpy(a, J, sizeof(a));
+  for (int c = 0; c < 3; c++) {
+    int piv = c;
+    for (int r = c + 1; r < 3; r++)
+      if (fabs(a[3 * r + c]) > fabs(a[3 * piv + c])) piv = r;
+    if (a[3 * piv + c] == 0.0 || !isfinite(a[3 * piv + c])) { pinv3(J, Jinv); return 1; }
+    for (int j = 0; j < 3; j++) {
+      double t = a[3 * c + j]; a[3 * c + j] = a[3 * piv + j]; a[3 * piv + j] = t;
+      t = b[3 * c + j]; b[3 * c + j] = b[3 * piv + j]; b[3 * piv + j] = t;
+    }
+    const double dd = a[3 * c + c];
+    for (int j = 0; j < 3; j++) { a[3 * c + j] /= dd; b[3 * c + j] /= dd; }
+    for (int r = 0; r < 3; r++)
+      if (r != c) {
+        const double f = a[3 * r + c];
+        for (int j = 0; j < 3; j++) { a[3 * r + j] -= f * a[3 * c + j]; b[3 * r + j] -= f * b[3 * c + j]; }
+      }
+  }
+  memcpy(Jinv, b, sizeof(b));
+  return 0;
+}
+
+/* math/numerics.cpp:23-50 */
+static double wrap_2pi(double a) {
+  const double PI = 3.14159265358979323846;
+  const double qf = floor(a / (2.0 * PI));
+  a -= qf * 2.0 * PI;
+  if (a < 0.0) a += 2.0 * PI;
+  return a;
+}
+static double wrap_pi(double r) {
+  const double PI = 3.14159265358979323846;
+  const double qf = floor((r + PI) / (2.0 * PI));
+  r = (r + PI) - qf * 2.0 * PI;
+  if (r < 0) r += 2.0 * PI;
+  return r - PI;
+}
+
+void orc_swing_torques(const orc_params* p, const orc_joint_gains* g, const orc_state* s, const orc_swing* sw,
+                       double tau[12], int present[4]) {
+  for (int leg = 0; leg < 4; leg++) {
+    present[leg] = 0;
+    if (s->contact[leg] != 0) continue; /* commander_node.cpp:485 */
+    double pb[3], vb[3];
+    for (int i = 0; i < 3; i++) { /* :491-492: Rwb' * position - x (sic), Rwb' * velocity */
+      double ap = 0.0, av = 0.0;
+      for (int k = 0; k < 3; k++) {
+        ap += s->Rwb[3 * k + i] * sw->foot_ref_pos[3 * leg + k];
+        av += s->Rwb[3 * k + i] * sw->foot_ref_vel[3 * leg + k];
+      }
+      pb[i] = ap - s->x[i];
+      vb[i] = av;
+    }
+    double qr[3], Jinv[9], qdr[3];
+    orc_leg_inverse_kinematics(p, leg, pb, qr);      /* :494 */
+    orc_leg_jacobian_inverse(p, leg, qr, Jinv);      /* :495-496 */
+    for (int i = 0; i < 3; i++) qdr[i] = Jinv[3 * i] * vb[0] + Jinv[3 * i + 1] * vb[1] + Jinv[3 * i + 2] * vb[2];
+    for (int i = 0; i < 3; i++) { /* joint_controller.cpp:27-35 */
+      const double qe = wrap_pi(wrap_2pi(qr[i]) - wrap_2pi(s->q[3 * leg + i]));
+      const double qde = qdr[i] - sw->qdot[3 * leg + i];
+      tau[3 * leg + i] = g->kp[i] * qe + g->kd[i] * qde + g->kff[i];
+    }
+    present[leg] = 1;
+  }
+}
+
+int orc_tick(const orc_params* p, const orc_joint_gains* g, const orc_state* s, const orc_swing* sw, orc_out* out) {
+  orc_params q = *p;
+  q.clamp_tau = 0; /* clamp once, after the merge (:515, :526) */
+  const int st = orc_control(&q, s, out, NULL);
+  const double* in = (const double*)s;
+  for (int i = 0; i < 60; i++)
+    if (!isfinite(in[i])) return st; /* nothing is published for a broken state */
+  /* the swing references are used as they come, like the reference does (NaN in -> NaN torque for that leg) */
+  double tau[12];
+  int present[4];
+  orc_swing_torques(p, g, s, sw, tau, present);
+  for (int leg = 0; leg < 4; leg++)
+    if (present[leg])
+      for (int i = 0; i < 3; i++) out->tau[3 * leg + i] = tau[3 * leg + i]; /* torque_map.insert(swing...), :515 */
+  if (p->clamp_tau)
+    for (int i = 0; i < 12; i++) out->tau[i] = fmin(fmax(out->tau[i], p->tau_min), p->tau_max); /* :526 */
+  return st;
+}
+
+typedef struct {
+  const orc_params* p;
+  const orc_joint_gains* g;
+  const orc_state* s;
+  const orc_swing* sw;
+  orc_out* out;
+  int64_t lo, hi;
+} tick_job;
+
+static void* tick_worker(void* arg) {
+  tick_job* j = (tick_job*)arg;
+  for (int64_t i = j->lo; i < j->hi; i++) orc_tick(j->p, j->g, &j->s[i], &j->sw[i], &j->out[i]);
+  return NULL;
+}
+
+void orc_tick_batch(const orc_params* p, const orc_joint_gains* g, const orc_state* s, const orc_swing* sw, int64_t n,
+                    orc_out* out, int nthreads) {
+  if (nthreads < 1) nthreads = 1;
+  if (nthreads > 256) nthreads = 256;
+  pthread_t th[256];
+  tick_job jobs[256];
+  for (int t = 0; t < nthreads; t++) {
+    jobs[t].p = p; jobs[t].g = g; jobs[t].s = s; jobs[t].sw = sw; jobs[t].out = out;
+    jobs[t].lo = n * t / nthreads;
+    jobs[t].hi = n * (t + 1) / nthreads;
+  }
+  for (int t = 1; t < nthreads; t++) pthread_create(&th[t], NULL, tick_worker, &jobs[t]);
+  tick_worker(&jobs[0]);
+  for (int t = 1; t < nthreads; t++) pthread_join(th[t], NULL);
+}

@@ -92,6 +92,31 @@ int orc_control(const orc_params* p, const orc_state* s, orc_out* out, double* f
 /* Batch driver used for the CPU baseline: nthreads pthreads over contiguous slices. */
 void orc_control_batch(const orc_params* p, const orc_state* s, int64_t n, orc_out* out, int nthreads);
 
+/* ---- swing-leg half of the control tick -----------------------------------------
+ * src/commander_node.cpp:482-505 (reference foot state -> body frame -> IK -> J^-1 v), :503-504 and
+ * joint_controller.cpp:21-39 (joint PD), :515 (merge with the stance torques), :526 (clamp);
+ * kinematics.cpp:117-160 (legInverseKinematics), :190-204 (legJacobianInverse: inv -> pinv -> J^T). */
+typedef struct orc_swing {
+  double foot_ref_pos[12]; /* world-frame reference foot positions (FootTrajectoryManager::referenceState) */
+  double foot_ref_vel[12]; /* world-frame reference foot velocities */
+  double qdot[12];         /* measured joint velocities (JointStatesMap.qdot) */
+} orc_swing;
+typedef struct orc_joint_gains {
+  double kff[3], kp[3], kd[3]; /* joint_control/{kff,kp,kd}: mit_cheetah_config.yaml:50-53 */
+} orc_joint_gains;
+
+void orc_default_joint_gains(orc_joint_gains* g);
+void orc_leg_inverse_kinematics(const orc_params* p, int leg, const double foothold[3], double q[3]);
+/* returns 0 = plain inverse, 1 = pseudo-inverse (a pivot was exactly zero), row-major 3x3 */
+int orc_leg_jacobian_inverse(const orc_params* p, int leg, const double q[3], double Jinv[9]);
+/* torques of the legs in swing (others untouched); present[leg] = 1 where written */
+void orc_swing_torques(const orc_params* p, const orc_joint_gains* g, const orc_state* s, const orc_swing* sw,
+                       double tau[12], int present[4]);
+/* whole tick: control() + jacobianTransposeControl() + swing torques merged, clamp if p->clamp_tau */
+int orc_tick(const orc_params* p, const orc_joint_gains* g, const orc_state* s, const orc_swing* sw, orc_out* out);
+void orc_tick_batch(const orc_params* p, const orc_joint_gains* g, const orc_state* s, const orc_swing* sw, int64_t n,
+                    orc_out* out, int nthreads);
+
 #ifdef __cplusplus
 }
 #endif

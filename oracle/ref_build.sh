@@ -16,7 +16,7 @@ fi
 gcc -O2 -std=c99 -fPIC -ffp-contract=off -c "$HERE/qpb_oracle.c" -o "$OUT/qpb_oracle.o"
 g++ -O2 -std=c++17 -fPIC -shared -ffp-contract=off -w \
     -I "$HERE/ref_stubs" -I "$REF/include" -I "$HERE" \
-    "$SRC/balance_controller.cpp" "$SRC/kinematics.cpp" "$SRC/gait.cpp" "$SRC/math/numerics.cpp" \
+    "$SRC/balance_controller.cpp" "$SRC/kinematics.cpp" "$SRC/gait.cpp" "$SRC/math/numerics.cpp" "$SRC/joint_controller.cpp" \
     "$HERE/ref_glue.cpp" "$OUT/qpb_oracle.o" -o "$OUT/libqpb_ref.so" -lm -lpthread
 rm -f "$OUT/qpb_oracle.o"
 echo "built $OUT/libqpb_ref.so"

@@ -172,3 +172,109 @@ void ref_leg_jacobian(int leg, const double* q3, double* J9)
 int ref_error_count(void) { return qpb_ref_error_count; }
 
 }  // extern "C"
+
+// ---- swing-leg half of the control tick: the reference's own legInverseKinematics, legJacobianInverse and
+//      JointController::control, driven exactly as commander_node.cpp:482-533 drives them -----------------------
+#include <quadruped_controller/joint_controller.hpp>
+
+extern "C" {
+
+void ref_leg_inverse_kinematics(int leg, const double* foothold3, double* q3)
+{
+  QuadrupedKinematics kin;
+  const arma::vec3 q = kin.legInverseKinematics(kLegs[leg], arma::vec3({ foothold3[0], foothold3[1], foothold3[2] }));
+  for (unsigned k = 0; k < 3; k++) q3[k] = q(k);
+}
+
+void ref_leg_jacobian_inverse(int leg, const double* q3, double* Jinv9)
+{
+  QuadrupedKinematics kin;
+  const arma::mat33 Ji = kin.legJacobianInverse(kLegs[leg], arma::vec3({ q3[0], q3[1], q3[2] }));
+  for (unsigned i = 0; i < 3; i++)
+    for (unsigned j = 0; j < 3; j++) Jinv9[3 * i + j] = Ji(i, j);
+}
+
+int ref_tick(const orc_params* p, const orc_joint_gains* g, const orc_state* s, const orc_swing* sw, orc_out* out)
+{
+  ensure(p);
+  std::memset(out, 0, sizeof(*out));
+  const JointController joint_controller(arma::vec3({ g->kff[0], g->kff[1], g->kff[2] }), arma::vec3({ g->kp[0], g->kp[1], g->kp[2] }),
+                                         arma::vec3({ g->kd[0], g->kd[1], g->kd[2] }));  // commander_node.cpp:341
+  const mat Rwb = to_mat(s->Rwb, 3, 3);
+  const vec x = to_vec(s->x, 3);
+  FootholdMap foot_map;
+  GaitMap gait_map;
+  JointStatesMap joint_states_map;
+  int n_stance = 0;
+  for (unsigned leg = 0; leg < 4; leg++)
+  {
+    foot_map.emplace(kLegs[leg], vec3({ s->feet[3 * leg], s->feet[3 * leg + 1], s->feet[3 * leg + 2] }));
+    const bool st = s->contact[leg] != 0;
+    n_stance += st ? 1 : 0;
+    gait_map.emplace(kLegs[leg], std::make_pair(st ? LegState::stance : LegState::swing, 0.0));
+    LegJointStates js;
+    for (unsigned k = 0; k < 3; k++)
+    {
+      js.q(k) = s->q[3 * leg + k];
+      js.qdot(k) = sw->qdot[3 * leg + k];
+    }
+    joint_states_map.emplace(kLegs[leg], js);
+  }
+  // commander_node.cpp:482-500
+  JointStatesMap swing_leg_js_map;
+  for (const auto& [leg_name, leg_state] : gait_map)
+  {
+    if (leg_state.first == LegState::swing)
+    {
+      unsigned leg = 0;
+      while (kLegs[leg] != leg_name) leg++;
+      FootState foot_state(vec3({ sw->foot_ref_pos[3 * leg], sw->foot_ref_pos[3 * leg + 1], sw->foot_ref_pos[3 * leg + 2] }),
+                           vec3({ sw->foot_ref_vel[3 * leg], sw->foot_ref_vel[3 * leg + 1], sw->foot_ref_vel[3 * leg + 2] }));
+      foot_state.position = Rwb.t() * foot_state.position - x;
+      foot_state.velocity = Rwb.t() * foot_state.velocity;
+      const vec3 q = g_cache.kin->legInverseKinematics(leg_name, foot_state.position);
+      const vec3 qdot = g_cache.kin->legJacobianInverse(leg_name, q) * foot_state.velocity;
+      swing_leg_js_map.emplace(leg_name, LegJointStates(q, qdot));
+    }
+  }
+  // :503-515
+  const TorqueMap swing_torque_map = joint_controller.control(swing_leg_js_map, joint_states_map);
+  const ForceMap force_map = g_cache.bc->control(Rwb, to_mat(s->Rwb_d, 3, 3), x, to_vec(s->xdot, 3), to_vec(s->w, 3),
+                                                 to_vec(s->x_d, 3), to_vec(s->xdot_d, 3), to_vec(s->w_d, 3), foot_map, gait_map);
+  TorqueMap torque_map = g_cache.kin->jacobianTransposeControl(joint_states_map, force_map);
+  torque_map.insert(swing_torque_map.begin(), swing_torque_map.end());
+  for (unsigned leg = 0; leg < 4; leg++)
+  {
+    const auto f = force_map.find(kLegs[leg]);
+    if (f != force_map.end())
+      for (unsigned k = 0; k < 3; k++) out->grf_body[3 * leg + k] = f->second(k);
+    const auto t = torque_map.find(kLegs[leg]);
+    if (t != torque_map.end())
+      for (unsigned k = 0; k < 3; k++)
+      {
+        double tau = t->second(k);
+        if (p->clamp_tau) tau = std::fmin(std::fmax(tau, p->tau_min), p->tau_max);  // arma::clamp, :526
+        out->tau[3 * leg + k] = tau;
+      }
+  }
+  out->status = (static_cast<int>(force_map.size()) == n_stance) ? 0 : 2;
+  return static_cast<int>(torque_map.size());
+}
+
+void ref_tick_batch(const orc_params* p, const orc_joint_gains* g, const orc_state* s, const orc_swing* sw, long long n,
+                    orc_out* out, int nthreads)
+{
+  if (nthreads <= 1)
+  {
+    for (long long i = 0; i < n; i++) ref_tick(p, g, &s[i], &sw[i], &out[i]);
+    return;
+  }
+  std::vector<std::thread> pool;
+  for (int t = 0; t < nthreads; t++)
+    pool.emplace_back([=]() {
+      for (long long i = n * t / nthreads; i < n * (t + 1) / nthreads; i++) ref_tick(p, g, &s[i], &sw[i], &out[i]);
+    });
+  for (auto& th : pool) th.join();
+}
+
+}  // extern "C"

@@ -7,6 +7,9 @@ from .records import (  # noqa: F401
     QPB_MAX_ITER,
     QPB_OK,
     STATE_DTYPE,
+    SWING_DTYPE,
+    JointGains,
+    default_joint_gains,
     Params,
     default_params,
 )

@@ -12,6 +12,7 @@
 
 #include "qpb_kernel.cuh"
 #include "qpb_kernel16.cuh"
+#include "qpb_swing.cuh"
 
 namespace {
 
@@ -70,6 +71,8 @@ struct qpb_handle {
   cudaStream_t streams[kHostSlots] = {};
   qpb_state_rec* d_in[kHostSlots] = {};
   qpb_out_rec* d_out[kHostSlots] = {};
+  qpb_swing_rec* d_sw[kHostSlots] = {};
+  qpb_joint_gains* d_gains = nullptr;  // JointController gains for the swing-leg half of the tick
   std::atomic<int64_t> launches{ 0 };
   // ring of work-ticket counters, one per in-flight launch of the balance kernel
   unsigned long long* d_tickets = nullptr;
@@ -110,6 +113,53 @@ int launch_balance(qpb_handle* h, const IO& io, int64_t n, int ctas_per_sm, cuda
     qpb::balance_qp_kernel<IO><<<grid, qpb::WARPS_PER_CTA * 32, 0, stream>>>(h->d_params, io, n, t0, t1);
   h->launches.fetch_add(1, std::memory_order_relaxed);
   QPB_CUDA(cudaGetLastError());
+  return QPB_SUCCESS;
+}
+
+// swing-leg kernel after the balance kernel on the same stream (stream order = the merge of commander_node.cpp:515)
+int launch_swing(qpb_handle* h, int64_t n, const qpb_state_rec* d_states, const qpb_swing_rec* d_swing, qpb_out_rec* d_out,
+                 cudaStream_t stream) {
+  if (n == 0) return QPB_SUCCESS;
+  const int64_t nlegs = 4 * n;
+  const int threads = 128;
+  qpb::swing_kernel<<<(unsigned)((nlegs + threads - 1) / threads), threads, 0, stream>>>(h->d_params, h->d_gains, d_states,
+                                                                                        d_swing, d_out, nlegs);
+  h->launches.fetch_add(1, std::memory_order_relaxed);
+  QPB_CUDA(cudaGetLastError());
+  return QPB_SUCCESS;
+}
+
+// Host-buffer pipeline shared by qpb_control_batch_host and qpb_tick_batch_host: stages of records are uploaded,
+// solved and downloaded on a ring of streams so the three overlap.
+int host_pipeline(qpb_handle* h, int64_t n, const qpb_state_rec* h_states, const qpb_swing_rec* h_swing, qpb_out_rec* h_out) {
+  if (n == 0) return QPB_SUCCESS;
+  DeviceGuard guard(h->device);
+  if (!guard.ok) return fail(QPB_ERR_CUDA, "cudaSetDevice failed");
+  for (int s = 0; s < kHostSlots; s++) {  // lazily create the pipeline
+    if (!h->streams[s]) QPB_CUDA(cudaStreamCreateWithFlags(&h->streams[s], cudaStreamNonBlocking));
+    if (!h->d_in[s]) QPB_CUDA(cudaMalloc(&h->d_in[s], kHostChunkMax * sizeof(qpb_state_rec)));
+    if (!h->d_out[s]) QPB_CUDA(cudaMalloc(&h->d_out[s], kHostChunkMax * sizeof(qpb_out_rec)));
+    if (h_swing && !h->d_sw[s]) QPB_CUDA(cudaMalloc(&h->d_sw[s], kHostChunkMax * sizeof(qpb_swing_rec)));
+  }
+  int slot = 0;
+  // Stage sizes halve towards the end of the batch so the last kernel + download (the part of the pipeline that
+  // cannot overlap an upload) is short.
+  const int64_t chunk = h->host_chunk, min_chunk = 1024;
+  for (int64_t lo = 0, m = 0; lo < n; lo += m, slot = (slot + 1) % kHostSlots) {
+    const int64_t left = n - lo;
+    m = left / 2 > chunk ? chunk : (left / 2 > min_chunk ? left / 2 : (left < min_chunk * 2 ? left : min_chunk));
+    if (m > chunk) m = chunk;
+    cudaStream_t st = h->streams[slot];
+    QPB_CUDA(cudaMemcpyAsync(h->d_in[slot], h_states + lo, m * sizeof(qpb_state_rec), cudaMemcpyHostToDevice, st));
+    if (h_swing)
+      QPB_CUDA(cudaMemcpyAsync(h->d_sw[slot], h_swing + lo, m * sizeof(qpb_swing_rec), cudaMemcpyHostToDevice, st));
+    qpb::PackedIO io{ h->d_in[slot], h->d_out[slot] };
+    int rc = launch_balance(h, io, m, h->ctas_per_sm_packed, st);
+    if (rc == QPB_SUCCESS && h_swing) rc = launch_swing(h, m, h->d_in[slot], h->d_sw[slot], h->d_out[slot], st);
+    if (rc != QPB_SUCCESS) return rc;
+    QPB_CUDA(cudaMemcpyAsync(h_out + lo, h->d_out[slot], m * sizeof(qpb_out_rec), cudaMemcpyDeviceToHost, st));
+  }
+  for (int s = 0; s < kHostSlots; s++) QPB_CUDA(cudaStreamSynchronize(h->streams[s]));
   return QPB_SUCCESS;
 }
 
@@ -186,6 +236,11 @@ int qpb_create(const qpb_params* params, int device, qpb_handle** out) {
   cudaError_t e = cudaGetDeviceProperties(&prop, device);
   if (e == cudaSuccess) e = cudaMalloc(&h->d_params, sizeof(qpb_params));
   if (e == cudaSuccess) e = cudaMemcpy(h->d_params, params, sizeof(qpb_params), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMalloc(&h->d_gains, sizeof(qpb_joint_gains));
+  if (e == cudaSuccess) {
+    const qpb_joint_gains g = { { 0.0, 0.0, 0.0 }, { 40.0, 40.0, 50.0 }, { 1.0, 1.0, 1.0 } };  // mit_cheetah_config.yaml:50-53
+    e = cudaMemcpy(h->d_gains, &g, sizeof(g), cudaMemcpyHostToDevice);
+  }
   if (e == cudaSuccess) e = cudaMalloc(&h->d_tickets, kTicketSlots * sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaMemset(h->d_tickets, 0, kTicketSlots * sizeof(unsigned long long));
   if (e == cudaSuccess)
@@ -205,6 +260,7 @@ int qpb_create(const qpb_params* params, int device, qpb_handle** out) {
     const std::string msg = std::string("qpb_create: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "kernel does not fit");
     if (h->d_params) cudaFree(h->d_params);
     if (h->d_tickets) cudaFree(h->d_tickets);
+    if (h->d_gains) cudaFree(h->d_gains);
     delete h;
     return fail(QPB_ERR_CUDA, msg);
   }
@@ -228,9 +284,11 @@ int qpb_destroy(qpb_handle* h) {
     if (h->streams[s]) cudaStreamDestroy(h->streams[s]);
     if (h->d_in[s]) cudaFree(h->d_in[s]);
     if (h->d_out[s]) cudaFree(h->d_out[s]);
+    if (h->d_sw[s]) cudaFree(h->d_sw[s]);
   }
   if (h->d_params) cudaFree(h->d_params);
   if (h->d_tickets) cudaFree(h->d_tickets);
+  if (h->d_gains) cudaFree(h->d_gains);
   delete h;
   return QPB_SUCCESS;
 }
@@ -264,31 +322,40 @@ int qpb_control_batch(qpb_handle* h, int64_t n, const double* Rwb, const double*
 int qpb_control_batch_host(qpb_handle* h, int64_t n, const qpb_state_rec* h_states, qpb_out_rec* h_out) {
   if (!h || n < 0 || (n > 0 && (!h_states || !h_out)))
     return fail(QPB_ERR_INVALID_ARG, "qpb_control_batch_host: bad argument");
-  if (n == 0) return QPB_SUCCESS;
+  return host_pipeline(h, n, h_states, nullptr, h_out);
+}
+
+int qpb_set_joint_gains(qpb_handle* h, const qpb_joint_gains* gains) {
+  if (!h || !gains) return fail(QPB_ERR_INVALID_ARG, "qpb_set_joint_gains: null pointer");
+  const double* g = reinterpret_cast<const double*>(gains);
+  for (int i = 0; i < 9; i++)
+    if (!std::isfinite(g[i])) return fail(QPB_ERR_BAD_PARAMS, "qpb_set_joint_gains: non-finite gain");
   DeviceGuard guard(h->device);
   if (!guard.ok) return fail(QPB_ERR_CUDA, "cudaSetDevice failed");
-  for (int s = 0; s < kHostSlots; s++) {  // lazily create the pipeline
-    if (!h->streams[s]) QPB_CUDA(cudaStreamCreateWithFlags(&h->streams[s], cudaStreamNonBlocking));
-    if (!h->d_in[s]) QPB_CUDA(cudaMalloc(&h->d_in[s], kHostChunkMax * sizeof(qpb_state_rec)));
-    if (!h->d_out[s]) QPB_CUDA(cudaMalloc(&h->d_out[s], kHostChunkMax * sizeof(qpb_out_rec)));
-  }
-  int slot = 0;
-  // Stage sizes halve towards the end of the batch so the last kernel + download (the part of the pipeline that
-  // cannot overlap an upload) is short.
-  const int64_t chunk = h->host_chunk, min_chunk = 1024;
-  for (int64_t lo = 0, m = 0; lo < n; lo += m, slot = (slot + 1) % kHostSlots) {
-    const int64_t left = n - lo;
-    m = left / 2 > chunk ? chunk : (left / 2 > min_chunk ? left / 2 : (left < min_chunk * 2 ? left : min_chunk));
-    if (m > chunk) m = chunk;
-    cudaStream_t st = h->streams[slot];
-    QPB_CUDA(cudaMemcpyAsync(h->d_in[slot], h_states + lo, m * sizeof(qpb_state_rec), cudaMemcpyHostToDevice, st));
-    qpb::PackedIO io{ h->d_in[slot], h->d_out[slot] };
-    const int rc = launch_balance(h, io, m, h->ctas_per_sm_packed, st);
-    if (rc != QPB_SUCCESS) return rc;
-    QPB_CUDA(cudaMemcpyAsync(h_out + lo, h->d_out[slot], m * sizeof(qpb_out_rec), cudaMemcpyDeviceToHost, st));
-  }
-  for (int s = 0; s < kHostSlots; s++) QPB_CUDA(cudaStreamSynchronize(h->streams[s]));
+  QPB_CUDA(cudaDeviceSynchronize());  // earlier launches may still read the old gains
+  QPB_CUDA(cudaMemcpy(h->d_gains, gains, sizeof(qpb_joint_gains), cudaMemcpyHostToDevice));
   return QPB_SUCCESS;
+}
+
+int qpb_tick_batch_packed(qpb_handle* h, int64_t n, const qpb_state_rec* d_states, const qpb_swing_rec* d_swing,
+                          qpb_out_rec* d_out, void* stream) {
+  if (!h || n < 0 || (n > 0 && (!d_states || !d_swing || !d_out)))
+    return fail(QPB_ERR_INVALID_ARG, "qpb_tick_batch_packed: bad argument");
+  if ((reinterpret_cast<uintptr_t>(d_states) & 15u) || (reinterpret_cast<uintptr_t>(d_out) & 15u))
+    return fail(QPB_ERR_INVALID_ARG, "qpb_tick_batch_packed: records must be 16-byte aligned");
+  DeviceGuard guard(h->device);
+  if (!guard.ok) return fail(QPB_ERR_CUDA, "cudaSetDevice failed");
+  qpb::PackedIO io{ d_states, d_out };
+  const int rc = launch_balance(h, io, n, h->ctas_per_sm_packed, static_cast<cudaStream_t>(stream));
+  if (rc != QPB_SUCCESS) return rc;
+  return launch_swing(h, n, d_states, d_swing, d_out, static_cast<cudaStream_t>(stream));
+}
+
+int qpb_tick_batch_host(qpb_handle* h, int64_t n, const qpb_state_rec* h_states, const qpb_swing_rec* h_swing,
+                        qpb_out_rec* h_out) {
+  if (!h || n < 0 || (n > 0 && (!h_states || !h_swing || !h_out)))
+    return fail(QPB_ERR_INVALID_ARG, "qpb_tick_batch_host: bad argument");
+  return host_pipeline(h, n, h_states, h_swing, h_out);
 }
 
 int qpb_jt_batch(qpb_handle* h, int64_t n, const double* q, const double* grf_body, const uint8_t* contact,

@@ -9,7 +9,7 @@ import os
 
 import numpy as np
 
-from .records import OUT_DTYPE, STATE_DTYPE, Params
+from .records import OUT_DTYPE, STATE_DTYPE, SWING_DTYPE, JointGains, Params
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("QPB_LIB") or os.path.join(_HERE, "libqpb200.so")  # QPB_LIB: experiment builds
@@ -27,6 +27,9 @@ EXPORTS = (
     "qpb_fk_batch",
     "qpb_jt_batch_host",
     "qpb_fk_batch_host",
+    "qpb_set_joint_gains",
+    "qpb_tick_batch_packed",
+    "qpb_tick_batch_host",
     "qpb_host_alloc",
     "qpb_host_free",
     "qpb_launch_count",
@@ -60,6 +63,9 @@ def load():
     L.qpb_fk_batch.argtypes = [vp, i64, dp, dp, vp]
     L.qpb_jt_batch_host.argtypes = [vp, i64, dp, dp, dp, dp]
     L.qpb_fk_batch_host.argtypes = [vp, i64, dp, dp]
+    L.qpb_set_joint_gains.argtypes = [vp, ctypes.POINTER(JointGains)]
+    L.qpb_tick_batch_packed.argtypes = [vp, i64, vp, vp, vp, vp]
+    L.qpb_tick_batch_host.argtypes = [vp, i64, vp, vp, vp]
     L.qpb_host_alloc.argtypes = [ctypes.POINTER(vp), ctypes.c_size_t]
     L.qpb_host_free.argtypes = [vp]
     L.qpb_launch_count.argtypes = [vp]
@@ -156,6 +162,21 @@ class BalanceSolver:
             out = np.empty(states.shape[0], dtype=OUT_DTYPE)
         assert out.dtype == OUT_DTYPE and out.shape[0] == states.shape[0] and out.flags.c_contiguous
         _check(load().qpb_control_batch_host(self._h, states.shape[0], states.ctypes.data, out.ctypes.data), "qpb_control_batch_host")
+        return out
+
+    # -- whole control tick: balance QP for stance legs + joint PD for swing legs (commander_node.cpp:482-533) --
+    def set_joint_gains(self, gains: JointGains):
+        _check(load().qpb_set_joint_gains(self._h, ctypes.byref(gains)), "qpb_set_joint_gains")
+
+    def tick_packed(self, d_states, d_swing, d_out, n, stream=None):
+        _check(load().qpb_tick_batch_packed(self._h, int(n), _ptr(d_states), _ptr(d_swing), _ptr(d_out), stream), "qpb_tick_batch_packed")
+
+    def tick_host(self, states: np.ndarray, swing: np.ndarray, out: np.ndarray = None):
+        states, swing = np.ascontiguousarray(states), np.ascontiguousarray(swing)
+        assert states.dtype == STATE_DTYPE and swing.dtype == SWING_DTYPE and len(states) == len(swing)
+        if out is None:
+            out = np.empty(states.shape[0], dtype=OUT_DTYPE)
+        _check(load().qpb_tick_batch_host(self._h, states.shape[0], states.ctypes.data, swing.ctypes.data, out.ctypes.data), "qpb_tick_batch_host")
         return out
 
     def jt(self, n, q, grf, contact, tau, stream=None):

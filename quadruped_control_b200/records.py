@@ -108,3 +108,25 @@ def default_params(mu=0.8):
     p.link[:] = link
     p.tau_min, p.tau_max, p.clamp_tau, p.max_iter = -20.0, 20.0, 0, 200
     return p
+
+
+# ---- swing-leg half of the control tick ----------------------------------------
+# One item per robot: the reference foot states FootTrajectoryManager::referenceState returns for swing legs
+# (world frame, commander_node.cpp:487-488) and the measured joint velocities (JointStatesMap.qdot).
+SWING_DTYPE = np.dtype([("foot_ref_pos", "<f8", (12,)), ("foot_ref_vel", "<f8", (12,)), ("qdot", "<f8", (12,))])
+assert SWING_DTYPE.itemsize == 288
+
+
+class JointGains(ctypes.Structure):
+    """``qpb_joint_gains``: JointController(kff, kp, kd) (joint_controller.hpp; commander_node.cpp:341)."""
+
+    _fields_ = [("kff", ctypes.c_double * 3), ("kp", ctypes.c_double * 3), ("kd", ctypes.c_double * 3)]
+
+
+def default_joint_gains():
+    """joint_control/{kff,kp,kd} of mit_cheetah_config.yaml:50-53."""
+    g = JointGains()
+    g.kff[:] = [0.0, 0.0, 0.0]
+    g.kp[:] = [40.0, 40.0, 50.0]
+    g.kd[:] = [1.0, 1.0, 1.0]
+    return g

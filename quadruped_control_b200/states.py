@@ -147,3 +147,23 @@ CONFIGS = {
     "cfg3_mixed_1m": dict(n=1048576, seed=20260103, mu=0.6, masks="mixed"),
     "cfg5_mixed_8m": dict(n=8388608, seed=20260105, mu=0.6, masks="mixed"),
 }
+
+
+def generate_swing(S, seed, params: Params = None, reach=0.25):
+    """Swing-leg references for the states ``S``: for every leg a joint-space target
+    q + U(-reach, reach), mapped through FK to a body-frame foot position p_b and to the world frame as
+    p_w = R (p_b + x) -- the inverse of the reference's own transform ``Rwb' * p_w - x`` (commander_node.cpp:491) --
+    plus N(0, 0.5 m/s) reference velocities and N(0, 2 rad/s) measured joint velocities."""
+    from .records import SWING_DTYPE
+
+    params = params or default_params()
+    rng = np.random.Generator(np.random.Philox(key=int(seed)))
+    n = len(S)
+    sw = np.zeros(n, dtype=SWING_DTYPE)
+    q_ref = S["q"] + rng.uniform(-reach, reach, size=(n, 12))
+    pb = forward_kinematics(q_ref, params).reshape(n, 4, 3)
+    R = S["Rwb"].reshape(n, 3, 3)
+    sw["foot_ref_pos"] = np.einsum("nij,nlj->nli", R, pb + S["x"][:, None, :]).reshape(n, 12)
+    sw["foot_ref_vel"] = rng.normal(0.0, 0.5, size=(n, 12))
+    sw["qdot"] = rng.normal(0.0, 2.0, size=(n, 12))
+    return sw
