@@ -55,6 +55,7 @@ bool is_sympd(const double* A, int n) {
 
 constexpr int kHostSlots = 6;          // streams / staging slots of the host-buffer pipeline
 constexpr int64_t kHostChunkMax = 16384;  // capacity of a pipeline stage (8 MiB in, 4 MiB out)
+constexpr int64_t kMaxRecordsPerLaunch = (int64_t)1 << 31;  // the kernels index work items with 32 bits
 constexpr uint32_t kTicketSlots = 4096;  // ring of work counters; a launch re-zeroes the slot half a ring ahead
 
 }  // namespace
@@ -97,6 +98,7 @@ struct DeviceGuard {
 template <class IO>
 int launch_balance(qpb_handle* h, const IO& io, int64_t n, int ctas_per_sm, cudaStream_t stream) {
   if (n == 0) return QPB_SUCCESS;
+  if (n > kMaxRecordsPerLaunch) return fail(QPB_ERR_INVALID_ARG, "more than 2^31 records in one call: split the batch");
   const int per_warp = h->qps_per_warp;  // 1: one warp per QP; 2: two QPs per warp (half-warp kernel)
   const int64_t units = (n + per_warp - 1) / per_warp;
   const int64_t want = (units + qpb::WARPS_PER_CTA - 1) / qpb::WARPS_PER_CTA;

@@ -77,9 +77,10 @@ balance_qp_kernel16(const qpb_params* __restrict__ gparams, IO io, int64_t n, un
   const int l = lane & 15;         // lane within the half
   const int hb = lane & 16;        // first lane of this half
   HalfSmem& hs = hsm[2 * wib + (lane >> 4)];
-  const int64_t gw = (int64_t)blockIdx.x * WARPS_PER_CTA + wib;
-  const int64_t nwarps = (int64_t)gridDim.x * WARPS_PER_CTA;
-  const int64_t npairs = (n + 1) >> 1;
+  // 32-bit work indices (qpb_api.cu bounds n per launch): fewer live registers in the solver loop
+  const uint32_t gw = blockIdx.x * WARPS_PER_CTA + wib;
+  const uint32_t nwarps = gridDim.x * WARPS_PER_CTA;
+  const uint32_t npairs = (uint32_t)((n + 1) >> 1);
 
   const bool isP = l < 12;  // variable lane: projector row, working-set slot, pseudo-inverse row
   const int vi = isP ? l : 0;
@@ -93,13 +94,11 @@ balance_qp_kernel16(const qpb_params* __restrict__ gparams, IO io, int64_t n, un
   const double bB = ax < 2 ? 0.0 : -P.fzmax;
   // a row is violated when its slack is below -1e-9 (1 + |bound|); one value per lane (the larger bound of its two rows)
   const double ntol = ax < 2 ? -1e-9 : -1e-9 * (1.0 + fmax(fabs(P.fzmin), fabs(P.fzmax)));
-  const int max_iter = P.max_iter;
-
-  int64_t pair = gw;
+  uint32_t pair = gw;
   while (pair < npairs) {
-    unsigned long long next_ticket = 0;
-    if (lane == 0) next_ticket = atomicAdd(ticket, 1ULL);
-    const int64_t rec = 2 * pair + (lane >> 4);
+    uint32_t next_ticket = 0;
+    if (lane == 0) next_ticket = (uint32_t)atomicAdd(ticket, 1ULL);
+    const int64_t rec = 2 * (int64_t)pair + (lane >> 4);
     const bool have = rec < n;  // the last pair may be half empty
     // ---- load + stage ---------------------------------------------------------------------------
     double2 va = make_double2(0.0, 0.0), vb = make_double2(0.0, 0.0);
@@ -292,7 +291,7 @@ balance_qp_kernel16(const qpb_params* __restrict__ gparams, IO io, int64_t n, un
       const uint32_t keyB = vB ? (((uint32_t)__double2hiint(sB) & ~31u) | (uint32_t)(2 * l + 1)) : 0u;
       const uint32_t kmax = half_max_u32(max(keyA, keyB));
       const bool fresh = p < 0;
-      if (!done && ((fresh && kmax == 0u) || iters >= max_iter)) {
+      if (!done && ((fresh && kmax == 0u) || iters >= P.max_iter)) {
         if (!(fresh && kmax == 0u)) status = QPB_MAX_ITER;
         done = true;
       }
@@ -418,7 +417,7 @@ balance_qp_kernel16(const qpb_params* __restrict__ gparams, IO io, int64_t n, un
     if (P.clamp_tau) tau = fmin(fmax(tau, P.tau_min), P.tau_max);
     if (!(good && stance)) tau = 0.0;
     if (have) store_rec(io, rec, l, fb, tau, status, iters);
-    pair = nwarps + (int64_t)__shfl_sync(FULL, next_ticket, 0);
+    pair = nwarps + __shfl_sync(FULL, next_ticket, 0);
   }
 }
 
