@@ -4,8 +4,8 @@
 // changes is the mapping: the 12 variable lanes of a half-warp own BOTH the projector row (Mp) and the
 // working-set slot / pseudo-inverse row (Mn) of their QP, lane 12 of the half computes zeta, and the
 // two halves run in lock step, so every bookkeeping instruction (slack tests, decode, step logic,
-// shared-memory broadcasts) is paid once for two problems.  Per-half reductions are 4-step shuffle
-// butterflies (REDUX is warp-wide).  A half that finishes early idles until its partner is done.
+// shared-memory broadcasts) is paid once for two problems.  Per-half reductions are pairs of warp-wide
+// REDUX with the other half's lanes neutralised.  A half that finishes early idles until its partner is done.
 #pragma once
 
 #include "qpb_kernel.cuh"
@@ -22,14 +22,16 @@ struct __align__(16) HalfSmem {
 
 __device__ __forceinline__ double shfl16(double v, int src) { return __shfl_sync(FULL, v, src, 16); }
 
-// Per-half reductions as 4-step butterflies.  (REDUX with a half-warp member mask was measured 8 % slower:
-// the compiler serialises the two member masks.)
-__device__ __forceinline__ uint32_t half_max_u32(uint32_t v) {
+// Per-half reductions.  Measured on config 2: 4-step shuffle butterflies 1.82e8 QP/s; REDUX with a half-warp
+// member mask 1.69e8 (the compiler serialises the two masks); two full-mask REDUX with the other half
+// neutralised 1.92e8 -- the default.
+#ifdef QPB_HALF_BUTTERFLY
+__device__ __forceinline__ uint32_t half_max_u32(uint32_t v, bool) {
 #pragma unroll
   for (int o = 8; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(FULL, v, o, 16));
   return v;
 }
-__device__ __forceinline__ double half_min_f64(double v) {
+__device__ __forceinline__ double half_min_f64(double v, bool) {
 #pragma unroll
   for (int o = 8; o > 0; o >>= 1) {
     const double w = __shfl_xor_sync(FULL, v, o, 16);
@@ -37,6 +39,26 @@ __device__ __forceinline__ double half_min_f64(double v) {
   }
   return v;
 }
+#else
+// Two full-mask REDUX per reduction, one per half with the other half's lanes neutralised: the results land in
+// uniform registers and the two are independent, so the chain is ~1 REDUX deep instead of 4 dependent shuffles.
+__device__ __forceinline__ uint32_t half_max_u32(uint32_t v, bool upper) {
+  const uint32_t a = __reduce_max_sync(FULL, upper ? 0u : v);
+  const uint32_t b = __reduce_max_sync(FULL, upper ? v : 0u);
+  return upper ? b : a;
+}
+// exact minimum of non-negative doubles (or +inf): their bit patterns order like unsigned integers
+__device__ __forceinline__ double half_min_f64(double v, bool upper) {
+  const uint32_t hi = (uint32_t)__double2hiint(v);
+  const uint32_t ah = __reduce_min_sync(FULL, upper ? 0xffffffffu : hi);
+  const uint32_t bh = __reduce_min_sync(FULL, upper ? hi : 0xffffffffu);
+  const uint32_t mh = upper ? bh : ah;
+  const uint32_t lo = (hi == mh) ? (uint32_t)__double2loint(v) : 0xffffffffu;
+  const uint32_t al = __reduce_min_sync(FULL, upper ? 0xffffffffu : lo);
+  const uint32_t bl = __reduce_min_sync(FULL, upper ? lo : 0xffffffffu);
+  return __hiloint2double((int)mh, (int)(upper ? bl : al));
+}
+#endif
 
 // 512-B record of this half: lane l holds slots {2l, 2l+1} (a) and {32+2l, 33+2l} (b)
 __device__ __forceinline__ void load_rec16(const PackedIO& io, int64_t rec, int l, double2& a, double2& b) {
@@ -289,7 +311,7 @@ balance_qp_kernel16(const qpb_params* __restrict__ gparams, IO io, int64_t n, un
       const bool vB = stance && !(act2 & 2u) && (sB < ntol);
       const uint32_t keyA = vA ? (((uint32_t)__double2hiint(sA) & ~31u) | (uint32_t)(2 * l)) : 0u;
       const uint32_t keyB = vB ? (((uint32_t)__double2hiint(sB) & ~31u) | (uint32_t)(2 * l + 1)) : 0u;
-      const uint32_t kmax = half_max_u32(max(keyA, keyB));
+      const uint32_t kmax = half_max_u32(max(keyA, keyB), hb != 0);
       const bool fresh = p < 0;
       if (!done && ((fresh && kmax == 0u) || iters >= P.max_iter)) {
         if (!(fresh && kmax == 0u)) status = QPB_MAX_ITER;
@@ -334,7 +356,7 @@ balance_qp_kernel16(const qpb_params* __restrict__ gparams, IO io, int64_t n, un
       const double uu = (__double2hiint(u) < 0) ? 0.0 : u;
       const double INF = __longlong_as_double(0x7ff0000000000000LL);
       const double ratio = cand ? uu * rcp_fast(mvN) : INF;
-      const double t1 = half_min_f64(ratio);
+      const double t1 = half_min_f64(ratio, hb != 0);
       const bool has1 = t1 < INF;
       const uint32_t wb = (__ballot_sync(FULL, cand && ratio == t1) >> hb) & 0xffffu;
       const int kl = __ffs(wb) - 1;  // lane (within the half) of the blocking slot, -1 if none
