@@ -520,6 +520,10 @@ balance_qp_kernel(const qpb_params* __restrict__ gparams, IO io, int64_t n, unsi
             // Row p lies in the span of the working set and no multiplier can give way.  The feasible set is
             // never empty (qpb_create), so this is rounding making the twin of an active row look violated
             // (e.g. fzmin == fzmax): the row holds to rounding, set it aside.
+            if (sp < -1e-6 * (1.0 + fmax(fabs(P.fzmin), fabs(P.fzmax)))) {  // not a rounding artefact: give up loudly
+              status = QPB_BAD_INPUT;
+              break;
+            }
             ignore |= 1u << p;
             p = -1;
             continue;

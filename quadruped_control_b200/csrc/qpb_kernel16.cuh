@@ -365,6 +365,10 @@ balance_qp_kernel16(const qpb_params* __restrict__ gparams, IO io, int64_t n, un
       // violated (e.g. fzmin == fzmax).  The row is satisfied to rounding: set it aside instead of failing.
       const bool skip = !done && dep && !has1;
       if (skip) {
+        if (sp < -1e-6 * (1.0 + fmax(fabs(P.fzmin), fabs(P.fzmax)))) {  // not a rounding artefact: give up loudly
+          status = QPB_BAD_INPUT;
+          done = true;
+        }
         ignore |= 1u << pp;
         p = -1;
       }
