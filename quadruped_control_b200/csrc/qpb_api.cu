@@ -122,10 +122,9 @@ int launch_balance(qpb_handle* h, const IO& io, int64_t n, int ctas_per_sm, cuda
 int launch_swing(qpb_handle* h, int64_t n, const qpb_state_rec* d_states, const qpb_swing_rec* d_swing, qpb_out_rec* d_out,
                  cudaStream_t stream) {
   if (n == 0) return QPB_SUCCESS;
-  const int64_t nlegs = 4 * n;
   const int threads = 128;
-  qpb::swing_kernel<<<(unsigned)((nlegs + threads - 1) / threads), threads, 0, stream>>>(h->d_params, h->d_gains, d_states,
-                                                                                        d_swing, d_out, nlegs);
+  qpb::swing_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, stream>>>(h->d_params, h->d_gains, d_states,
+                                                                                    d_swing, d_out, n);
   h->launches.fetch_add(1, std::memory_order_relaxed);
   QPB_CUDA(cudaGetLastError());
   return QPB_SUCCESS;
