@@ -144,52 +144,52 @@ __global__ void swing_kernel(const qpb_params* __restrict__ P, const qpb_joint_g
   if (todo == 0u) return;
   if (out[rob].status == QPB_BAD_INPUT) return;  // nothing is commanded for a broken state
   for (; todo != 0u; todo &= todo - 1u) {
-  const int leg = __ffs(todo) - 1;
-  const qpb_swing_rec& sw = swing[rob];
-  double pb[3], vb[3];
+    const int leg = __ffs(todo) - 1;
+    const qpb_swing_rec& sw = swing[rob];
+    double pb[3], vb[3];
 #pragma unroll
-  for (int a = 0; a < 3; a++) {  // commander_node.cpp:491-492: Rwb' p - x (sic), Rwb' v
-    pb[a] = s.Rwb[a] * sw.foot_ref_pos[3 * leg] + s.Rwb[3 + a] * sw.foot_ref_pos[3 * leg + 1] +
-            s.Rwb[6 + a] * sw.foot_ref_pos[3 * leg + 2] - s.x[a];
-    vb[a] = s.Rwb[a] * sw.foot_ref_vel[3 * leg] + s.Rwb[3 + a] * sw.foot_ref_vel[3 * leg + 1] +
-            s.Rwb[6 + a] * sw.foot_ref_vel[3 * leg + 2];
-  }
-  // legInverseKinematics, kinematics.cpp:117-160
-  const double x = pb[0] - P->hip_offset[3 * leg], y = pb[1] - P->hip_offset[3 * leg + 1], z = pb[2] - P->hip_offset[3 * leg + 2];
-  const double sl1 = P->link[3 * leg], sl2 = P->link[3 * leg + 1], sl3 = P->link[3 * leg + 2];
-  const double l1 = fabs(sl1), l2 = fabs(sl2), l3 = fabs(sl3);
-  double d = (x * x + y * y + z * z - l1 * l1 - l2 * l2 - l3 * l3) / (2.0 * l2 * l3);
-  if (d > 1.0) d = 1.0;
-  double sc = y * y + z * z - l1 * l1;
-  if (sc < 0.0) sc = 0.0;
-  const double rsc = sqrt(sc);
-  double q0;
-  if (sl1 < 0.0) q0 = atan2(z, y) + atan2(rsc, -l1);  // right legs
-  else q0 = -(atan2(z, -y) + atan2(rsc, -l1));
-  const double q2 = atan2(-sqrt(1.0 - d * d), d);
-  double s3, c3;
-  sincos(q2, &s3, &c3);
-  const double q1 = -atan2(x, rsc) - atan2(l3 * s3, l2 + l3 * c3);
-  // legJacobian at the reference pose, kinematics.cpp:162-188
-  double s1, c1, s2, c2, s23, c23;
-  sincos(q0, &s1, &c1);
-  sincos(q1, &s2, &c2);
-  sincos(q1 + q2, &s23, &c23);
-  const double h = sl2 * s2 + sl3 * s23;
-  const double J[9] = { 0.0, sl2 * c2 + sl3 * c23, sl3 * c23,
-                        -sl1 * s1 - sl2 * c1 * c2 - sl3 * c1 * c23, h * s1, sl3 * s1 * s23,
-                        sl1 * c1 - sl2 * s1 * c2 - sl3 * s1 * c23, -h * c1, -sl3 * s23 * c1 };
-  double Ji[9];
-  inv3_or_pinv(J, Ji);  // legJacobianInverse, kinematics.cpp:190-204
-  const double qr[3] = { q0, q1, q2 };
+    for (int a = 0; a < 3; a++) {  // commander_node.cpp:491-492: Rwb' p - x (sic), Rwb' v
+      pb[a] = s.Rwb[a] * sw.foot_ref_pos[3 * leg] + s.Rwb[3 + a] * sw.foot_ref_pos[3 * leg + 1] +
+              s.Rwb[6 + a] * sw.foot_ref_pos[3 * leg + 2] - s.x[a];
+      vb[a] = s.Rwb[a] * sw.foot_ref_vel[3 * leg] + s.Rwb[3 + a] * sw.foot_ref_vel[3 * leg + 1] +
+              s.Rwb[6 + a] * sw.foot_ref_vel[3 * leg + 2];
+    }
+    // legInverseKinematics, kinematics.cpp:117-160
+    const double x = pb[0] - P->hip_offset[3 * leg], y = pb[1] - P->hip_offset[3 * leg + 1], z = pb[2] - P->hip_offset[3 * leg + 2];
+    const double sl1 = P->link[3 * leg], sl2 = P->link[3 * leg + 1], sl3 = P->link[3 * leg + 2];
+    const double l1 = fabs(sl1), l2 = fabs(sl2), l3 = fabs(sl3);
+    double d = (x * x + y * y + z * z - l1 * l1 - l2 * l2 - l3 * l3) / (2.0 * l2 * l3);
+    if (d > 1.0) d = 1.0;
+    double sc = y * y + z * z - l1 * l1;
+    if (sc < 0.0) sc = 0.0;
+    const double rsc = sqrt(sc);
+    double q0;
+    if (sl1 < 0.0) q0 = atan2(z, y) + atan2(rsc, -l1);  // right legs
+    else q0 = -(atan2(z, -y) + atan2(rsc, -l1));
+    const double q2 = atan2(-sqrt(1.0 - d * d), d);
+    double s3, c3;
+    sincos(q2, &s3, &c3);
+    const double q1 = -atan2(x, rsc) - atan2(l3 * s3, l2 + l3 * c3);
+    // legJacobian at the reference pose, kinematics.cpp:162-188
+    double s1, c1, s2, c2, s23, c23;
+    sincos(q0, &s1, &c1);
+    sincos(q1, &s2, &c2);
+    sincos(q1 + q2, &s23, &c23);
+    const double h = sl2 * s2 + sl3 * s23;
+    const double J[9] = { 0.0, sl2 * c2 + sl3 * c23, sl3 * c23,
+                          -sl1 * s1 - sl2 * c1 * c2 - sl3 * c1 * c23, h * s1, sl3 * s1 * s23,
+                          sl1 * c1 - sl2 * s1 * c2 - sl3 * s1 * c23, -h * c1, -sl3 * s23 * c1 };
+    double Ji[9];
+    inv3_or_pinv(J, Ji);  // legJacobianInverse, kinematics.cpp:190-204
+    const double qr[3] = { q0, q1, q2 };
 #pragma unroll
-  for (int a = 0; a < 3; a++) {  // JointController::control, joint_controller.cpp:27-35
-    const double qdr = Ji[3 * a] * vb[0] + Ji[3 * a + 1] * vb[1] + Ji[3 * a + 2] * vb[2];
-    const double qe = wrap_pi(wrap_2pi(qr[a]) - wrap_2pi(s.q[3 * leg + a]));
-    double tau = G->kp[a] * qe + G->kd[a] * (qdr - sw.qdot[3 * leg + a]) + G->kff[a];
-    if (P->clamp_tau) tau = fmin(fmax(tau, P->tau_min), P->tau_max);  // commander_node.cpp:526
-    out[rob].tau[3 * leg + a] = tau;
-  }
+    for (int a = 0; a < 3; a++) {  // JointController::control, joint_controller.cpp:27-35
+      const double qdr = Ji[3 * a] * vb[0] + Ji[3 * a + 1] * vb[1] + Ji[3 * a + 2] * vb[2];
+      const double qe = wrap_pi(wrap_2pi(qr[a]) - wrap_2pi(s.q[3 * leg + a]));
+      double tau = G->kp[a] * qe + G->kd[a] * (qdr - sw.qdot[3 * leg + a]) + G->kff[a];
+      if (P->clamp_tau) tau = fmin(fmax(tau, P->tau_min), P->tau_max);  // commander_node.cpp:526
+      out[rob].tau[3 * leg + a] = tau;
+    }
   }
 }
 
