@@ -363,12 +363,12 @@ def test_degenerate_and_extreme_parameter_regimes(built):
 
 
 def test_randomised_parameter_sets(built):
-    """tools/fuzz_gpu.py: random SPD S/W, inertia, gains, mu in [0.02, 3], mass, fz bounds (incl. fzmin = 0 and
+    """tests/tools/fuzz_gpu.py: random SPD S/W, inertia, gains, mu in [0.02, 3], mass, fz bounds (incl. fzmin = 0 and
     fzmin == fzmax), every profile and mask family, both kernel mappings -- all against the oracle."""
     import sys
 
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    res = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_gpu.py"), "10", "1024", "77"],
+    res = subprocess.run([sys.executable, os.path.join(root, "tests", "tools", "fuzz_gpu.py"), "10", "1024", "77"],
                          capture_output=True, text=True, timeout=900)
     assert res.returncode == 0, res.stderr[-2000:]
     last = res.stdout.strip().splitlines()[-1]

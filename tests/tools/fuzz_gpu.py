@@ -1,6 +1,6 @@
 """Randomised parameter fuzz: CUDA path (both kernel mappings) vs the CPU oracle."""
 import sys, os, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, oracle
 from quadruped_control_b200 import default_params, states, lib
 trials = int(sys.argv[1]) if len(sys.argv) > 1 else 40

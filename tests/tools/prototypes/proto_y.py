@@ -1,6 +1,6 @@
 """y-space (whitened) operator-form dual active set: y = L'x, Hessian = I."""
 import numpy as np, sys
-sys.path.insert(0,"/root/repo"); sys.path.insert(0,"/root/repo/tools/prototypes")
+sys.path.insert(0,"/root/repo"); sys.path.insert(0,"/root/repo/tests/tools/prototypes")
 import oracle
 from quadruped_control_b200 import default_params, states
 from proto_gi import cons_table

@@ -1,6 +1,6 @@
 """Times the packed balance kernel of the library named by $QPB_LIB on one workload (CUDA events)."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 from quadruped_control_b200 import lib, states, default_params, OUT_DTYPE
 from bench import WORKLOADS
