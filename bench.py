@@ -119,8 +119,9 @@ def _cpu_arm():
     return "port", oracle.control_batch, "oracle port (plain C restatement)"
 
 
-def cpu_baseline(params, S, budget_s=12.0):
-    """The reference CPU path on the host cores over a bounded sample of the workload."""
+def cpu_baseline(params, S, budget_s=12.0, check=None):
+    """The reference CPU path on the host cores over a bounded sample of the workload.  ``check`` = (states, GPU
+    outputs): their max relative GRF error against the oracle is returned beside the baseline."""
     import oracle
 
     kind, fn, desc = _cpu_arm()
@@ -142,9 +143,13 @@ def cpu_baseline(params, S, budget_s=12.0):
     t0 = time.perf_counter()
     oracle.control_batch(params, S[:n], cores)
     port = n / (time.perf_counter() - t0)
+    err = None
+    if check is not None:
+        ref = oracle.control_batch(params, check[0], cores)
+        err = float((np.abs(check[1]["grf_body"] - ref["grf_body"]).max(axis=1) / np.maximum(np.abs(ref["grf_body"]).max(axis=1), 1.0)).max())
     return {"value": best, "unit": UNIT, "cores": cores, "kind": kind,
             "sample": f"first {n} records of the workload, best of 3, {cores} threads; {desc}; 1 thread: {one:.0f} QP/s",
-            "one_thread": one, "c_port_all_cores": port}
+            "one_thread": one, "c_port_all_cores": port}, err
 
 
 def run_reference(args):
@@ -268,13 +273,10 @@ def run_ours(args):
     e2e_checksum_ok = bool((pin_out.array["status"] == 0).all())
 
     if rank == 0:
-        import oracle
-
-        sample = np.ascontiguousarray(host_batches[(args.steps - 1) % n_rot][:: max(1, n // 2048)])
-        ref = oracle.control_batch(params, sample, os.cpu_count() or 1)
-        got = np.ascontiguousarray(last[:: max(1, n // 2048)])
-        err = float((np.abs(got["grf_body"] - ref["grf_body"]).max(axis=1) / np.maximum(np.abs(ref["grf_body"]).max(axis=1), 1.0)).max())
-        cpu = cpu_baseline(params, host_batches[0])
+        # the CPU-baseline leg also checks what was just timed against the oracle (strided sample of the last step)
+        stride = max(1, n // 2048)
+        cpu, err = cpu_baseline(params, host_batches[0], check=(np.ascontiguousarray(host_batches[(args.steps - 1) % n_rot][::stride]),
+                                                                np.ascontiguousarray(last[::stride])))
         peak, peak_src = measured_peak_hbm()
         kernel_ms = elapsed_ms / args.steps  # one kernel launch per step on the timed stream
         achieved = ALGO_BYTES_PER_QP * n / (kernel_ms * 1e-3) / 1e9
