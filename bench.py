@@ -296,7 +296,7 @@ def run_ours(args):
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_qps, "unit": UNIT, "h2d_bytes_per_step": n * STATE_DTYPE.itemsize,
                     "d2h_bytes_per_step": n * OUT_DTYPE.itemsize, "steps": e2e_steps, "ok": e2e_checksum_ok,
-                    "api": "qpb_control_batch_host (pinned host buffers, chunked H2D/kernel/D2H pipeline)"},
+                    "api": "qpb_control_batch_host (pinned host buffers; the kernel reads records and writes results over PCIe itself)"},
             "gpu_launches": int(tot_launches),
             "clocks": clocks,
         }

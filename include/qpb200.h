@@ -108,9 +108,9 @@ int qpb_control_batch(qpb_handle* h, int64_t n, const double* Rwb, const double*
                       const double* w_d, const double* feet_body, const uint8_t* contact, const double* q,
                       double* grf_body, double* tau, int32_t* status, void* stream);
 
-/* Host-buffer entry point: copies records to the device in chunks, solves, copies results back,
- * overlapping the three on internal streams; returns when h_out is complete.  Buffers may be
- * pageable; pinned ones (qpb_host_alloc) reach PCIe speed. */
+/* Host-buffer entry point; returns when h_out is complete.  Pinned buffers (qpb_host_alloc / cudaHostAlloc) are
+ * read and written by the kernel itself over PCIe in one launch; pageable buffers are copied to the device in
+ * chunks, solved and copied back, overlapping the three on internal streams. */
 int qpb_control_batch_host(qpb_handle* h, int64_t n, const qpb_state_rec* h_states, qpb_out_rec* h_out);
 
 /* jacobianTransposeControl() alone (kinematics.cpp:218-231): tau = J(q)^T f for stance legs,

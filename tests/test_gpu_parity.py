@@ -135,7 +135,14 @@ def test_pinned_host_buffers(solver06, params06):
     pin_out = lib.PinnedBuffer(n, OUT_DTYPE)
     pin_in.array[:] = S
     out = solver06.control_host(pin_in.array, pin_out.array)
-    assert out.tobytes() == solver06.control_host(S).tobytes()
+    staged = solver06.control_host(S)  # pageable buffers: the staged pipeline; pinned ones: read in place over PCIe
+    assert out.tobytes() == staged.tobytes()
+    # a window inside the pinned allocation, and pinned input with a pageable output (falls back to staging)
+    pin_out.array[:] = np.zeros(1, dtype=OUT_DTYPE)
+    solver06.control_host(pin_in.array[1001:30001], pin_out.array[1001:30001])
+    assert pin_out.array[1001:30001].tobytes() == staged[1001:30001].tobytes()
+    assert not pin_out.array[:1001]["grf_body"].any() and not pin_out.array[30001:]["grf_body"].any()
+    assert solver06.control_host(pin_in.array).tobytes() == staged.tobytes()
     pin_in.free()
     pin_out.free()
 
