@@ -161,6 +161,56 @@ int qpb_host_free(void* ptr);
 /* Number of CUDA kernels this handle has launched so far (for the benchmark's gpu_launches). */
 int64_t qpb_launch_count(const qpb_handle* h);
 
+/* ---- 10-step convex-MPC ground-reaction-force QP (BASELINE.json config 4) --------------
+ * The reference has NO code for this path (README.md:22-26 describes only the instantaneous QP of
+ * balance_controller.cpp), so there is no reference interface to cite: the formulation is the condensed
+ * single-rigid-body MPC of Di Carlo et al. (IROS 2018) with the reference's friction-pyramid rows
+ * (balance_controller.cpp:278-289) and bounds (:296-301 stance, :312-316 swing) on every foot and step.
+ *   state x = [roll pitch yaw | p | omega | v | g] (13), input u_k = 4 world-frame foot forces (RL FL RR FR)
+ *   psi_k = xref[k][2];  T_k = Rz(psi_k)^T;  I_k = Rz(psi_k) Ib Rz(psi_k)^T
+ *   Theta' = Theta + dt T_k omega;  p' = p + dt v;  omega' = omega + dt sum_i I_k^-1 (r_ki x f_i);
+ *   v' = v + dt (sum_i f_i / mass + e_z g);  g' = g
+ *   min sum_k (x_{k+1} - xref[k])' diag(Lw) (x_{k+1} - xref[k]) + alpha |u_k|^2
+ *   s.t. per foot and step: |fx| <= mu fz, |fy| <= mu fz, fzmin <= fz <= fzmax (stance) or f = 0 (swing). */
+typedef struct qpb_mpc_params {
+  double mu, mass, fzmin, fzmax;
+  double Ib[9];
+  double dt;
+  double Lw[13]; /* state weights (>= 0); Lw[12] (gravity state) is ignored */
+  double alpha;  /* force weight (> 0: keeps the QP strictly convex) */
+  int32_t max_iter; /* working-set changes allowed per QP */
+  int32_t pad;
+} qpb_mpc_params;
+
+typedef struct qpb_mpc_rec { /* 2176 bytes, 16-byte aligned */
+  double x0[13];
+  double xref[10][13]; /* reference for x_1 .. x_10 */
+  double r[10][4][3];  /* foot position minus CoM, world frame, per step and foot */
+  uint8_t contact[10][4]; /* 1 = stance, 0 = swing */
+  uint8_t pad[32];
+} qpb_mpc_rec;
+
+typedef struct qpb_mpc_out_rec { /* 1024 bytes */
+  double U[120];  /* world-frame forces, step-major, then foot, then xyz; swing feet 0; all 0 when status != QPB_OK */
+  int32_t status; /* QPB_OK / QPB_MAX_ITER (iteration or working-set capacity limit) / QPB_BAD_INPUT */
+  int32_t iters;
+  uint8_t pad[56];
+} qpb_mpc_out_rec;
+
+typedef struct qpb_mpc_handle qpb_mpc_handle;
+
+/* Robot constants of mit_cheetah_config.yaml:95-99, mu = 0.6, dt = 0.03, Lw and alpha of Di Carlo et al. */
+int qpb_mpc_default_params(qpb_mpc_params* out);
+/* Rejects non-finite values, mu <= 0, fzmin > fzmax, fzmax < 0, 2*mu*fzmax > 1e6, mass <= 0, dt <= 0, alpha <= 0,
+ * negative weights, singular Ib, max_iter < 1. */
+int qpb_mpc_create(const qpb_mpc_params* params, int device, qpb_mpc_handle** out);
+int qpb_mpc_destroy(qpb_mpc_handle* h);
+/* n QPs, records resident on the device; asynchronous on stream. */
+int qpb_mpc_batch_packed(qpb_mpc_handle* h, int64_t n, const qpb_mpc_rec* d_recs, qpb_mpc_out_rec* d_out, void* stream);
+/* Host buffers (pinned or pageable); returns when h_out is complete. */
+int qpb_mpc_batch_host(qpb_mpc_handle* h, int64_t n, const qpb_mpc_rec* h_recs, qpb_mpc_out_rec* h_out);
+int64_t qpb_mpc_launch_count(const qpb_mpc_handle* h);
+
 #ifdef __cplusplus
 }
 #endif

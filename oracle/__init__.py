@@ -15,7 +15,7 @@ _lib = None
 
 def build(force=False):
     if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < max(
-        os.path.getmtime(os.path.join(_HERE, f)) for f in ("qpb_oracle.c", "qpb_oracle.h")
+        os.path.getmtime(os.path.join(_HERE, f)) for f in ("qpb_oracle.c", "qpb_oracle.h", "mpc_oracle.c", "mpc_oracle.h")
     ):
         subprocess.run(["make", "-C", _HERE, "-B"], check=True, capture_output=True)
     return _LIB_PATH
@@ -227,4 +227,48 @@ def ref_tick_batch(params, gains, states, swing, nthreads=1):
     out = np.zeros(len(states), dtype=OUT_DTYPE)
     ref_lib().ref_tick_batch(ctypes.byref(params), ctypes.byref(gains), states.ctypes.data, swing.ctypes.data, len(states),
                              out.ctypes.data, int(nthreads))
+    return out
+
+
+# ---- 10-step convex-MPC QP (BASELINE config 4; parity unpinned: no reference code exists) ---------------------
+def _mpc_protos():
+    L = lib()
+    if not getattr(L, "_mpc_ready", False):
+        vp = ctypes.c_void_p
+        dp = ctypes.POINTER(ctypes.c_double)
+        L.orc_mpc_default_params.argtypes = [vp]
+        L.orc_mpc_assemble.argtypes = [vp, vp, dp, dp, dp, dp, dp]
+        L.orc_mpc_solve.argtypes = [vp, vp, vp]
+        L.orc_mpc_solve.restype = ctypes.c_int
+        L.orc_mpc_batch.argtypes = [vp, vp, ctypes.c_int64, vp, ctypes.c_int]
+        L._mpc_ready = True
+    return L
+
+
+def mpc_default_params():
+    from quadruped_control_b200.records import MpcParams
+
+    p = MpcParams()
+    _mpc_protos().orc_mpc_default_params(ctypes.byref(p))
+    return p
+
+
+def mpc_assemble(params, rec):
+    from quadruped_control_b200.records import MPC_REC_DTYPE
+
+    rec = np.ascontiguousarray(rec).reshape(1)
+    assert rec.dtype == MPC_REC_DTYPE
+    H, g, C = np.empty(120 * 120), np.empty(120), np.empty(200 * 120)
+    lb, ub = np.empty(200), np.empty(200)
+    _mpc_protos().orc_mpc_assemble(ctypes.byref(params), rec.ctypes.data, _dp(H), _dp(g), _dp(C), _dp(lb), _dp(ub))
+    return dict(Q=H.reshape(120, 120), c=g, C=C.reshape(200, 120), lb=lb, ub=ub)
+
+
+def mpc_batch(params, recs, nthreads=1):
+    from quadruped_control_b200.records import MPC_OUT_DTYPE, MPC_REC_DTYPE
+
+    recs = np.ascontiguousarray(recs)
+    assert recs.dtype == MPC_REC_DTYPE
+    out = np.zeros(len(recs), dtype=MPC_OUT_DTYPE)
+    _mpc_protos().orc_mpc_batch(ctypes.byref(params), recs.ctypes.data, len(recs), out.ctypes.data, int(nthreads))
     return out

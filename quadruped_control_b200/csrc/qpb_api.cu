@@ -10,6 +10,7 @@
 #include <new>
 #include <string>
 
+#include "qpb_internal.h"
 #include "qpb_kernel.cuh"
 #include "qpb_kernel16.cuh"
 #include "qpb_swing.cuh"
@@ -59,6 +60,8 @@ constexpr int64_t kMaxRecordsPerLaunch = (int64_t)1 << 31;  // the kernels index
 constexpr uint32_t kTicketSlots = 4096;  // ring of work counters; a launch re-zeroes the slot half a ring ahead
 
 }  // namespace
+
+int qpb_internal_fail(int code, const std::string& msg) { return fail(code, msg); }
 
 struct qpb_handle {
   int device = 0;

@@ -9,7 +9,7 @@ import os
 
 import numpy as np
 
-from .records import OUT_DTYPE, STATE_DTYPE, SWING_DTYPE, JointGains, Params
+from .records import MPC_OUT_DTYPE, MPC_REC_DTYPE, OUT_DTYPE, STATE_DTYPE, SWING_DTYPE, JointGains, MpcParams, Params
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("QPB_LIB") or os.path.join(_HERE, "libqpb200.so")  # QPB_LIB: experiment builds
@@ -33,6 +33,12 @@ EXPORTS = (
     "qpb_host_alloc",
     "qpb_host_free",
     "qpb_launch_count",
+    "qpb_mpc_default_params",
+    "qpb_mpc_create",
+    "qpb_mpc_destroy",
+    "qpb_mpc_batch_packed",
+    "qpb_mpc_batch_host",
+    "qpb_mpc_launch_count",
 )
 
 _lib = None
@@ -70,6 +76,13 @@ def load():
     L.qpb_host_free.argtypes = [vp]
     L.qpb_launch_count.argtypes = [vp]
     L.qpb_launch_count.restype = i64
+    L.qpb_mpc_default_params.argtypes = [ctypes.POINTER(MpcParams)]
+    L.qpb_mpc_create.argtypes = [ctypes.POINTER(MpcParams), ctypes.c_int, ctypes.POINTER(vp)]
+    L.qpb_mpc_destroy.argtypes = [vp]
+    L.qpb_mpc_batch_packed.argtypes = [vp, i64, vp, vp, vp]
+    L.qpb_mpc_batch_host.argtypes = [vp, i64, vp, vp]
+    L.qpb_mpc_launch_count.argtypes = [vp]
+    L.qpb_mpc_launch_count.restype = i64
     for name in EXPORTS:
         getattr(L, name)
     _lib = L
@@ -199,3 +212,48 @@ class BalanceSolver:
 
     def fk(self, n, q, feet, stream=None):
         _check(load().qpb_fk_batch(self._h, int(n), _ptr(q), _ptr(feet), stream), "qpb_fk_batch")
+
+
+def default_mpc_params():
+    p = MpcParams()
+    _check(load().qpb_mpc_default_params(ctypes.byref(p)), "qpb_mpc_default_params")
+    return p
+
+
+class MpcSolver:
+    """Owns one ``qpb_mpc_handle``: the batched 10-step convex-MPC QP (BASELINE config 4)."""
+
+    def __init__(self, params: MpcParams = None, device: int = 0):
+        L = load()
+        self.params = params.copy() if params is not None else default_mpc_params()
+        h = ctypes.c_void_p()
+        _check(L.qpb_mpc_create(ctypes.byref(self.params), int(device), ctypes.byref(h)), "qpb_mpc_create")
+        self._h = h
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load().qpb_mpc_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launches(self):
+        return int(load().qpb_mpc_launch_count(self._h))
+
+    def solve_packed(self, d_recs, d_out, n, stream=None):
+        _check(load().qpb_mpc_batch_packed(self._h, int(n), _ptr(d_recs), _ptr(d_out), stream), "qpb_mpc_batch_packed")
+
+    def solve_host(self, recs: np.ndarray, out: np.ndarray = None):
+        recs = np.ascontiguousarray(recs)
+        assert recs.dtype == MPC_REC_DTYPE
+        if out is None:
+            out = np.empty(recs.shape[0], dtype=MPC_OUT_DTYPE)
+        assert out.dtype == MPC_OUT_DTYPE and out.shape[0] == recs.shape[0] and out.flags.c_contiguous
+        _check(load().qpb_mpc_batch_host(self._h, recs.shape[0], recs.ctypes.data, out.ctypes.data), "qpb_mpc_batch_host")
+        return out

@@ -130,3 +130,59 @@ def default_joint_gains():
     g.kp[:] = [40.0, 40.0, 50.0]
     g.kd[:] = [1.0, 1.0, 1.0]
     return g
+
+
+# ---- 10-step convex-MPC QP (BASELINE config 4) -----------------------------------
+# The reference has no code for this path; the formulation is stated in include/qpb200.h (qpb_mpc_*).
+MPC_HORIZON, MPC_NV, MPC_NC = 10, 120, 200
+
+MPC_REC_DTYPE = np.dtype(
+    [
+        ("x0", "<f8", (13,)),
+        ("xref", "<f8", (10, 13)),
+        ("r", "<f8", (10, 4, 3)),
+        ("contact", "u1", (10, 4)),
+        ("pad", "u1", (32,)),
+    ]
+)
+assert MPC_REC_DTYPE.itemsize == 2176
+
+MPC_OUT_DTYPE = np.dtype([("U", "<f8", (120,)), ("status", "<i4"), ("iters", "<i4"), ("pad", "u1", (56,))])
+assert MPC_OUT_DTYPE.itemsize == 1024
+
+# Algorithmic bytes per MPC QP: 263 doubles + 40 contact bytes in, 120 doubles + status out.
+MPC_ALGO_BYTES_PER_QP = 263 * 8 + 40 + 120 * 8 + 4
+
+
+class MpcParams(ctypes.Structure):
+    """``qpb_mpc_params``."""
+
+    _fields_ = [
+        ("mu", ctypes.c_double),
+        ("mass", ctypes.c_double),
+        ("fzmin", ctypes.c_double),
+        ("fzmax", ctypes.c_double),
+        ("Ib", ctypes.c_double * 9),
+        ("dt", ctypes.c_double),
+        ("Lw", ctypes.c_double * 13),
+        ("alpha", ctypes.c_double),
+        ("max_iter", ctypes.c_int32),
+        ("pad", ctypes.c_int32),
+    ]
+
+    def copy(self):
+        other = MpcParams()
+        ctypes.memmove(ctypes.byref(other), ctypes.byref(self), ctypes.sizeof(self))
+        return other
+
+
+def default_mpc_params(mu=0.6):
+    """Robot constants of mit_cheetah_config.yaml:95-99; horizon step and weights of Di Carlo et al. (IROS 2018)."""
+    p = MpcParams()
+    p.mu, p.mass, p.fzmin, p.fzmax = mu, 11.0, 10.0, 120.0
+    p.Ib[:] = np.diag([0.011253, 0.036203, 0.042673]).ravel().tolist()
+    p.dt = 0.03
+    p.Lw[:] = [0.25, 0.25, 10.0, 2.0, 2.0, 50.0, 0.0, 0.0, 0.3, 0.2, 0.2, 0.1, 0.0]
+    p.alpha = 4e-5
+    p.max_iter = 1000
+    return p

@@ -167,3 +167,85 @@ def generate_swing(S, seed, params: Params = None, reach=0.25):
     sw["foot_ref_vel"] = rng.normal(0.0, 0.5, size=(n, 12))
     sw["qdot"] = rng.normal(0.0, 2.0, size=(n, 12))
     return sw
+
+
+# ---- BASELINE config 4: 10-step convex-MPC records ----------------------------
+MPC_DRAWS_PER_RECORD = 32
+CONFIGS["cfg4_mpc_65536"] = dict(n=65536, seed=20260104, mu=0.6)
+
+
+def generate_mpc(n, seed, lo=0, params=None, gaits="mixed", scale=1.0):
+    """Records [lo, lo+n) of MPC stream ``seed`` as an MPC_REC_DTYPE array (index-addressable like generate_states).
+
+    Current state: roll, pitch ~ U(+-0.15), yaw ~ U(+-pi), p = (U(+-0.05), U(+-0.05), 0.26 + U(+-0.03)),
+    omega ~ N(0, 0.5^2), v ~ N(0, 0.3^2).  Reference: level body at z = 0.26 moving with a commanded yaw-frame
+    velocity (U(+-0.5), U(+-0.2), 0) and yaw rate U(+-0.5), integrated over the horizon.  Gait: stand (4 feet),
+    trot (diagonal pairs alternating every 5 steps) or crawl (one leg swinging at a time), uniform, random phase.
+    Feet: nominal stance rectangle (+-0.196, +-0.14) in the yaw frame + U(+-0.03), fixed in the world; lever arms
+    are taken from the reference CoM of each step.  ``scale`` multiplies the attitude, twist and command magnitudes
+    (a stress knob for the parity tests: more pyramid rows become active)."""
+    from .records import MPC_REC_DTYPE, default_mpc_params
+
+    params = params or default_mpc_params()
+    n = int(n)
+    bg = np.random.Philox(key=int(seed))
+    bg.advance(int(lo) * (MPC_DRAWS_PER_RECORD // 4))
+    raw = bg.random_raw(n * MPC_DRAWS_PER_RECORD).reshape(n, MPC_DRAWS_PER_RECORD)
+    u = (raw >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
+    uni = u[:, :24]
+    rad = np.sqrt(-2.0 * np.log(1.0 - u[:, 24:28]))
+    ang = 2.0 * np.pi * u[:, 28:32]
+    nrm = np.concatenate([rad * np.cos(ang), rad * np.sin(ang)], axis=1)  # 8 normals
+
+    def sym(col, half):
+        return (2.0 * uni[:, col] - 1.0) * half
+
+    rec = np.zeros(n, dtype=MPC_REC_DTYPE)
+    yaw0 = sym(2, np.pi)
+    p0 = np.stack([sym(3, 0.05), sym(4, 0.05), 0.26 + sym(5, 0.03)], axis=1)
+    rec["x0"][:, 0], rec["x0"][:, 1], rec["x0"][:, 2] = sym(0, 0.15 * scale), sym(1, 0.15 * scale), yaw0
+    rec["x0"][:, 3:6] = p0
+    rec["x0"][:, 6:9] = nrm[:, 0:3] * 0.5 * scale
+    rec["x0"][:, 9:12] = nrm[:, 3:6] * 0.3 * scale
+    rec["x0"][:, 12] = -9.81
+    vcmd = np.stack([sym(6, 0.5 * scale), sym(7, 0.2 * scale)], axis=1)
+    yawrate = sym(8, 0.5 * scale)
+    c0, s0 = np.cos(yaw0), np.sin(yaw0)
+    vw = np.stack([c0 * vcmd[:, 0] - s0 * vcmd[:, 1], s0 * vcmd[:, 0] + c0 * vcmd[:, 1]], axis=1)
+    dt = params.dt
+    steps = np.arange(1, 11, dtype=np.float64)
+    xr = rec["xref"]
+    xr[:, :, 2] = yaw0[:, None] + yawrate[:, None] * dt * steps
+    xr[:, :, 3] = p0[:, 0:1] + vw[:, 0:1] * dt * steps
+    xr[:, :, 4] = p0[:, 1:2] + vw[:, 1:2] * dt * steps
+    xr[:, :, 5] = 0.26
+    xr[:, :, 8] = yawrate[:, None]
+    xr[:, :, 9] = vw[:, 0:1]
+    xr[:, :, 10] = vw[:, 1:2]
+    xr[:, :, 12] = -9.81
+    # feet, fixed in the world
+    sx = np.array([-1.0, 1.0, -1.0, 1.0]) * 0.196
+    sy = np.array([1.0, 1.0, -1.0, -1.0]) * 0.14
+    fx = sx[None, :] + (2.0 * uni[:, 9:13] - 1.0) * 0.03
+    fy = sy[None, :] + (2.0 * uni[:, 13:17] - 1.0) * 0.03
+    foot_w = np.empty((n, 4, 3))
+    foot_w[:, :, 0] = p0[:, 0:1] + c0[:, None] * fx - s0[:, None] * fy
+    foot_w[:, :, 1] = p0[:, 1:2] + s0[:, None] * fx + c0[:, None] * fy
+    foot_w[:, :, 2] = 0.0
+    rec["r"] = foot_w[:, None, :, :] - xr[:, :, None, 3:6]
+    # gait
+    k = np.arange(10)[None, :]
+    phase = np.minimum((uni[:, 18] * 10).astype(np.int64), 9)[:, None]
+    if gaits == "mixed":
+        gait = np.minimum((uni[:, 17] * 3).astype(np.int64), 2)
+    else:
+        gait = np.full(n, {"stand": 0, "trot": 1, "crawl": 2}[gaits], dtype=np.int64)
+    contact = np.ones((n, 10, 4), dtype=np.uint8)
+    first = ((k + phase) % 10) < 5  # trot: RL+FR stance on the first half-period, FL+RR on the second
+    trot = np.stack([first, ~first, ~first, first], axis=2).astype(np.uint8)
+    swing_leg = ((k + phase) % 8) // 2  # crawl: leg swing_leg is in the air
+    crawl = (np.arange(4)[None, None, :] != swing_leg[:, :, None]).astype(np.uint8)
+    contact = np.where((gait == 1)[:, None, None], trot, contact)
+    contact = np.where((gait == 2)[:, None, None], crawl, contact)
+    rec["contact"] = contact
+    return rec
