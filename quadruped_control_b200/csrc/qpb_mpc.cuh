@@ -62,6 +62,8 @@ struct __align__(16) Smem {
   double u[QCAP];
   double r[QCAP];
   double dd[QCAP];
+  double ratio[QCAP];   // max(u_k, 0) / r_k where r_k > 0, else +inf
+  double part[2][NW];   // per-warp partial sums of |n~|^2 and n~.z~
   int A[QCAP];
   unsigned red[NW];
   unsigned char slot_of_row[MROWS];
@@ -73,7 +75,7 @@ struct __align__(16) Smem {
 
 #ifdef QPB_MPC_PROFILE
 // developer build only (tools/time_mpc.py): cycles per phase summed over all QPs, [assembly, sweep, start, loop, io, count]
-__device__ unsigned long long g_mpc_prof[8];
+__device__ unsigned long long g_mpc_prof[16];
 #define MPC_TICK(slot)                                              \
   do {                                                              \
     if (tid == 0) {                                                 \
@@ -110,16 +112,87 @@ __device__ __forceinline__ double& ns_at(Smem& S, int k, int i) {
   return S.M[(119 - 2 * (k - QMAX) - h) * LD + (i - 60 * h)];
 }
 
-template <int B>
+template <int B, int NB>
 __device__ __forceinline__ void publish_col(const double (&m)[8][8], double* dst, int ty) {
 #pragma unroll
-  for (int a = 0; a < 8; a++) dst[ty + 16 * a] = m[a][B];
+  for (int a = 0; a < NB; a++) dst[ty + 16 * a] = m[a][B < 8 ? B : 7];
 }
-template <int A>
-__device__ __forceinline__ void assign_row(double (&m)[8][8], const double (&ci)[8], int tx, int j) {
+
+// Steps j = 16*BJ .. 16*BJ+15 of the Gauss-Jordan sweep over NB x NB blocks of 16 (see phase E).  The block index of
+// the pivot is a template parameter, so every register index is static and eliminated column blocks cost nothing.
+template <int NB, int BJ>
+struct SweepBlock {
+  static __device__ __forceinline__ bool run(double (&m)[8][8], Smem& S, int n, int tx, int ty, int tid) {
+#pragma unroll 1
+    for (int tj = 0; tj < 16; tj++) {
+      const int j = 16 * BJ + tj;
+      if (j >= n) return true;
+      const double* cur = S.col[j & 1];
+      double* nxt = S.col[(j + 1) & 1];
+      const double d = cur[j];
+      if (!(d > 0.0)) return false;  // uniform: every thread reads the same value
+      const double rd = rcp_fast(d);
+      if (tid == 0) S.dval[j] = d;
+      double ci[8], cv[8];
 #pragma unroll
-  for (int b = 0; b < 8; b++)
-    if (tx + 16 * b > j) m[A][b] = -ci[b];
+      for (int a = 0; a < NB; a++) cv[a] = cur[ty + 16 * a];
+      if (ty == tj) cv[BJ] = 0.0;  // row j itself is assigned below
+#pragma unroll
+      for (int b = BJ; b < NB; b++) ci[b] = cur[tx + 16 * b] * rd;  // rows/columns >= n are zero already
+      if (tx <= tj) ci[BJ] = 0.0;    // columns <= j are finished
+#pragma unroll
+      for (int b = BJ; b < NB; b++)
+#pragma unroll
+        for (int a = 0; a < NB; a++) m[a][b] = fma(-cv[a], ci[b], m[a][b]);
+      if (ty == tj) {
+        if (tx > tj) m[BJ][BJ] = -ci[BJ];
+#pragma unroll
+        for (int b = BJ + 1; b < NB; b++) m[BJ][b] = -ci[b];
+      }
+      if (tj < 15) {
+        if (tx == tj + 1) publish_col<BJ, NB>(m, nxt, ty);
+      } else if (BJ + 1 < NB) {
+        if (tx == 0) publish_col<BJ + 1, NB>(m, nxt, ty);
+      }
+      __syncthreads();
+    }
+    return SweepBlock<NB, BJ + 1>::run(m, S, n, tx, ty, tid);
+  }
+};
+template <int NB>
+struct SweepBlock<NB, NB> {
+  static __device__ __forceinline__ bool run(double (&)[8][8], Smem&, int, int, int, int) { return true; }
+};
+
+// load the symmetric H into the register tiles, sweep, and store X^T above the diagonal of S.M
+template <int NB>
+__device__ __noinline__ bool sweep(Smem& S, int n, int tid) {
+  const int tx = tid & 15, ty = tid >> 4;
+  double m[8][8];
+#pragma unroll
+  for (int a = 0; a < NB; a++)
+#pragma unroll
+    for (int b = 0; b < NB; b++) {
+      const int R = ty + 16 * a, C = tx + 16 * b;
+      m[a][b] = (R < n && C < n) ? (C <= R ? S.M[R * LD + C] : S.M[C * LD + R]) : 0.0;
+    }
+  if (tx == 0) publish_col<0, NB>(m, S.col[0], ty);
+  __syncthreads();
+  const bool ok = SweepBlock<NB, 0>::run(m, S, n, tx, ty, tid);
+  if (!__syncthreads_and(ok)) return false;
+  if (tid < n) S.dinv[tid] = 1.0 / sqrt(S.dval[tid]);
+  __syncthreads();
+#pragma unroll
+  for (int b = 0; b < NB; b++) {
+    const int C = tx + 16 * b;
+    const double sc = C < n ? S.dinv[C] : 0.0;
+#pragma unroll
+    for (int a = 0; a < NB; a++) {
+      const int R = ty + 16 * a;
+      if (C > R && C < n) S.M[R * LD + C] = m[a][b] * sc;  // X[i][c] = Xu[i][c] / L_ii at M[c][i]
+    }
+  }
+  return true;
 }
 
 // X(i, c) for the inverse factor stored transposed above the diagonal
@@ -162,6 +235,98 @@ __device__ __forceinline__ double tri_XT(const Smem& S, const double* v, int c, 
   return a + __shfl_xor_sync(FULL, a, 1);
 }
 
+// Triangular mat-vecs with X^T stored above the diagonal of M (leading dimension 121).  Mapping: a warp serves the
+// pair of 8-row blocks (warp, nb8-1-warp) -- a short and a long one, n-1 terms together, so the 8 warps are balanced --
+// lane = 8*s + r8: r8 picks the row of the block, s in 0..3 the residue class of the inner index,
+// inner = 16t + 8(s&1) + 4(s>>1) + u, u = 0..3.  Within a half-warp the two classes sit 8 inner indices apart, which
+// with the odd leading dimension makes every 64-bit shared-memory access conflict-free in both sweep directions.
+// Partial sums are combined over the four classes with two shuffles; every lane returns the full sum.
+struct TriMap {
+  int iA, iB, off;
+  bool onA, onB;
+};
+__device__ __forceinline__ TriMap tri_map(int n, int lane, int warp) {
+  const int nb8 = (n + 7) >> 3, bA = warp, bB = nb8 - 1 - warp, r8 = lane & 7, s = lane >> 3;
+  TriMap t;
+  t.iA = 8 * bA + r8;
+  t.iB = 8 * bB + r8;
+  t.off = 8 * (s & 1) + 4 * (s >> 1);
+  t.onA = bA <= bB && t.iA < n;
+  t.onB = bA < bB && t.iB < n;
+  return t;
+}
+__device__ __forceinline__ double quad_sum(double a) {
+  a += __shfl_xor_sync(FULL, a, 8);
+  return a + __shfl_xor_sync(FULL, a, 16);
+}
+// sum_{c < i} M[c][i] v_c over this lane's residue class
+__device__ __forceinline__ double tri_col_part(const double* Mi, const double* v, int i, int off) {
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  int c = off;
+  for (; c + 3 < i; c += 16) {
+    a0 = fma(Mi[c * LD], v[c], a0);
+    a1 = fma(Mi[(c + 1) * LD], v[c + 1], a1);
+    a2 = fma(Mi[(c + 2) * LD], v[c + 2], a2);
+    a3 = fma(Mi[(c + 3) * LD], v[c + 3], a3);
+  }
+  if (c < i) a0 = fma(Mi[c * LD], v[c], a0);
+  if (c + 1 < i) a1 = fma(Mi[(c + 1) * LD], v[c + 1], a1);
+  if (c + 2 < i) a2 = fma(Mi[(c + 2) * LD], v[c + 2], a2);
+  return (a0 + a1) + (a2 + a3);
+}
+// sum_{c < i < n} M[c][i] v_i over this lane's residue class
+__device__ __forceinline__ double tri_row_part(const double* Mc, const double* v, int c, int n, int off) {
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  int i = ((c + 1) & ~15) + off;  // first 16-aligned window that can hold an index > c
+  if (i + 3 > c) {                // head window: some of its four indices may still be <= c
+    if (i > c && i < n) a0 = fma(Mc[i], v[i], a0);
+    if (i + 1 > c && i + 1 < n) a1 = fma(Mc[i + 1], v[i + 1], a1);
+    if (i + 2 > c && i + 2 < n) a2 = fma(Mc[i + 2], v[i + 2], a2);
+    if (i + 3 < n) a3 = fma(Mc[i + 3], v[i + 3], a3);
+  }
+  i += 16;
+  for (; i + 3 < n; i += 16) {
+    a0 = fma(Mc[i], v[i], a0);
+    a1 = fma(Mc[i + 1], v[i + 1], a1);
+    a2 = fma(Mc[i + 2], v[i + 2], a2);
+    a3 = fma(Mc[i + 3], v[i + 3], a3);
+  }
+  if (i < n) a0 = fma(Mc[i], v[i], a0);
+  if (i + 1 < n) a1 = fma(Mc[i + 1], v[i + 1], a1);
+  if (i + 2 < n) a2 = fma(Mc[i + 2], v[i + 2], a2);
+  return (a0 + a1) + (a2 + a3);
+}
+// (X v)_i = sum_{c < i} M[c][i] v_c + dinv_i v_i for rows iA, iB of the map
+__device__ __forceinline__ void tri_X8(const Smem& S, const double* v, const TriMap& t, double& oA, double& oB) {
+  const double a = quad_sum(t.onA ? tri_col_part(&S.M[t.iA], v, t.iA, t.off) : 0.0);
+  const double b = quad_sum(t.onB ? tri_col_part(&S.M[t.iB], v, t.iB, t.off) : 0.0);
+  oA = t.onA ? fma(S.dinv[t.iA], v[t.iA], a) : 0.0;
+  oB = t.onB ? fma(S.dinv[t.iB], v[t.iB], b) : 0.0;
+}
+// (X^T v)_c = dinv_c v_c + sum_{i > c} M[c][i] v_i for columns iA, iB of the map
+__device__ __forceinline__ void tri_XT8(const Smem& S, const double* v, int n, const TriMap& t, double& oA, double& oB) {
+  const double a = quad_sum(t.onA ? tri_row_part(&S.M[t.iA * LD], v, t.iA, n, t.off) : 0.0);
+  const double b = quad_sum(t.onB ? tri_row_part(&S.M[t.iB * LD], v, t.iB, n, t.off) : 0.0);
+  oA = t.onA ? fma(S.dinv[t.iA], v[t.iA], a) : 0.0;
+  oB = t.onB ? fma(S.dinv[t.iB], v[t.iB], b) : 0.0;
+}
+
+// sum over the 16 lanes of a half-warp
+__device__ __forceinline__ double half_sum(double v) {
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+  return v;
+}
+
+// exact minimum over the warp of non-negative doubles (or +inf): their bit patterns order like unsigned integers
+__device__ __forceinline__ double warp_min_nonneg(double v) {
+  const unsigned hi = (unsigned)__double2hiint(v);
+  const unsigned mh = __reduce_min_sync(FULL, hi);
+  const unsigned lo = (hi == mh) ? (unsigned)__double2loint(v) : 0xffffffffu;
+  const unsigned ml = __reduce_min_sync(FULL, lo);
+  return __hiloint2double((int)mh, (int)ml);
+}
+
 // coefficient of pyramid row type t (0..5) on component comp (0..2) of its foot-step
 __device__ __forceinline__ double row_coef(int t, int comp, double mu) {
   if (comp == 2) return t < 4 ? mu : (t == 4 ? 1.0 : -1.0);
@@ -169,15 +334,12 @@ __device__ __forceinline__ double row_coef(int t, int comp, double mu) {
   return t == 1 ? -1.0 : (t == 2 ? 1.0 : 0.0);
 }
 
+// slack n.f - b of row type t, branch-free
 __device__ __forceinline__ double row_slack(int t, double fx, double fy, double fz, const DevParams& P) {
-  switch (t) {
-    case 0: return fma(P.mu, fz, -fx);
-    case 1: return fma(P.mu, fz, -fy);
-    case 2: return fma(P.mu, fz, fy);
-    case 3: return fma(P.mu, fz, fx);
-    case 4: return fz - P.fzmin;
-    default: return P.fzmax - fz;
-  }
+  const double lat = (t == 0 || t == 3) ? fx : fy;                    // lateral component the row looks at
+  const double sl = (t == 0 || t == 1) ? -lat : lat;
+  const double pyr = fma(P.mu, fz, sl);
+  return t < 4 ? pyr : (t == 4 ? fz - P.fzmin : P.fzmax - fz);
 }
 
 __global__ void __launch_bounds__(NT, 1)
@@ -308,32 +470,60 @@ mpc_qp_kernel(const __grid_constant__ DevParams P, const qpb_mpc_rec* __restrict
       }
       __syncthreads();
 
-      // ---- phase D: H (lower triangle) and the gradient ------------------------------------------------------
-      for (int idx = tid; idx < n * n; idx += NT) {
-        const int a = idx / n, b = idx - a * n;
-        if (b > a) continue;
-        const int fa = a / 3, fb = b / 3, ca = a - 3 * fa, cbb = b - 3 * fb;
-        const int ja = S.sfk[fa], jb = S.sfk[fb];  // jb <= ja: the compact order is step-major
-        const double* Ta = &ThW[3 * NH * a];
-        const double* Tb = &ThW[3 * NH * b];
-        double t = 0.0, tb1 = 0.0, tb2 = 0.0;
-        for (int k = ja + 1; k < NH; k++) {
-          t = fma(Ta[3 * k], Tb[3 * k], t);
-          tb1 = fma(Ta[3 * k + 1], Tb[3 * k + 1], tb1);
-          tb2 = fma(Ta[3 * k + 2], Tb[3 * k + 2], tb2);
-        }
-        t += tb1 + tb2;
-        const double cnt = (double)(NH - ja);
-        const double* ga = &S.G[3 * a];
-        const double* gb = &S.G[3 * b];
-        t += dt2 * cnt * (P.Lw[6] * ga[0] * gb[0] + P.Lw[7] * ga[1] * gb[1] + P.Lw[8] * ga[2] * gb[2]);
-        if (ca == cbb) {
+      // ---- phase D: H in 3x3 blocks (foot-step fa x foot-step fb, fb <= fa) and the gradient ------------------
+      // Rows fa' and ns-1-fa' of the block triangle together hold ns+1 blocks, so idx -> (fa, fb) needs one division
+      // and no thread draws a block above the diagonal.
+      {
+        const int per = ns + 1, half = (ns + 1) >> 1;
+        for (int idx = tid; idx < half * per; idx += NT) {
+          const int rp = idx / per, t = idx - rp * per;
+          const bool lowrow = t <= rp;
+          if (!lowrow && 2 * rp == ns - 1) continue;  // odd ns: the middle row is its own partner
+          const int fa = lowrow ? rp : ns - 1 - rp, fb = lowrow ? t : t - rp - 1;
+          const int ja = S.sfk[fa], jb = S.sfk[fb];  // jb <= ja: the compact order is step-major
+          const double* Ta = &ThW[9 * NH * fa];      // [i][k][s] for the three variables of the foot-step
+          const double* Tb = &ThW[9 * NH * fb];
+          double acc[3][3];
+          const double cnt = (double)(NH - ja);
+          {
+            double A[3][3], B[3][3];
+#pragma unroll
+            for (int i = 0; i < 3; i++)
+#pragma unroll
+              for (int c = 0; c < 3; c++) {
+                A[i][c] = S.G[9 * fa + 3 * i + c];
+                B[i][c] = dt2 * cnt * P.Lw[6 + c] * S.G[9 * fb + 3 * i + c];
+              }
+#pragma unroll
+            for (int i = 0; i < 3; i++)
+#pragma unroll
+              for (int l = 0; l < 3; l++) acc[i][l] = A[i][0] * B[l][0] + A[i][1] * B[l][1] + A[i][2] * B[l][2];
+          }
+          for (int k = ja + 1; k < NH; k++) {
+            double A[3][3], B[3][3];
+#pragma unroll
+            for (int i = 0; i < 3; i++)
+#pragma unroll
+              for (int c = 0; c < 3; c++) {
+                A[i][c] = Ta[(i * NH + k) * 3 + c];
+                B[i][c] = Tb[(i * NH + k) * 3 + c];
+              }
+#pragma unroll
+            for (int i = 0; i < 3; i++)
+#pragma unroll
+              for (int l = 0; l < 3; l++)
+                acc[i][l] = fma(A[i][0], B[l][0], fma(A[i][1], B[l][1], fma(A[i][2], B[l][2], acc[i][l])));
+          }
           const double s1 = 0.5 * (cnt - 1.0) * cnt, s2 = (cnt - 1.0) * cnt * (2.0 * cnt - 1.0) * (1.0 / 6.0);
-          t += (dt * im) * (dt * im) * P.Lw[9 + ca] * cnt;
-          t += (dt2 * im) * (dt2 * im) * P.Lw[3 + ca] * (s2 + (double)(ja - jb) * s1);
+          const double lin = (dt * im) * (dt * im) * cnt, quad = (dt2 * im) * (dt2 * im) * (s2 + (double)(ja - jb) * s1);
+#pragma unroll
+          for (int i = 0; i < 3; i++) {
+            acc[i][i] += P.Lw[9 + i] * lin + P.Lw[3 + i] * quad;
+            if (fa == fb) acc[i][i] += P.alpha;
+#pragma unroll
+            for (int l = 0; l < 3; l++) S.M[(3 * fa + i) * LD + 3 * fb + l] = 2.0 * acc[i][l];  // diagonal blocks: all 9
+          }
         }
-        if (a == b) t += P.alpha;
-        S.M[a * LD + b] = 2.0 * t;
       }
       if (tid < n) {
         const int a = tid, fa = a / 3, ca = a - 3 * fa, ja = S.sfk[fa];
@@ -359,82 +549,13 @@ mpc_qp_kernel(const __grid_constant__ DevParams P, const qpb_mpc_rec* __restrict
       // Below the diagonal this is the Cholesky elimination (never read again); above it, it accumulates the rows of
       // the unscaled inverse factor: afterwards X[i][c] = M[c][i] / sqrt(d_i) for c < i.  One barrier per step.
       {
-        const int tx = tid & 15, ty = tid >> 4;
-        double m[8][8];
-#pragma unroll
-        for (int a = 0; a < 8; a++)
-#pragma unroll
-          for (int b = 0; b < 8; b++) {
-            const int R = ty + 16 * a, C = tx + 16 * b;
-            m[a][b] = (R < n && C < n) ? (C <= R ? S.M[R * LD + C] : S.M[C * LD + R]) : 0.0;
-          }
-        if (tx == 0) publish_col<0>(m, S.col[0], ty);
-        __syncthreads();
-        for (int j = 0; j < n; j++) {
-          const double* cur = S.col[j & 1];
-          double* nxt = S.col[(j + 1) & 1];
-          const double d = cur[j];
-          if (!(d > 0.0)) { status = QPB_BAD_INPUT; break; }  // uniform: every thread reads the same value
-          const double rd = rcp_fast(d);
-          if (tid == 0) S.dval[j] = d;
-          const int bj = j >> 4, tj = j & 15;
-          double ci[8], cv[8];
-#pragma unroll
-          for (int b = 0; b < 8; b++) {
-            const int C = tx + 16 * b, R = ty + 16 * b;
-            ci[b] = (C > j && C < n) ? cur[C] * rd : 0.0;
-            cv[b] = (R != j) ? cur[R] : 0.0;
-          }
-#pragma unroll
-          for (int b = 0; b < 8; b++) {
-            if (b < bj || 16 * b >= n) continue;  // uniform: columns already eliminated / beyond the matrix
-#pragma unroll
-            for (int a = 0; a < 8; a++)
-              if (16 * a < n) m[a][b] = fma(-cv[a], ci[b], m[a][b]);
-          }
-          if (ty == tj) {
-            switch (bj) {
-              case 0: assign_row<0>(m, ci, tx, j); break;
-              case 1: assign_row<1>(m, ci, tx, j); break;
-              case 2: assign_row<2>(m, ci, tx, j); break;
-              case 3: assign_row<3>(m, ci, tx, j); break;
-              case 4: assign_row<4>(m, ci, tx, j); break;
-              case 5: assign_row<5>(m, ci, tx, j); break;
-              case 6: assign_row<6>(m, ci, tx, j); break;
-              default: assign_row<7>(m, ci, tx, j); break;
-            }
-          }
-          const int jn = j + 1;
-          if (tx == (jn & 15)) {
-            switch (jn >> 4) {
-              case 0: publish_col<0>(m, nxt, ty); break;
-              case 1: publish_col<1>(m, nxt, ty); break;
-              case 2: publish_col<2>(m, nxt, ty); break;
-              case 3: publish_col<3>(m, nxt, ty); break;
-              case 4: publish_col<4>(m, nxt, ty); break;
-              case 5: publish_col<5>(m, nxt, ty); break;
-              case 6: publish_col<6>(m, nxt, ty); break;
-              default: publish_col<7>(m, nxt, ty); break;
-            }
-          }
-          __syncthreads();
-        }
-        status = __syncthreads_or(status) ? QPB_BAD_INPUT : QPB_OK;
-        if (status == QPB_OK) {
-          if (tid < n) S.dinv[tid] = 1.0 / sqrt(S.dval[tid]);
-          __syncthreads();
-          // X^T above the diagonal: M[c][i] = Xu[i][c] / L_ii
-#pragma unroll
-          for (int b = 0; b < 8; b++) {
-            const int C = tx + 16 * b;
-            const double sc = C < n ? S.dinv[C] : 0.0;
-#pragma unroll
-            for (int a = 0; a < 8; a++) {
-              const int R = ty + 16 * a;
-              if (C > R && C < n) S.M[R * LD + C] = m[a][b] * sc;
-            }
-          }
-        }
+        const int nb = (n + 15) >> 4;
+        bool ok;
+        if (nb <= 2) ok = sweep<2>(S, n, tid);
+        else if (nb <= 4) ok = sweep<4>(S, n, tid);
+        else if (nb <= 6) ok = sweep<6>(S, n, tid);
+        else ok = sweep<8>(S, n, tid);
+        if (!ok) status = QPB_BAD_INPUT;
       }
     }
 
@@ -442,15 +563,17 @@ mpc_qp_kernel(const __grid_constant__ DevParams P, const qpb_mpc_rec* __restrict
     if (status == QPB_OK && n > 0) {
       __syncthreads();
       // ---- unconstrained minimiser f0 = -X^T X g ----------------------------------------------------------
-      const int part = tid & 1;
-      const bool on = (tid >> 1) < n;
-      const int pi = on ? (tid >> 1) : 0;
+      const TriMap tm = tri_map(n, lane, warp);
+      const bool wrA = tm.onA && lane < 8, wrB = tm.onB && lane < 8;  // class-0 lanes write the results
       {
-        const double y = tri_X(S, S.w, pi, part, on);
-        if (on && part == 0) S.zt[pi] = -y;
+        double ya, yb;
+        tri_X8(S, S.w, tm, ya, yb);
+        if (wrA) S.zt[tm.iA] = -ya;
+        if (wrB) S.zt[tm.iB] = -yb;
         __syncthreads();
-        const double f0 = tri_XT(S, S.zt, pi, n, part, on);
-        if (on && part == 0) S.f[pi] = f0;
+        tri_XT8(S, S.zt, n, tm, ya, yb);
+        if (wrA) S.f[tm.iA] = ya;
+        if (wrB) S.f[tm.iB] = yb;
         __syncthreads();
       }
 
@@ -458,6 +581,8 @@ mpc_qp_kernel(const __grid_constant__ DevParams P, const qpb_mpc_rec* __restrict
       // ---- dual active-set loop ---------------------------------------------------------------------------
       const int m = 2 * n;  // 6 rows per stance foot-step
       const double fzs = 1.0 + fmax(fabs(P.fzmin), fabs(P.fzmax));
+      const int hl = lane & 15, hh = lane >> 4;         // half-warp per working-set slot
+      const int ci = tid & 127, ck = tid >> 7;          // rank-1 updates: column ci, slots ck, ck+2, ...
       int q = 0;
       for (;;) {
         unsigned key = 0;
@@ -473,6 +598,7 @@ mpc_qp_kernel(const __grid_constant__ DevParams P, const qpb_mpc_rec* __restrict
         key = S.red[0];
 #pragma unroll
         for (int i = 1; i < NW; i++) key = max(key, S.red[i]);
+        MPC_TICK(6);
         if (key == 0u) break;  // primal feasible: optimal
         const int p = (int)(key & 0xffu);
         const int pc = p / 6, pt = p - 6 * pc;
@@ -484,20 +610,37 @@ mpc_qp_kernel(const __grid_constant__ DevParams P, const qpb_mpc_rec* __restrict
         for (;;) {  // steps towards row p until it joins the working set
           if (iters >= P.max_iter) { status = QPB_MAX_ITER; stop = true; break; }
           iters++;
-          // (1) n~ = X n_p
-          if (tid < n) S.nt[tid] = cvv * X_at(S, tid, vv) + czz * X_at(S, tid, zz);
+          // (1) n~ = X n_p, per-warp partials of |n~|^2
+          {
+            double v = 0.0;
+            if (tid < n) {
+              v = cvv * X_at(S, tid, vv) + czz * X_at(S, tid, zz);
+              S.nt[tid] = v;
+            }
+            v = warp_sum(v * v);
+            if (lane == 0) S.part[0][warp] = v;
+          }
           __syncthreads();
+          MPC_TICK(8);
           const double* ztp = S.nt;
           if (q > 0) {
-            // (2) r = N* n~
-            for (int k = warp; k < q; k += NW) {
+            // (2) r = N* n~ (half-warp per slot); the slot leader also forms the ratio-test entry
+            for (int k0 = 2 * warp; k0 < q; k0 += 2 * NW) {
+              const int k = k0 + hh;
+              const bool valid = k < q;
               double a = 0.0;
-              for (int i = lane; i < n; i += 32) a = fma(ns_at(S, k, i), S.nt[i], a);
-              a = warp_sum(a);
-              if (lane == 0) S.r[k] = a;
+              if (valid)
+                for (int i = hl; i < n; i += 16) a = fma(ns_at(S, k, i), S.nt[i], a);
+              a = half_sum(a);
+              if (valid && hl == 0) {
+                S.r[k] = a;
+                S.ratio[k] = a > 0.0 ? fmax(S.u[k], 0.0) * rcp_fast(a) : INF;
+              }
             }
             __syncthreads();
-            // (3) w = N r through the sparse rows, then z~ = n~ - X w
+            MPC_TICK(9);
+            // (3) w = N r gathered through the sparse rows in a fixed order (an atomic scatter would be one barrier
+            //     cheaper but not bitwise reproducible), then z~ = n~ - X w and per-warp partials of zeta = n~.z~
             if (tid < n) {
               const int c = tid / 3, comp = tid - 3 * c;
               double a = 0.0;
@@ -509,34 +652,48 @@ mpc_qp_kernel(const __grid_constant__ DevParams P, const qpb_mpc_rec* __restrict
               S.w[tid] = a;
             }
             __syncthreads();
-            const double xw = tri_X(S, S.w, pi, part, on);
-            if (on && part == 0) S.zt[pi] = S.nt[pi] - xw;
+            MPC_TICK(10);
+            double xa, xb;
+            tri_X8(S, S.w, tm, xa, xb);
+            double zp = 0.0;
+            if (wrA) {
+              const double za = S.nt[tm.iA] - xa;
+              S.zt[tm.iA] = za;
+              zp = za * S.nt[tm.iA];
+            }
+            if (wrB) {
+              const double zb = S.nt[tm.iB] - xb;
+              S.zt[tm.iB] = zb;
+              zp = fma(zb, S.nt[tm.iB], zp);
+            }
+            zp = warp_sum(zp);
+            if (lane == 0) S.part[1][warp] = zp;
             __syncthreads();
             ztp = S.zt;
           }
-          // (4) zeta = n~.z~, |n~|^2, ratio test -- every warp computes them redundantly (identical results)
-          double zeta = 0.0, nn = 0.0;
-          for (int i = lane; i < n; i += 32) {
-            zeta = fma(S.nt[i], ztp[i], zeta);
-            nn = fma(S.nt[i], S.nt[i], nn);
+          MPC_TICK(11);
+          // (4) zeta, |n~|^2 (fixed summation order: identical in every thread) and the ratio test
+          double nn = 0.0, zeta = 0.0;
+#pragma unroll
+          for (int i = 0; i < NW; i++) nn += S.part[0][i];
+          if (q > 0) {
+#pragma unroll
+            for (int i = 0; i < NW; i++) zeta += S.part[1][i];
+          } else {
+            zeta = nn;
           }
-          zeta = warp_sum(zeta);
-          nn = warp_sum(nn);
           const bool dep = !(zeta > 1e-13 * nn);
           double t1 = INF;
           int ks = -1;
           for (int k = lane; k < q; k += 32) {
-            const double rk = S.r[k];
-            if (rk > 0.0) {
-              const double ratio = fmax(S.u[k], 0.0) / rk;
-              if (ratio < t1) { t1 = ratio; ks = k; }
-            }
+            const double rt = S.ratio[k];
+            if (rt < t1) { t1 = rt; ks = k; }
           }
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            const double ot = __shfl_xor_sync(FULL, t1, o);
-            const int ok = __shfl_xor_sync(FULL, ks, o);
-            if (ok >= 0 && (ks < 0 || ot < t1 || (ot == t1 && ok < ks))) { t1 = ot; ks = ok; }
+          {
+            const double tmin = warp_min_nonneg(t1);
+            const unsigned who = __ballot_sync(FULL, ks >= 0 && t1 == tmin);
+            ks = who ? __shfl_sync(FULL, ks, __ffs(who) - 1) : -1;
+            t1 = tmin;
           }
           const bool has1 = ks >= 0;
           if (dep && !has1) {
@@ -547,25 +704,31 @@ mpc_qp_kernel(const __grid_constant__ DevParams P, const qpb_mpc_rec* __restrict
             __syncthreads();
             break;
           }
-          const double t2 = dep ? INF : -sp / zeta;
+          const double iz = dep ? 0.0 : rcp_fast(zeta);
+          const double t2 = dep ? INF : -sp * iz;
           const bool full = !dep && (!has1 || t2 <= t1);
           const double t = full ? t2 : t1;
+          MPC_TICK(12);
           // (5) primal and dual step
           if (!dep) {
-            const double df = tri_XT(S, ztp, pi, n, part, on);
-            if (on && part == 0) S.f[pi] = fma(t, df, S.f[pi]);
+            double da, db;
+            tri_XT8(S, ztp, n, tm, da, db);
+            if (wrA) S.f[tm.iA] = fma(t, da, S.f[tm.iA]);
+            if (wrB) S.f[tm.iB] = fma(t, db, S.f[tm.iB]);
             sp = fma(t, zeta, sp);
           }
           if (tid < q) S.u[tid] = fma(-t, S.r[tid], S.u[tid]);
           up += t;
+          MPC_TICK(13);
           if (full) {
             if (q >= QCAP) { status = QPB_MAX_ITER; stop = true; __syncthreads(); break; }  // cannot happen: rows are independent
-            const double iz = 1.0 / zeta;
-            for (int idx = tid; idx < (q + 1) * n; idx += NT) {
-              const int k = idx / n, i = idx - k * n;
-              const double val = ztp[i] * iz;
-              double& e = ns_at(S, k, i);
-              e = k < q ? fma(-S.r[k], val, e) : val;
+            if (ci < n) {
+              const double val = ztp[ci] * iz;
+              for (int k = ck; k < q; k += 2) {
+                double& e = ns_at(S, k, ci);
+                e = fma(-S.r[k], val, e);
+              }
+              if ((q & 1) == ck) ns_at(S, q, ci) = val;
             }
             if (tid == 0) {
               S.A[q] = p;
@@ -575,23 +738,28 @@ mpc_qp_kernel(const __grid_constant__ DevParams P, const qpb_mpc_rec* __restrict
             }
             q++;
             __syncthreads();
+            MPC_TICK(14);
             break;
           }
           // partial step: slot ks leaves the working set
-          for (int j = warp; j < q; j += NW) {
+          for (int k0 = 2 * warp; k0 < q; k0 += 2 * NW) {
+            const int j = k0 + hh;
+            const bool valid = j < q;
             double a = 0.0;
-            for (int i = lane; i < n; i += 32) a = fma(ns_at(S, j, i), ns_at(S, ks, i), a);
-            a = warp_sum(a);
-            if (lane == 0) S.dd[j] = a;
+            if (valid)
+              for (int i = hl; i < n; i += 16) a = fma(ns_at(S, j, i), ns_at(S, ks, i), a);
+            a = half_sum(a);
+            if (valid && hl == 0) S.dd[j] = a;
           }
           __syncthreads();
-          const double idl = 1.0 / S.dd[ks];
-          for (int idx = tid; idx < q * n; idx += NT) {
-            const int j = idx / n, i = idx - j * n;
-            if (j != ks) {
-              double& e = ns_at(S, j, i);
-              e = fma(-S.dd[j] * idl, ns_at(S, ks, i), e);
-            }
+          const double idl = rcp_fast(S.dd[ks]);
+          if (ci < n) {
+            const double nu = ns_at(S, ks, ci);
+            for (int j = ck; j < q; j += 2)
+              if (j != ks) {
+                double& e = ns_at(S, j, ci);
+                e = fma(-S.dd[j] * idl, nu, e);
+              }
           }
           __syncthreads();
           const int last = q - 1;
@@ -606,6 +774,7 @@ mpc_qp_kernel(const __grid_constant__ DevParams P, const qpb_mpc_rec* __restrict
           }
           q--;
           __syncthreads();
+          MPC_TICK(15);
         }
         if (stop) break;
       }
