@@ -35,6 +35,13 @@ METRIC = "balance QPs/sec (batched)"
 UNIT = "QP/s"
 N_ROTATE = 8  # distinct device batches cycled through so a step never re-reads L2-resident inputs
 
+# BASELINE config 4 (10-step convex-MPC QP, 120 variables): a secondary workload with its own
+# metric.  The reference has no code for it, so its CPU arm is the oracle port (kind "port", parity unpinned).
+MPC_N, MPC_SEED = 65536, 20260104
+MPC_METRIC = "MPC QPs/sec (10-step horizon, 120 variables, batched)"
+MPC_DESC = "cfg4: 65536 10-step convex-MPC QPs per GPU (stand/trot/crawl gaits mixed), mu=0.6"
+FP64_PEAK_TFLOPS = 148 * 64 * 2 * 1.965e9 / 1e12  # nominal; tools/ubench_fp64 measures 64.0 DFMA lanes/clk/SM
+
 
 def measured_peak_hbm():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -310,16 +317,171 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def mpc_algorithmic_flops(contact, iters):
+    """FP64 flops the MPC path needs per QP, as a model: Cholesky + triangular inverse of the n x n Hessian (2 n^3 / 3),
+    its assembly (about 40 per lower-triangle entry) and two triangular mat-vecs plus the N* updates per iteration."""
+    n = 3.0 * contact.reshape(len(contact), -1).sum(axis=1)
+    q = np.minimum(iters, n)
+    return 2.0 * n**3 / 3.0 + 20.0 * n * n + iters * (2.0 * n * n + 8.0 * 0.5 * q * n)
+
+
+def run_mpc_reference(args):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    import oracle
+    from quadruped_control_b200.records import default_mpc_params
+
+    p = default_mpc_params(MU)
+    cores = os.cpu_count() or 1
+    R_full = states.generate_mpc(4096, MPC_SEED)
+    t0 = time.perf_counter()
+    oracle.mpc_batch(p, R_full[:256], cores)
+    rate = 256 / (time.perf_counter() - t0)
+    total_steps = args.steps + args.warmup
+    per_step = int(min(len(R_full), max(64, rate * 100.0 / total_steps)))
+    R = np.ascontiguousarray(R_full[:per_step])
+    for _ in range(args.warmup):
+        oracle.mpc_batch(p, R, cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out = oracle.mpc_batch(p, R, cores)
+    dt = time.perf_counter() - t0
+    assert (out["status"] == 0).all()
+    value = per_step * args.steps / dt
+    sample = f"first {per_step} of {MPC_N} records per step, {cores} host threads; oracle port (the reference has no MPC code)"
+    print(json.dumps({
+        "impl": "reference", "metric": MPC_METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": {"workload": MPC_DESC, "qps_per_step": per_step},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}), flush=True)
+
+
+def run_mpc(args):
+    """--workload cfg4: the batched 10-step convex-MPC QP through qpb_mpc_batch_packed / qpb_mpc_batch_host."""
+    import torch
+
+    from quadruped_control_b200 import lib
+    from quadruped_control_b200.records import MPC_ALGO_BYTES_PER_QP, MPC_OUT_DTYPE, MPC_REC_DTYPE, default_mpc_params
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback for the product path)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    n = MPC_N
+    p = default_mpc_params(MU)
+    solver = lib.MpcSolver(p, device=local_rank)
+    host = [states.generate_mpc(n, MPC_SEED + 1000 * k, lo=rank * n) for k in range(2)]  # 143 MB each: larger than L2
+    d_in = [torch.from_numpy(b.view(np.uint8).reshape(-1)).to(dev) for b in host]
+    d_out = [torch.empty(n * MPC_OUT_DTYPE.itemsize, dtype=torch.uint8, device=dev) for _ in range(2)]
+    stream = torch.cuda.current_stream()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        solver.solve_packed(d_in[i % 2], d_out[i % 2], n, stream.cuda_stream)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    barrier()
+    launches0 = solver.launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_begin = time.perf_counter()
+    ev0.record(stream)
+    for i in range(args.steps):
+        solver.solve_packed(d_in[i % 2], d_out[i % 2], n, stream.cuda_stream)
+    ev1.record(stream)
+    barrier()
+    t_end = time.perf_counter()
+    launches = solver.launches - launches0
+    clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
+    last = d_out[(args.steps - 1) % 2].cpu().numpy().view(MPC_OUT_DTYPE)
+    failed = int((last["status"] != 0).sum())
+    elapsed_ms, (tot_launches, tot_failed) = reduce_report(ev0.elapsed_time(ev1), [launches, failed], dist, dev)
+    total_qps = world * n * args.steps / (elapsed_ms * 1e-3)
+
+    pin_in, pin_out = lib.PinnedBuffer(n, MPC_REC_DTYPE), lib.PinnedBuffer(n, MPC_OUT_DTYPE)
+    pin_in.array[:] = host[0]
+    e2e_steps = max(3, min(args.steps, 10))
+    solver.solve_host(pin_in.array, pin_out.array)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        solver.solve_host(pin_in.array, pin_out.array)
+    e2e_local = (time.perf_counter() - t0) * 1e3
+    barrier()
+    e2e_ms, _ = reduce_report(e2e_local, [0], dist, dev)
+    e2e_qps = world * n * e2e_steps / (e2e_ms * 1e-3)
+
+    if rank == 0:
+        import oracle
+
+        cores = os.cpu_count() or 1
+        hb = host[(args.steps - 1) % 2]
+        idx = np.arange(0, n, n // 256)
+        ref = oracle.mpc_batch(p, np.ascontiguousarray(hb[idx]), cores)
+        err = float((np.abs(last["U"][idx] - ref["U"]).max(axis=1) / np.maximum(np.abs(ref["U"]).max(axis=1), 1.0)).max())
+        t0 = time.perf_counter()
+        oracle.mpc_batch(p, hb[:512], cores)
+        rate = 512 / (time.perf_counter() - t0)
+        m = int(min(n, max(512, rate * 10.0)))
+        t0 = time.perf_counter()
+        oracle.mpc_batch(p, hb[:m], cores)
+        cpu_rate = m / (time.perf_counter() - t0)
+        peak, peak_src = measured_peak_hbm()
+        kernel_ms = elapsed_ms / args.steps
+        achieved = MPC_ALGO_BYTES_PER_QP * n / (kernel_ms * 1e-3) / 1e9
+        flops = float(mpc_algorithmic_flops(hb["contact"], last["iters"].astype(np.float64)).mean())
+        tflops = flops * n / (kernel_ms * 1e-3) / 1e12
+        print(json.dumps({
+            "metric": MPC_METRIC, "value": total_qps, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": MPC_DESC, "qps_per_step_per_gpu": n, "global_batch": world * n, "parallelism": f"batch-sharded x{world}",
+                       "l2": "inputs larger than L2 (143 MB of records per step, two batches alternate)",
+                       "iters_mean": float(last["iters"].mean()), "iters_max": int(last["iters"].max())},
+            "max_rel_force_err_vs_oracle": err, "failed_qps": int(tot_failed),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic_per_launch("cfg4"),
+                         "peak_source": peak_src, "algorithmic_bytes_per_qp": MPC_ALGO_BYTES_PER_QP, "kernel": "mpc_qp_kernel", "kernel_ms": kernel_ms,
+                         "fp64": {"achieved_tflops": tflops, "peak_tflops": FP64_PEAK_TFLOPS, "frac": tflops / FP64_PEAK_TFLOPS,
+                                  "algorithmic_flops_per_qp": flops, "peak_source": "nominal 148 SM x 64 lanes x 2 x 1.965 GHz (tools/ubench_fp64: 64.0 lanes/clk/SM measured)"},
+                         "note": "compute path: ~2e6 FP64 flops and 3.1 KB per QP; the FP64 fraction is the meaningful one (SURVEY.md 8d)"},
+            "cpu_baseline": {"value": cpu_rate, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"first {m} records, {cores} threads; oracle/mpc_oracle.c (dense condensed model + Goldfarb-Idnani); the reference has no MPC code"},
+            "e2e": {"value": e2e_qps, "unit": UNIT, "h2d_bytes_per_step": n * MPC_REC_DTYPE.itemsize, "d2h_bytes_per_step": n * MPC_OUT_DTYPE.itemsize,
+                    "steps": e2e_steps, "ok": bool((pin_out.array["status"] == 0).all()), "api": "qpb_mpc_batch_host (pinned host buffers, staged H2D/kernel/D2H ring)"},
+            "gpu_launches": int(tot_launches), "clocks": clocks}), flush=True)
+    pin_in.free()
+    pin_out.free()
+    solver.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=("ours", "reference"), default="ours")
-    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="cfg2")
+    ap.add_argument("--workload", choices=sorted(WORKLOADS) + ["cfg4"], default="cfg2")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
-    if args.impl == "reference":
+    if args.workload == "cfg4":
+        (run_mpc_reference if args.impl == "reference" else run_mpc)(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)
