@@ -161,6 +161,58 @@ int qpb_host_free(void* ptr);
 /* Number of CUDA kernels this handle has launched so far (for the benchmark's gpu_launches). */
 int64_t qpb_launch_count(const qpb_handle* h);
 
+/* ---- The caller code either side of the tick -----------------------------------------
+ * Foothold planner + swing-foot trajectory: FootPlanner::singleFoot (foot_planner.cpp:76-104) when a leg switches
+ * stance -> swing, FootTrajectory/FootTrajectoryManager (trajectory.cpp:220-254, 300-307, 323-324, 366-388) every tick,
+ * as the reference calls them at commander_node.cpp:429-461 and 482-488.  Stateless per call: what the reference keeps
+ * in FootPlanner::state_map_ and FootTrajectoryManager::traj_map_ lives in the caller's qpb_plan_rec. */
+typedef struct qpb_plan_params {
+  double k_raibert;        /* FootPlanner::k_ = 0.01, foot_planner.cpp:26 */
+  double g;                /* 9.81, foot_planner.cpp:22 */
+  double thigh_offset[12]; /* base -> thigh per leg (+-0.196, +-0.127, 0), foot_planner.cpp:28-42 */
+  double height, t_swing, t_stance; /* gait/height, t_swing, t_stance: mit_cheetah_config.yaml:17-19 */
+} qpb_plan_params;
+
+typedef struct qpb_plan_rec { /* 240 bytes */
+  double p_start[12], p_final[12]; /* FootTrajBounds per leg, world frame (types.hpp:52-65) */
+  double phase[4];                 /* GaitMap[leg].second */
+  uint8_t replan[4];               /* in: 1 = the leg switched stance -> swing this tick; cleared once planned */
+  uint8_t pad[12];
+} qpb_plan_rec;
+
+int qpb_default_plan_params(qpb_plan_params* out);
+int qpb_set_plan_params(qpb_handle* h, const qpb_plan_params* p);
+/* For every swing leg (qpb_state_rec.contact == 0): re-plan p_start / p_final if flagged, then write the reference foot
+ * position and velocity (world frame) into d_swing[i].foot_ref_pos / foot_ref_vel, which qpb_tick_batch_packed consumes.
+ * Stance legs are left untouched.  Device pointers; asynchronous on stream. */
+int qpb_plan_batch(qpb_handle* h, int64_t n, const qpb_state_rec* d_states, qpb_plan_rec* d_plan, qpb_swing_rec* d_swing,
+                   void* stream);
+
+/* Message adapters.  quadruped_msgs/CoMState and sensor_msgs/JointState flattened in message field order; the
+ * adapter does what stateCallback, jointCallback (commander_node.cpp:127-187) and forwardKinematics (:383-384) do:
+ * fills Rwb, x, xdot, w, q, feet of the state record and qdot of the swing record (other fields are left as they are). */
+typedef struct qpb_com_msg {
+  double position[3];
+  double orientation[4]; /* geometry_msgs/Quaternion: x y z w */
+  double linear[3], angular[3];
+} qpb_com_msg;
+typedef struct qpb_joint_msg {
+  double position[12], velocity[12]; /* joint_names order: 4 hips, 4 thighs, 4 calves, each RL FL RR FR (yaml:35-37) */
+} qpb_joint_msg;
+int qpb_adapt_inputs_batch(qpb_handle* h, int64_t n, const qpb_com_msg* d_com, const qpb_joint_msg* d_joints,
+                           qpb_state_rec* d_states, qpb_swing_rec* d_swing, void* stream);
+
+/* quadruped_msgs/JointTorqueCmd.torque as commander_node.cpp:517-533 fills it: legs in std::map order (FL FR RL RR),
+ * stance legs only when the QP returned forces, three joints each, clamped to [tau_min, tau_max]; leg[k] names the leg
+ * of entry k (stands in for actuator_name), count = number of entries. */
+typedef struct qpb_torque_cmd {
+  double torque[12];
+  uint8_t leg[12];
+  int32_t count;
+} qpb_torque_cmd;
+int qpb_torque_cmd_batch(qpb_handle* h, int64_t n, const qpb_state_rec* d_states, const qpb_out_rec* d_out,
+                         qpb_torque_cmd* d_cmd, void* stream);
+
 /* ---- 10-step convex-MPC ground-reaction-force QP (BASELINE.json config 4) --------------
  * The reference has NO code for this path (README.md:22-26 describes only the instantaneous QP of
  * balance_controller.cpp), so there is no reference interface to cite: the formulation is the condensed

@@ -15,7 +15,7 @@ _lib = None
 
 def build(force=False):
     if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < max(
-        os.path.getmtime(os.path.join(_HERE, f)) for f in ("qpb_oracle.c", "qpb_oracle.h", "mpc_oracle.c", "mpc_oracle.h")
+        os.path.getmtime(os.path.join(_HERE, f)) for f in ("qpb_oracle.c", "qpb_oracle.h", "mpc_oracle.c", "mpc_oracle.h", "plan_oracle.c", "plan_oracle.h")
     ):
         subprocess.run(["make", "-C", _HERE, "-B"], check=True, capture_output=True)
     return _LIB_PATH
@@ -272,3 +272,92 @@ def mpc_batch(params, recs, nthreads=1):
     out = np.zeros(len(recs), dtype=MPC_OUT_DTYPE)
     _mpc_protos().orc_mpc_batch(ctypes.byref(params), recs.ctypes.data, len(recs), out.ctypes.data, int(nthreads))
     return out
+
+
+# ---- foothold planner + swing-foot trajectory, message adapters (rank 3) ---------------
+def _plan_protos():
+    L = lib()
+    if not getattr(L, "_plan_ready", False):
+        vp, dp = ctypes.c_void_p, ctypes.POINTER(ctypes.c_double)
+        L.orc_default_plan_params.argtypes = [vp]
+        L.orc_single_foot.argtypes = [vp, ctypes.c_int, vp, dp]
+        L.orc_foot_trajectory.argtypes = [dp, dp, dp, dp]
+        L.orc_foot_trajectory.restype = ctypes.c_int
+        L.orc_track_trajectory.argtypes = [dp, ctypes.c_double, dp, dp]
+        L.orc_plan_batch.argtypes = [vp, vp, vp, vp, ctypes.c_int64]
+        L.orc_adapt_inputs.argtypes = [vp, vp, vp, vp, vp]
+        L.orc_torque_cmd.argtypes = [vp, dp, ctypes.POINTER(ctypes.c_int), dp, ctypes.POINTER(ctypes.c_int)]
+        L.orc_torque_cmd.restype = ctypes.c_int
+        L._plan_ready = True
+    return L
+
+
+def plan_default_params():
+    from quadruped_control_b200.records import PlanParams
+
+    p = PlanParams()
+    _plan_protos().orc_default_plan_params(ctypes.byref(p))
+    return p
+
+
+def single_foot(pp, leg, state):
+    state = np.ascontiguousarray(state).reshape(1)
+    out = np.empty(3)
+    _plan_protos().orc_single_foot(ctypes.byref(pp), int(leg), state.ctypes.data, _dp(out))
+    return out
+
+
+def foot_trajectory(p_start, p_center, p_final):
+    a, b, c = (np.ascontiguousarray(v, dtype=np.float64) for v in (p_start, p_center, p_final))
+    coef = np.empty(21)
+    rc = _plan_protos().orc_foot_trajectory(_dp(a), _dp(b), _dp(c), _dp(coef))
+    return rc, coef.reshape(7, 3)
+
+
+def track_trajectory(coef, t):
+    coef = np.ascontiguousarray(coef, dtype=np.float64).reshape(21)
+    pos, vel = np.empty(3), np.empty(3)
+    _plan_protos().orc_track_trajectory(_dp(coef), float(t), _dp(pos), _dp(vel))
+    return pos, vel
+
+
+def plan_batch(pp, states, plan, swing):
+    """In place: re-plans the flagged swing legs in ``plan`` and writes the reference foot states into ``swing``."""
+    from quadruped_control_b200.records import PLAN_DTYPE
+
+    assert states.dtype == STATE_DTYPE and plan.dtype == PLAN_DTYPE and swing.dtype == SWING_DTYPE
+    assert states.flags.c_contiguous and plan.flags.c_contiguous and swing.flags.c_contiguous
+    _plan_protos().orc_plan_batch(ctypes.byref(pp), states.ctypes.data, plan.ctypes.data, swing.ctypes.data, len(states))
+
+
+def ref_plan_batch(pp, states, plan, swing):
+    """Same through the reference's own FootPlanner / FootTrajectoryManager (oracle/_ref)."""
+    R = ref_lib()
+    R.ref_plan_batch.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_longlong]
+    R.ref_plan_batch(ctypes.byref(pp), states.ctypes.data, plan.ctypes.data, swing.ctypes.data, len(states))
+
+
+def ref_single_foot(t_stance, leg, state):
+    state = np.ascontiguousarray(state).reshape(1)
+    out = np.empty(3)
+    R = ref_lib()
+    R.ref_single_foot.argtypes = [ctypes.c_double, ctypes.c_int, ctypes.c_void_p, ctypes.POINTER(ctypes.c_double)]
+    R.ref_single_foot(float(t_stance), int(leg), state.ctypes.data, _dp(out))
+    return out
+
+
+def adapt_inputs(params, com, joints, states, swing):
+    """In place: CoMState + JointState messages -> Rwb, x, xdot, w, q, feet of ``states`` and qdot of ``swing``."""
+    L = _plan_protos()
+    for i in range(len(com)):
+        L.orc_adapt_inputs(ctypes.byref(params), com[i:i + 1].ctypes.data, joints[i:i + 1].ctypes.data,
+                           states[i:i + 1].ctypes.data, swing[i:i + 1].ctypes.data)
+
+
+def torque_cmd(params, tau, present):
+    tau = np.ascontiguousarray(tau, dtype=np.float64).reshape(12)
+    pres = (ctypes.c_int * 4)(*[int(v) for v in present])
+    torque = np.zeros(12)
+    legs = (ctypes.c_int * 12)()
+    n = _plan_protos().orc_torque_cmd(ctypes.byref(params), _dp(tau), pres, _dp(torque), legs)
+    return n, torque, np.array(list(legs), dtype=np.int64)

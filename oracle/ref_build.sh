@@ -9,7 +9,8 @@ REF=/root/reference/quadruped_controller
 OUT="$HERE/_ref"
 mkdir -p "$OUT"
 SRC="$REF/src/quadruped_controller"
-if [ "$OUT/libqpb_ref.so" -nt "$HERE/ref_glue.cpp" ] && [ "$OUT/libqpb_ref.so" -nt "$HERE/qpb_oracle.c" ] && \
+if [ "$OUT/libqpb_ref.so" -nt "$HERE/ref_glue.cpp" ] && [ "$OUT/libqpb_ref.so" -nt "$HERE/ref_glue_plan.cpp" ] && [ "$OUT/libqpb_ref.so" -nt "$HERE/plan_oracle.c" ] && \
+   [ "$OUT/libqpb_ref.so" -nt "$HERE/ref_stubs/quadruped_controller/math/rigid3d.hpp" ] && [ "$OUT/libqpb_ref.so" -nt "$HERE/qpb_oracle.c" ] && \
    [ "$OUT/libqpb_ref.so" -nt "$HERE/ref_stubs/armadillo" ] && [ "$OUT/libqpb_ref.so" -nt "$HERE/ref_stubs/qpOASES.hpp" ]; then
   exit 0
 fi
@@ -17,6 +18,7 @@ gcc -O2 -std=c99 -fPIC -ffp-contract=off -c "$HERE/qpb_oracle.c" -o "$OUT/qpb_or
 g++ -O2 -std=c++17 -fPIC -shared -ffp-contract=off -w \
     -I "$HERE/ref_stubs" -I "$REF/include" -I "$HERE" \
     "$SRC/balance_controller.cpp" "$SRC/kinematics.cpp" "$SRC/gait.cpp" "$SRC/math/numerics.cpp" "$SRC/joint_controller.cpp" \
+    "$SRC/foot_planner.cpp" "$SRC/trajectory.cpp" "$HERE/ref_glue_plan.cpp" \
     "$HERE/ref_glue.cpp" "$OUT/qpb_oracle.o" -o "$OUT/libqpb_ref.so" -lm -lpthread
 rm -f "$OUT/qpb_oracle.o"
 echo "built $OUT/libqpb_ref.so"

@@ -8,4 +8,8 @@ extern int qpb_ref_error_count;  // bumped by every ROS_ERROR the reference rais
 #define ROS_WARN_STREAM_NAMED(name, args) do { } while (0)
 #define ROS_INFO_STREAM_NAMED(name, args) do { } while (0)
 #define ROS_DEBUG_STREAM_NAMED(name, args) do { } while (0)
+#define ROS_ERROR_NAMED(name, ...) do { qpb_ref_error_count++; } while (0)
+#define ROS_WARN_NAMED(name, ...) do { } while (0)
+#define ROS_INFO_NAMED(name, ...) do { } while (0)
+#define ROS_DEBUG_NAMED(name, ...) do { } while (0)
 #endif

@@ -13,6 +13,7 @@
 #include "qpb_internal.h"
 #include "qpb_kernel.cuh"
 #include "qpb_kernel16.cuh"
+#include "qpb_plan.cuh"
 #include "qpb_swing.cuh"
 
 namespace {
@@ -77,6 +78,7 @@ struct qpb_handle {
   qpb_out_rec* d_out[kHostSlots] = {};
   qpb_swing_rec* d_sw[kHostSlots] = {};
   qpb_joint_gains* d_gains = nullptr;  // JointController gains for the swing-leg half of the tick
+  qpb_plan_params* d_plan = nullptr;   // FootPlanner / FootTrajectoryManager constants
   std::atomic<int64_t> launches{ 0 };
   // ring of work-ticket counters, one per in-flight launch of the balance kernel
   unsigned long long* d_tickets = nullptr;
@@ -264,6 +266,12 @@ int qpb_create(const qpb_params* params, int device, qpb_handle** out) {
     const qpb_joint_gains g = { { 0.0, 0.0, 0.0 }, { 40.0, 40.0, 50.0 }, { 1.0, 1.0, 1.0 } };  // mit_cheetah_config.yaml:50-53
     e = cudaMemcpy(h->d_gains, &g, sizeof(g), cudaMemcpyHostToDevice);
   }
+  if (e == cudaSuccess) e = cudaMalloc(&h->d_plan, sizeof(qpb_plan_params));
+  if (e == cudaSuccess) {
+    qpb_plan_params pp;
+    qpb_default_plan_params(&pp);
+    e = cudaMemcpy(h->d_plan, &pp, sizeof(pp), cudaMemcpyHostToDevice);
+  }
   if (e == cudaSuccess) e = cudaMalloc(&h->d_tickets, kTicketSlots * sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaMemset(h->d_tickets, 0, kTicketSlots * sizeof(unsigned long long));
   if (e == cudaSuccess)
@@ -284,6 +292,7 @@ int qpb_create(const qpb_params* params, int device, qpb_handle** out) {
     if (h->d_params) cudaFree(h->d_params);
     if (h->d_tickets) cudaFree(h->d_tickets);
     if (h->d_gains) cudaFree(h->d_gains);
+    if (h->d_plan) cudaFree(h->d_plan);
     delete h;
     return fail(QPB_ERR_CUDA, msg);
   }
@@ -313,6 +322,7 @@ int qpb_destroy(qpb_handle* h) {
   if (h->d_params) cudaFree(h->d_params);
   if (h->d_tickets) cudaFree(h->d_tickets);
   if (h->d_gains) cudaFree(h->d_gains);
+  if (h->d_plan) cudaFree(h->d_plan);
   delete h;
   return QPB_SUCCESS;
 }
@@ -448,6 +458,80 @@ int qpb_fk_batch_host(qpb_handle* h, int64_t n, const double* q, double* feet_bo
   cudaFree(d);
   if (e != cudaSuccess) return fail(QPB_ERR_CUDA, std::string("qpb_fk_batch_host: ") + cudaGetErrorString(e));
   return rc;
+}
+
+int qpb_default_plan_params(qpb_plan_params* p) {
+  if (!p) return fail(QPB_ERR_INVALID_ARG, "qpb_default_plan_params: null pointer");
+  std::memset(p, 0, sizeof(*p));
+  p->k_raibert = 0.01;
+  p->g = 9.81;
+  const double sx[4] = { -1.0, 1.0, -1.0, 1.0 }, sy[4] = { 1.0, 1.0, -1.0, -1.0 };  // RL FL RR FR
+  for (int leg = 0; leg < 4; leg++) {
+    p->thigh_offset[3 * leg] = sx[leg] * 0.196;
+    p->thigh_offset[3 * leg + 1] = sy[leg] * 0.127;
+    p->thigh_offset[3 * leg + 2] = 0.0;
+  }
+  p->height = 0.08;
+  p->t_swing = 0.18;
+  p->t_stance = 0.8;
+  return QPB_SUCCESS;
+}
+
+int qpb_set_plan_params(qpb_handle* h, const qpb_plan_params* p) {
+  if (!h || !p) return fail(QPB_ERR_INVALID_ARG, "qpb_set_plan_params: null pointer");
+  const double* v = reinterpret_cast<const double*>(p);
+  for (size_t i = 0; i < sizeof(*p) / sizeof(double); i++)
+    if (!std::isfinite(v[i])) return fail(QPB_ERR_BAD_PARAMS, "qpb_set_plan_params: non-finite parameter");
+  if (!(p->g > 0.0) || !(p->t_swing > 0.0) || !(p->t_stance >= 0.0))
+    return fail(QPB_ERR_BAD_PARAMS, "qpb_set_plan_params: g and t_swing must be > 0, t_stance >= 0");
+  DeviceGuard guard(h->device);
+  if (!guard.ok) return fail(QPB_ERR_CUDA, "cudaSetDevice failed");
+  QPB_CUDA(cudaDeviceSynchronize());  // earlier launches may still read the old constants
+  QPB_CUDA(cudaMemcpy(h->d_plan, p, sizeof(*p), cudaMemcpyHostToDevice));
+  return QPB_SUCCESS;
+}
+
+int qpb_plan_batch(qpb_handle* h, int64_t n, const qpb_state_rec* d_states, qpb_plan_rec* d_plan, qpb_swing_rec* d_swing,
+                   void* stream) {
+  if (!h || n < 0 || (n > 0 && (!d_states || !d_plan || !d_swing))) return fail(QPB_ERR_INVALID_ARG, "qpb_plan_batch: bad argument");
+  if (n == 0) return QPB_SUCCESS;
+  DeviceGuard guard(h->device);
+  if (!guard.ok) return fail(QPB_ERR_CUDA, "cudaSetDevice failed");
+  const int threads = 128;
+  qpb::plan_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, static_cast<cudaStream_t>(stream)>>>(
+      h->d_plan, d_states, d_plan, d_swing, n);
+  h->launches.fetch_add(1, std::memory_order_relaxed);
+  QPB_CUDA(cudaGetLastError());
+  return QPB_SUCCESS;
+}
+
+int qpb_adapt_inputs_batch(qpb_handle* h, int64_t n, const qpb_com_msg* d_com, const qpb_joint_msg* d_joints,
+                           qpb_state_rec* d_states, qpb_swing_rec* d_swing, void* stream) {
+  if (!h || n < 0 || (n > 0 && (!d_com || !d_joints || !d_states || !d_swing)))
+    return fail(QPB_ERR_INVALID_ARG, "qpb_adapt_inputs_batch: bad argument");
+  if (n == 0) return QPB_SUCCESS;
+  DeviceGuard guard(h->device);
+  if (!guard.ok) return fail(QPB_ERR_CUDA, "cudaSetDevice failed");
+  const int threads = 128;
+  qpb::adapt_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, static_cast<cudaStream_t>(stream)>>>(
+      h->d_params, d_com, d_joints, d_states, d_swing, n);
+  h->launches.fetch_add(1, std::memory_order_relaxed);
+  QPB_CUDA(cudaGetLastError());
+  return QPB_SUCCESS;
+}
+
+int qpb_torque_cmd_batch(qpb_handle* h, int64_t n, const qpb_state_rec* d_states, const qpb_out_rec* d_out,
+                         qpb_torque_cmd* d_cmd, void* stream) {
+  if (!h || n < 0 || (n > 0 && (!d_states || !d_out || !d_cmd))) return fail(QPB_ERR_INVALID_ARG, "qpb_torque_cmd_batch: bad argument");
+  if (n == 0) return QPB_SUCCESS;
+  DeviceGuard guard(h->device);
+  if (!guard.ok) return fail(QPB_ERR_CUDA, "cudaSetDevice failed");
+  const int threads = 128;
+  qpb::torque_cmd_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, static_cast<cudaStream_t>(stream)>>>(
+      h->d_params, d_states, d_out, d_cmd, n);
+  h->launches.fetch_add(1, std::memory_order_relaxed);
+  QPB_CUDA(cudaGetLastError());
+  return QPB_SUCCESS;
 }
 
 int qpb_host_alloc(void** ptr, size_t bytes) {

@@ -9,7 +9,8 @@ import os
 
 import numpy as np
 
-from .records import MPC_OUT_DTYPE, MPC_REC_DTYPE, OUT_DTYPE, STATE_DTYPE, SWING_DTYPE, JointGains, MpcParams, Params
+from .records import (MPC_OUT_DTYPE, MPC_REC_DTYPE, OUT_DTYPE, STATE_DTYPE, SWING_DTYPE, JointGains, MpcParams, Params,
+                      PlanParams)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("QPB_LIB") or os.path.join(_HERE, "libqpb200.so")  # QPB_LIB: experiment builds
@@ -33,6 +34,11 @@ EXPORTS = (
     "qpb_host_alloc",
     "qpb_host_free",
     "qpb_launch_count",
+    "qpb_default_plan_params",
+    "qpb_set_plan_params",
+    "qpb_plan_batch",
+    "qpb_adapt_inputs_batch",
+    "qpb_torque_cmd_batch",
     "qpb_mpc_default_params",
     "qpb_mpc_create",
     "qpb_mpc_destroy",
@@ -76,6 +82,11 @@ def load():
     L.qpb_host_free.argtypes = [vp]
     L.qpb_launch_count.argtypes = [vp]
     L.qpb_launch_count.restype = i64
+    L.qpb_default_plan_params.argtypes = [ctypes.POINTER(PlanParams)]
+    L.qpb_set_plan_params.argtypes = [vp, ctypes.POINTER(PlanParams)]
+    L.qpb_plan_batch.argtypes = [vp, i64, vp, vp, vp, vp]
+    L.qpb_adapt_inputs_batch.argtypes = [vp, i64, vp, vp, vp, vp, vp]
+    L.qpb_torque_cmd_batch.argtypes = [vp, i64, vp, vp, vp, vp]
     L.qpb_mpc_default_params.argtypes = [ctypes.POINTER(MpcParams)]
     L.qpb_mpc_create.argtypes = [ctypes.POINTER(MpcParams), ctypes.c_int, ctypes.POINTER(vp)]
     L.qpb_mpc_destroy.argtypes = [vp]
@@ -191,6 +202,20 @@ class BalanceSolver:
             out = np.empty(states.shape[0], dtype=OUT_DTYPE)
         _check(load().qpb_tick_batch_host(self._h, states.shape[0], states.ctypes.data, swing.ctypes.data, out.ctypes.data), "qpb_tick_batch_host")
         return out
+
+    # -- the caller code either side of the tick: planner + swing trajectory, message adapters (device pointers) --
+    def set_plan_params(self, pp: PlanParams):
+        _check(load().qpb_set_plan_params(self._h, ctypes.byref(pp)), "qpb_set_plan_params")
+
+    def plan(self, d_states, d_plan, d_swing, n, stream=None):
+        _check(load().qpb_plan_batch(self._h, int(n), _ptr(d_states), _ptr(d_plan), _ptr(d_swing), stream), "qpb_plan_batch")
+
+    def adapt_inputs(self, d_com, d_joints, d_states, d_swing, n, stream=None):
+        _check(load().qpb_adapt_inputs_batch(self._h, int(n), _ptr(d_com), _ptr(d_joints), _ptr(d_states), _ptr(d_swing), stream),
+               "qpb_adapt_inputs_batch")
+
+    def torque_cmd(self, d_states, d_out, d_cmd, n, stream=None):
+        _check(load().qpb_torque_cmd_batch(self._h, int(n), _ptr(d_states), _ptr(d_out), _ptr(d_cmd), stream), "qpb_torque_cmd_batch")
 
     def jt(self, n, q, grf, contact, tau, stream=None):
         _check(load().qpb_jt_batch(self._h, int(n), _ptr(q), _ptr(grf), _ptr(contact), _ptr(tau), stream), "qpb_jt_batch")

@@ -186,3 +186,49 @@ def default_mpc_params(mu=0.6):
     p.alpha = 4e-5
     p.max_iter = 1000
     return p
+
+
+# ---- foothold planner + swing-foot trajectory and message adapters (rank 3) --------------
+# One PLAN item per robot: the reference's FootTrajBounds per leg (types.hpp:52-65; the state FootTrajectoryManager
+# keeps in traj_map_), the gait phase of every leg (GaitMap[leg].second) and the "switched stance -> swing this tick"
+# flags FootPlanner::updateStates derives (foot_planner.cpp:106-157).
+PLAN_DTYPE = np.dtype([("p_start", "<f8", (12,)), ("p_final", "<f8", (12,)), ("phase", "<f8", (4,)), ("replan", "u1", (4,)),
+                       ("pad", "u1", (12,))])
+assert PLAN_DTYPE.itemsize == 240
+
+# quadruped_msgs/CoMState in message field order (pose.position, pose.orientation x y z w, twist.linear, twist.angular)
+COM_MSG_DTYPE = np.dtype([("position", "<f8", (3,)), ("orientation", "<f8", (4,)), ("linear", "<f8", (3,)), ("angular", "<f8", (3,))])
+assert COM_MSG_DTYPE.itemsize == 104
+# sensor_msgs/JointState position / velocity in joint_names order (mit_cheetah_config.yaml:35-37)
+JOINT_MSG_DTYPE = np.dtype([("position", "<f8", (12,)), ("velocity", "<f8", (12,))])
+assert JOINT_MSG_DTYPE.itemsize == 192
+# quadruped_msgs/JointTorqueCmd.torque as the reference fills it (legs in std::map order FL FR RL RR), entry count, and
+# the leg each entry belongs to (stands in for actuator_name, commander_node.cpp:517-533)
+TORQUE_CMD_DTYPE = np.dtype([("torque", "<f8", (12,)), ("leg", "u1", (12,)), ("count", "<i4")])
+assert TORQUE_CMD_DTYPE.itemsize == 112
+
+
+class PlanParams(ctypes.Structure):
+    """``qpb_plan_params``: FootPlanner constants (foot_planner.cpp:22-42) and the gait/ parameters
+    FootTrajectoryManager is constructed with (commander_node.cpp:245-247, 360-361)."""
+
+    _fields_ = [
+        ("k_raibert", ctypes.c_double),
+        ("g", ctypes.c_double),
+        ("thigh_offset", ctypes.c_double * 12),
+        ("height", ctypes.c_double),
+        ("t_swing", ctypes.c_double),
+        ("t_stance", ctypes.c_double),
+    ]
+
+
+def default_plan_params():
+    p = PlanParams()
+    p.k_raibert, p.g = 0.01, 9.81
+    sx, sy = (-1.0, 1.0, -1.0, 1.0), (1.0, 1.0, -1.0, -1.0)
+    off = []
+    for leg in range(4):
+        off += [sx[leg] * 0.196, sy[leg] * 0.127, 0.0]
+    p.thigh_offset[:] = off
+    p.height, p.t_swing, p.t_stance = 0.08, 0.18, 0.8  # mit_cheetah_config.yaml:17-19
+    return p
