@@ -23,8 +23,7 @@
 
 namespace qpbmpc {
 
-constexpr int NT = 256;  // threads per CTA
-constexpr int NW = NT / 32;
+constexpr int NWMAX = 16;  // the kernel is instantiated for 256 and 512 threads per CTA (template parameter NT)
 constexpr int NH = 10;
 constexpr int NV = 120;   // variables before compaction
 constexpr int LD = 121;   // odd leading dimension: row- and column-wise sweeps are both bank-conflict free
@@ -63,9 +62,9 @@ struct __align__(16) Smem {
   double r[QCAP];
   double dd[QCAP];
   double ratio[QCAP];   // max(u_k, 0) / r_k where r_k > 0, else +inf
-  double part[2][NW];   // per-warp partial sums of |n~|^2 and n~.z~
+  double part[2][NWMAX];   // per-warp partial sums of |n~|^2 and n~.z~
   int A[QCAP];
-  unsigned red[NW];
+  unsigned red[NWMAX];
   unsigned char slot_of_row[MROWS];
   unsigned char act[MROWS];
   unsigned char sfk[40], sff[40];
@@ -112,20 +111,33 @@ __device__ __forceinline__ double& ns_at(Smem& S, int k, int i) {
   return S.M[(119 - 2 * (k - QMAX) - h) * LD + (i - 60 * h)];
 }
 
-template <int B, int NB>
-__device__ __forceinline__ void publish_col(const double (&m)[8][8], double* dst, int ty) {
+// Register tiling of the sweep: a 16 x TXN thread grid (TXN = NT/16 = 16 or 32 thread columns); thread (ty, tx) owns
+// the elements (ty + 16a, tx + TXN b), a < 8, b < CB = 128 / TXN.
+template <int NT>
+struct Tile {
+  static constexpr int TXN = NT / 16;
+  static constexpr int CB = 128 / TXN;
+};
+
+template <int NT, int B, int NB>
+__device__ __forceinline__ void publish_col(const double (&m)[8][Tile<NT>::CB], double* dst, int ty) {
+  constexpr int BB = B < Tile<NT>::CB ? B : Tile<NT>::CB - 1;
 #pragma unroll
-  for (int a = 0; a < NB; a++) dst[ty + 16 * a] = m[a][B < 8 ? B : 7];
+  for (int a = 0; a < NB; a++) dst[ty + 16 * a] = m[a][BB];
 }
 
-// Steps j = 16*BJ .. 16*BJ+15 of the Gauss-Jordan sweep over NB x NB blocks of 16 (see phase E).  The block index of
+// Steps j = 16*BJ .. 16*BJ+15 of the Gauss-Jordan sweep over NB row blocks of 16 (see phase E).  The block index of
 // the pivot is a template parameter, so every register index is static and eliminated column blocks cost nothing.
-template <int NB, int BJ>
+template <int NT, int NB, int BJ>
 struct SweepBlock {
-  static __device__ __forceinline__ bool run(double (&m)[8][8], Smem& S, int n, int tx, int ty, int tid) {
+  static constexpr int TXN = Tile<NT>::TXN, CB = Tile<NT>::CB;
+  static constexpr int NBC = (16 * NB + TXN - 1) / TXN;  // column blocks in use
+  static constexpr int CBJ = (16 * BJ) / TXN;            // column block of the pivots of this step group
+  static constexpr int TX0 = (16 * BJ) % TXN;            // thread column of its first pivot
+  static __device__ __forceinline__ bool run(double (&m)[8][CB], Smem& S, int n, int tx, int ty, int tid) {
 #pragma unroll 1
     for (int tj = 0; tj < 16; tj++) {
-      const int j = 16 * BJ + tj;
+      const int j = 16 * BJ + tj, txj = TX0 + tj;
       if (j >= n) return true;
       const double* cur = S.col[j & 1];
       double* nxt = S.col[(j + 1) & 1];
@@ -133,58 +145,60 @@ struct SweepBlock {
       if (!(d > 0.0)) return false;  // uniform: every thread reads the same value
       const double rd = rcp_fast(d);
       if (tid == 0) S.dval[j] = d;
-      double ci[8], cv[8];
+      double ci[CB], cv[8];
 #pragma unroll
       for (int a = 0; a < NB; a++) cv[a] = cur[ty + 16 * a];
       if (ty == tj) cv[BJ] = 0.0;  // row j itself is assigned below
 #pragma unroll
-      for (int b = BJ; b < NB; b++) ci[b] = cur[tx + 16 * b] * rd;  // rows/columns >= n are zero already
-      if (tx <= tj) ci[BJ] = 0.0;    // columns <= j are finished
+      for (int b = CBJ; b < NBC; b++) ci[b] = cur[tx + TXN * b] * rd;  // rows/columns >= n are zero already
+      if (tx <= txj) ci[CBJ] = 0.0;  // columns <= j are finished
 #pragma unroll
-      for (int b = BJ; b < NB; b++)
+      for (int b = CBJ; b < NBC; b++)
 #pragma unroll
         for (int a = 0; a < NB; a++) m[a][b] = fma(-cv[a], ci[b], m[a][b]);
       if (ty == tj) {
-        if (tx > tj) m[BJ][BJ] = -ci[BJ];
+        if (tx > txj) m[BJ][CBJ] = -ci[CBJ];
 #pragma unroll
-        for (int b = BJ + 1; b < NB; b++) m[BJ][b] = -ci[b];
+        for (int b = CBJ + 1; b < NBC; b++) m[BJ][b] = -ci[b];
       }
       if (tj < 15) {
-        if (tx == tj + 1) publish_col<BJ, NB>(m, nxt, ty);
+        if (tx == txj + 1) publish_col<NT, CBJ, NB>(m, nxt, ty);
       } else if (BJ + 1 < NB) {
-        if (tx == 0) publish_col<BJ + 1, NB>(m, nxt, ty);
+        constexpr int CBN = (16 * (BJ + 1)) / TXN, TXN0 = (16 * (BJ + 1)) % TXN;
+        if (tx == TXN0) publish_col<NT, CBN, NB>(m, nxt, ty);
       }
       __syncthreads();
     }
-    return SweepBlock<NB, BJ + 1>::run(m, S, n, tx, ty, tid);
+    return SweepBlock<NT, NB, BJ + 1>::run(m, S, n, tx, ty, tid);
   }
 };
-template <int NB>
-struct SweepBlock<NB, NB> {
-  static __device__ __forceinline__ bool run(double (&)[8][8], Smem&, int, int, int, int) { return true; }
+template <int NT, int NB>
+struct SweepBlock<NT, NB, NB> {
+  static __device__ __forceinline__ bool run(double (&)[8][Tile<NT>::CB], Smem&, int, int, int, int) { return true; }
 };
 
 // load the symmetric H into the register tiles, sweep, and store X^T above the diagonal of S.M
-template <int NB>
+template <int NT, int NB>
 __device__ __noinline__ bool sweep(Smem& S, int n, int tid) {
-  const int tx = tid & 15, ty = tid >> 4;
-  double m[8][8];
+  constexpr int TXN = Tile<NT>::TXN, CB = Tile<NT>::CB, NBC = (16 * NB + TXN - 1) / TXN;
+  const int tx = tid % TXN, ty = tid / TXN;
+  double m[8][CB];
 #pragma unroll
   for (int a = 0; a < NB; a++)
 #pragma unroll
-    for (int b = 0; b < NB; b++) {
-      const int R = ty + 16 * a, C = tx + 16 * b;
+    for (int b = 0; b < NBC; b++) {
+      const int R = ty + 16 * a, C = tx + TXN * b;
       m[a][b] = (R < n && C < n) ? (C <= R ? S.M[R * LD + C] : S.M[C * LD + R]) : 0.0;
     }
-  if (tx == 0) publish_col<0, NB>(m, S.col[0], ty);
+  if (tx == 0) publish_col<NT, 0, NB>(m, S.col[0], ty);
   __syncthreads();
-  const bool ok = SweepBlock<NB, 0>::run(m, S, n, tx, ty, tid);
+  const bool ok = SweepBlock<NT, NB, 0>::run(m, S, n, tx, ty, tid);
   if (!__syncthreads_and(ok)) return false;
   if (tid < n) S.dinv[tid] = 1.0 / sqrt(S.dval[tid]);
   __syncthreads();
 #pragma unroll
-  for (int b = 0; b < NB; b++) {
-    const int C = tx + 16 * b;
+  for (int b = 0; b < NBC; b++) {
+    const int C = tx + TXN * b;
     const double sc = C < n ? S.dinv[C] : 0.0;
 #pragma unroll
     for (int a = 0; a < NB; a++) {
@@ -200,70 +214,48 @@ __device__ __forceinline__ double X_at(const Smem& S, int i, int c) {
   return i > c ? S.M[c * LD + i] : (i == c ? S.dinv[i] : 0.0);
 }
 
-// (X v)_i = sum_{c <= i} X[i][c] v_c ; two threads per i (c parity), result valid in the even thread of the pair
-// (all 32 lanes must call: the pair is combined with a full-mask shuffle; lanes with !on contribute nothing)
-__device__ __forceinline__ double tri_X(const Smem& S, const double* v, int i, int part, bool on) {
-  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-  int c = on ? part : i;
-  const double* col = &S.M[i];
-  for (; c + 6 < i; c += 8) {
-    a0 = fma(col[c * LD], v[c], a0);
-    a1 = fma(col[(c + 2) * LD], v[c + 2], a1);
-    a2 = fma(col[(c + 4) * LD], v[c + 4], a2);
-    a3 = fma(col[(c + 6) * LD], v[c + 6], a3);
-  }
-  for (; c < i; c += 2) a0 = fma(col[c * LD], v[c], a0);
-  double a = (a0 + a1) + (a2 + a3);
-  if (on && part == 0) a = fma(S.dinv[i], v[i], a);
-  return a + __shfl_xor_sync(FULL, a, 1);
-}
-
-// (X^T v)_c = sum_{i >= c} X[i][c] v_i ; two threads per c
-__device__ __forceinline__ double tri_XT(const Smem& S, const double* v, int c, int n, int part, bool on) {
-  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-  const double* row = &S.M[c * LD];
-  int i = on ? c + 1 + part : n;
-  for (; i + 6 < n; i += 8) {
-    a0 = fma(row[i], v[i], a0);
-    a1 = fma(row[i + 2], v[i + 2], a1);
-    a2 = fma(row[i + 4], v[i + 4], a2);
-    a3 = fma(row[i + 6], v[i + 6], a3);
-  }
-  for (; i < n; i += 2) a0 = fma(row[i], v[i], a0);
-  double a = (a0 + a1) + (a2 + a3);
-  if (on && part == 0) a = fma(S.dinv[c], v[c], a);
-  return a + __shfl_xor_sync(FULL, a, 1);
-}
-
 // Triangular mat-vecs with X^T stored above the diagonal of M (leading dimension 121).  Mapping: a warp serves the
-// pair of 8-row blocks (warp, nb8-1-warp) -- a short and a long one, n-1 terms together, so the 8 warps are balanced --
-// lane = 8*s + r8: r8 picks the row of the block, s in 0..3 the residue class of the inner index,
-// inner = 16t + 8(s&1) + 4(s>>1) + u, u = 0..3.  Within a half-warp the two classes sit 8 inner indices apart, which
-// with the odd leading dimension makes every 64-bit shared-memory access conflict-free in both sweep directions.
-// Partial sums are combined over the four classes with two shuffles; every lane returns the full sum.
+// pair of RB-row blocks (warp, nblk-1-warp) -- a short and a long one, n-1 terms together, so the warps are balanced --
+// with RB = 8 rows per block for 8 warps and 4 for 16 warps.  lane = RB*s + rr: rr picks the row of the block, s the
+// residue class of the inner index; each lane takes four consecutive inner indices per window of W = 4 * (32/RB), and
+// within a half-warp the classes sit 8 (RB = 8) or 4 (RB = 4) inner indices apart, which with the odd leading dimension
+// makes every 64-bit shared-memory access conflict-free in both sweep directions.  Partial sums are combined over the
+// classes with shuffles; every lane returns the full sum.
+template <int NT>
+struct Tri {
+  static constexpr int RB = NT == 256 ? 8 : 4;  // rows per block
+  static constexpr int NCL = 32 / RB;           // residue classes
+  static constexpr int W = 4 * NCL;             // inner window
+};
 struct TriMap {
   int iA, iB, off;
   bool onA, onB;
 };
+template <int NT>
 __device__ __forceinline__ TriMap tri_map(int n, int lane, int warp) {
-  const int nb8 = (n + 7) >> 3, bA = warp, bB = nb8 - 1 - warp, r8 = lane & 7, s = lane >> 3;
+  constexpr int RB = Tri<NT>::RB;
+  const int nblk = (n + RB - 1) / RB, bA = warp, bB = nblk - 1 - warp, rr = lane % RB, s = lane / RB;
   TriMap t;
-  t.iA = 8 * bA + r8;
-  t.iB = 8 * bB + r8;
-  t.off = 8 * (s & 1) + 4 * (s >> 1);
+  t.iA = RB * bA + rr;
+  t.iB = RB * bB + rr;
+  t.off = RB == 8 ? 8 * (s & 1) + 4 * (s >> 1) : 4 * (s & 3) + 16 * (s >> 2);
   t.onA = bA <= bB && t.iA < n;
   t.onB = bA < bB && t.iB < n;
   return t;
 }
-__device__ __forceinline__ double quad_sum(double a) {
+template <int NT>
+__device__ __forceinline__ double class_sum(double a) {
+  if (Tri<NT>::RB == 4) a += __shfl_xor_sync(FULL, a, 4);
   a += __shfl_xor_sync(FULL, a, 8);
   return a + __shfl_xor_sync(FULL, a, 16);
 }
 // sum_{c < i} M[c][i] v_c over this lane's residue class
+template <int NT>
 __device__ __forceinline__ double tri_col_part(const double* Mi, const double* v, int i, int off) {
+  constexpr int W = Tri<NT>::W;
   double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
   int c = off;
-  for (; c + 3 < i; c += 16) {
+  for (; c + 3 < i; c += W) {
     a0 = fma(Mi[c * LD], v[c], a0);
     a1 = fma(Mi[(c + 1) * LD], v[c + 1], a1);
     a2 = fma(Mi[(c + 2) * LD], v[c + 2], a2);
@@ -275,17 +267,19 @@ __device__ __forceinline__ double tri_col_part(const double* Mi, const double* v
   return (a0 + a1) + (a2 + a3);
 }
 // sum_{c < i < n} M[c][i] v_i over this lane's residue class
+template <int NT>
 __device__ __forceinline__ double tri_row_part(const double* Mc, const double* v, int c, int n, int off) {
+  constexpr int W = Tri<NT>::W;
   double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-  int i = ((c + 1) & ~15) + off;  // first 16-aligned window that can hold an index > c
-  if (i + 3 > c) {                // head window: some of its four indices may still be <= c
+  int i = ((c + 1) & ~(W - 1)) + off;  // first W-aligned window that can hold an index > c
+  if (i + 3 > c) {                     // head window: some of its four indices may still be <= c
     if (i > c && i < n) a0 = fma(Mc[i], v[i], a0);
     if (i + 1 > c && i + 1 < n) a1 = fma(Mc[i + 1], v[i + 1], a1);
     if (i + 2 > c && i + 2 < n) a2 = fma(Mc[i + 2], v[i + 2], a2);
     if (i + 3 < n) a3 = fma(Mc[i + 3], v[i + 3], a3);
   }
-  i += 16;
-  for (; i + 3 < n; i += 16) {
+  i += W;
+  for (; i + 3 < n; i += W) {
     a0 = fma(Mc[i], v[i], a0);
     a1 = fma(Mc[i + 1], v[i + 1], a1);
     a2 = fma(Mc[i + 2], v[i + 2], a2);
@@ -297,16 +291,18 @@ __device__ __forceinline__ double tri_row_part(const double* Mc, const double* v
   return (a0 + a1) + (a2 + a3);
 }
 // (X v)_i = sum_{c < i} M[c][i] v_c + dinv_i v_i for rows iA, iB of the map
+template <int NT>
 __device__ __forceinline__ void tri_X8(const Smem& S, const double* v, const TriMap& t, double& oA, double& oB) {
-  const double a = quad_sum(t.onA ? tri_col_part(&S.M[t.iA], v, t.iA, t.off) : 0.0);
-  const double b = quad_sum(t.onB ? tri_col_part(&S.M[t.iB], v, t.iB, t.off) : 0.0);
+  const double a = class_sum<NT>(t.onA ? tri_col_part<NT>(&S.M[t.iA], v, t.iA, t.off) : 0.0);
+  const double b = class_sum<NT>(t.onB ? tri_col_part<NT>(&S.M[t.iB], v, t.iB, t.off) : 0.0);
   oA = t.onA ? fma(S.dinv[t.iA], v[t.iA], a) : 0.0;
   oB = t.onB ? fma(S.dinv[t.iB], v[t.iB], b) : 0.0;
 }
 // (X^T v)_c = dinv_c v_c + sum_{i > c} M[c][i] v_i for columns iA, iB of the map
+template <int NT>
 __device__ __forceinline__ void tri_XT8(const Smem& S, const double* v, int n, const TriMap& t, double& oA, double& oB) {
-  const double a = quad_sum(t.onA ? tri_row_part(&S.M[t.iA * LD], v, t.iA, n, t.off) : 0.0);
-  const double b = quad_sum(t.onB ? tri_row_part(&S.M[t.iB * LD], v, t.iB, n, t.off) : 0.0);
+  const double a = class_sum<NT>(t.onA ? tri_row_part<NT>(&S.M[t.iA * LD], v, t.iA, n, t.off) : 0.0);
+  const double b = class_sum<NT>(t.onB ? tri_row_part<NT>(&S.M[t.iB * LD], v, t.iB, n, t.off) : 0.0);
   oA = t.onA ? fma(S.dinv[t.iA], v[t.iA], a) : 0.0;
   oB = t.onB ? fma(S.dinv[t.iB], v[t.iB], b) : 0.0;
 }
@@ -342,11 +338,13 @@ __device__ __forceinline__ double row_slack(int t, double fx, double fy, double 
   return t < 4 ? pyr : (t == 4 ? fz - P.fzmin : P.fzmax - fz);
 }
 
+template <int NT>
 __global__ void __launch_bounds__(NT, 1)
 mpc_qp_kernel(const __grid_constant__ DevParams P, const qpb_mpc_rec* __restrict__ in, qpb_mpc_out_rec* __restrict__ out,
               int64_t nrec, unsigned long long* __restrict__ ticket, unsigned long long* __restrict__ ticket_clear) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem& S = *reinterpret_cast<Smem*>(smem_raw);
+  constexpr int NW = NT / 32;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const double INF = __longlong_as_double(0x7ff0000000000000LL);
   if (blockIdx.x == 0 && tid == 0) *ticket_clear = 0ull;  // counter of a launch far in the future
@@ -551,10 +549,10 @@ mpc_qp_kernel(const __grid_constant__ DevParams P, const qpb_mpc_rec* __restrict
       {
         const int nb = (n + 15) >> 4;
         bool ok;
-        if (nb <= 2) ok = sweep<2>(S, n, tid);
-        else if (nb <= 4) ok = sweep<4>(S, n, tid);
-        else if (nb <= 6) ok = sweep<6>(S, n, tid);
-        else ok = sweep<8>(S, n, tid);
+        if (nb <= 2) ok = sweep<NT, 2>(S, n, tid);
+        else if (nb <= 4) ok = sweep<NT, 4>(S, n, tid);
+        else if (nb <= 6) ok = sweep<NT, 6>(S, n, tid);
+        else ok = sweep<NT, 8>(S, n, tid);
         if (!ok) status = QPB_BAD_INPUT;
       }
     }
@@ -563,15 +561,15 @@ mpc_qp_kernel(const __grid_constant__ DevParams P, const qpb_mpc_rec* __restrict
     if (status == QPB_OK && n > 0) {
       __syncthreads();
       // ---- unconstrained minimiser f0 = -X^T X g ----------------------------------------------------------
-      const TriMap tm = tri_map(n, lane, warp);
-      const bool wrA = tm.onA && lane < 8, wrB = tm.onB && lane < 8;  // class-0 lanes write the results
+      const TriMap tm = tri_map<NT>(n, lane, warp);
+      const bool wrA = tm.onA && lane < Tri<NT>::RB, wrB = tm.onB && lane < Tri<NT>::RB;  // class-0 lanes write the results
       {
         double ya, yb;
-        tri_X8(S, S.w, tm, ya, yb);
+        tri_X8<NT>(S, S.w, tm, ya, yb);
         if (wrA) S.zt[tm.iA] = -ya;
         if (wrB) S.zt[tm.iB] = -yb;
         __syncthreads();
-        tri_XT8(S, S.zt, n, tm, ya, yb);
+        tri_XT8<NT>(S, S.zt, n, tm, ya, yb);
         if (wrA) S.f[tm.iA] = ya;
         if (wrB) S.f[tm.iB] = yb;
         __syncthreads();
@@ -582,7 +580,8 @@ mpc_qp_kernel(const __grid_constant__ DevParams P, const qpb_mpc_rec* __restrict
       const int m = 2 * n;  // 6 rows per stance foot-step
       const double fzs = 1.0 + fmax(fabs(P.fzmin), fabs(P.fzmax));
       const int hl = lane & 15, hh = lane >> 4;         // half-warp per working-set slot
-      const int ci = tid & 127, ck = tid >> 7;          // rank-1 updates: column ci, slots ck, ck+2, ...
+      const int ci = tid & 127, ck = tid >> 7;          // rank-1 updates: column ci, slots ck, ck + NT/128, ...
+      constexpr int CKS = NT / 128;
       int q = 0;
       for (;;) {
         unsigned key = 0;
@@ -654,7 +653,7 @@ mpc_qp_kernel(const __grid_constant__ DevParams P, const qpb_mpc_rec* __restrict
             __syncthreads();
             MPC_TICK(10);
             double xa, xb;
-            tri_X8(S, S.w, tm, xa, xb);
+            tri_X8<NT>(S, S.w, tm, xa, xb);
             double zp = 0.0;
             if (wrA) {
               const double za = S.nt[tm.iA] - xa;
@@ -712,7 +711,7 @@ mpc_qp_kernel(const __grid_constant__ DevParams P, const qpb_mpc_rec* __restrict
           // (5) primal and dual step
           if (!dep) {
             double da, db;
-            tri_XT8(S, ztp, n, tm, da, db);
+            tri_XT8<NT>(S, ztp, n, tm, da, db);
             if (wrA) S.f[tm.iA] = fma(t, da, S.f[tm.iA]);
             if (wrB) S.f[tm.iB] = fma(t, db, S.f[tm.iB]);
             sp = fma(t, zeta, sp);
@@ -724,11 +723,11 @@ mpc_qp_kernel(const __grid_constant__ DevParams P, const qpb_mpc_rec* __restrict
             if (q >= QCAP) { status = QPB_MAX_ITER; stop = true; __syncthreads(); break; }  // cannot happen: rows are independent
             if (ci < n) {
               const double val = ztp[ci] * iz;
-              for (int k = ck; k < q; k += 2) {
+              for (int k = ck; k < q; k += CKS) {
                 double& e = ns_at(S, k, ci);
                 e = fma(-S.r[k], val, e);
               }
-              if ((q & 1) == ck) ns_at(S, q, ci) = val;
+              if (q % CKS == ck) ns_at(S, q, ci) = val;
             }
             if (tid == 0) {
               S.A[q] = p;
@@ -755,7 +754,7 @@ mpc_qp_kernel(const __grid_constant__ DevParams P, const qpb_mpc_rec* __restrict
           const double idl = rcp_fast(S.dd[ks]);
           if (ci < n) {
             const double nu = ns_at(S, ks, ci);
-            for (int j = ck; j < q; j += 2)
+            for (int j = ck; j < q; j += CKS)
               if (j != ks) {
                 double& e = ns_at(S, j, ci);
                 e = fma(-S.dd[j] * idl, nu, e);

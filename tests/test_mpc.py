@@ -158,6 +158,61 @@ def test_mpc_gpu_matches_oracle(mpc_solver, mpc_params, gaits, scale, seed):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("threads", ["256", "512"])
+def test_mpc_gpu_both_thread_counts_match_oracle(built, mpc_params, threads, monkeypatch):
+    """The kernel is instantiated for 256 and 512 threads per CTA (QPB_MPC_THREADS at create time): both mappings against
+    the oracle on every gait, two disturbance scales and ragged / empty contact patterns."""
+    import oracle
+
+    monkeypatch.setenv("QPB_MPC_THREADS", threads)
+    s = lib.MpcSolver(mpc_params, device=0)
+    R = np.concatenate([generate_mpc(300, 71), generate_mpc(150, 72, scale=4.0), generate_mpc(60, 73, gaits="trot")])
+    R["contact"][5] = 0
+    R["contact"][6, ::3, 1] = 0
+    out = s.solve_host(R)
+    s.close()
+    ref = oracle.mpc_batch(mpc_params, R, NCPU)
+    assert (out["status"] == ref["status"]).all() and (ref["status"] == 0).all()
+    assert rel_err(out["U"], ref["U"]) <= TOL
+    assert _feasible(mpc_params, R, out)
+
+
+@pytest.mark.gpu
+def test_mpc_gpu_random_parameter_sets(built):
+    """Fuzz over controller parameters: friction, force limits, mass, a full inertia matrix, horizon step, state weights
+    (some zero) and force weights down to 1e-7 (condition numbers up to ~1e8)."""
+    import oracle
+
+    rng = np.random.default_rng(2026)
+    worst = 0.0
+    for trial in range(8):
+        p = default_mpc_params()
+        p.mu = float(rng.uniform(0.2, 1.2))
+        p.fzmin = float(rng.choice([0.0, 5.0, 10.0]))
+        p.fzmax = float(rng.uniform(60.0, 300.0))
+        p.mass = float(rng.uniform(5.0, 40.0))
+        A = rng.normal(size=(3, 3)) * 0.01
+        Ib = np.diag([0.011253, 0.036203, 0.042673]) * rng.uniform(0.5, 5.0) + A @ A.T
+        p.Ib[:] = Ib.ravel().tolist()
+        p.dt = float(rng.uniform(0.01, 0.06))
+        Lw = np.array(default_mpc_params().Lw[:]) * rng.uniform(0.1, 10.0, size=13)
+        Lw[rng.integers(0, 12)] = 0.0
+        p.Lw[:] = Lw.tolist()
+        p.alpha = float(10.0 ** rng.uniform(-7, -3))
+        R = generate_mpc(96, 500 + trial, params=p, scale=float(rng.choice([1.0, 2.5])))
+        s = lib.MpcSolver(p, device=0)
+        out = s.solve_host(R)
+        s.close()
+        ref = oracle.mpc_batch(p, R, NCPU)
+        assert (ref["status"] == 0).all() and (out["status"] == 0).all(), (trial, np.bincount(out["status"]))
+        err = rel_err(out["U"], ref["U"])
+        worst = max(worst, err)
+        assert err <= TOL, (trial, err, p.alpha)
+        assert _feasible(p, R, out)
+    print("worst rel err over parameter sets", worst)
+
+
+@pytest.mark.gpu
 def test_mpc_gpu_passes_kkt_certificate(mpc_solver, mpc_params):
     import oracle
     from oracle import kkt
