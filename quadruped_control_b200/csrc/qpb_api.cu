@@ -59,6 +59,8 @@ constexpr int kHostSlots = 6;          // streams / staging slots of the host-bu
 constexpr int64_t kHostChunkMax = 16384;  // capacity of a pipeline stage (8 MiB in, 4 MiB out)
 constexpr int64_t kMaxRecordsPerLaunch = (int64_t)1 << 31;  // the kernels index work items with 32 bits
 constexpr uint32_t kTicketSlots = 4096;  // ring of work counters; a launch re-zeroes the slot half a ring ahead
+constexpr int64_t kSmallCall = 128;      // host calls up to this many robots go through one pinned, mapped staging block
+constexpr size_t kSmallBytes = (size_t)kSmallCall * 1536;  // states + results + swing records (or the kinematics arrays)
 
 }  // namespace
 
@@ -83,6 +85,11 @@ struct qpb_handle {
   // ring of work-ticket counters, one per in-flight launch of the balance kernel
   unsigned long long* d_tickets = nullptr;
   std::atomic<uint32_t> ticket_slot{ 0 };
+  // Per-tick callers (the C++ shim: one robot, pageable stack records) get a latency path: the records are copied into
+  // a pinned, mapped block the kernel reads and writes over PCIe itself -- one launch and one stream synchronisation,
+  // no cudaMemcpy, no cudaMalloc.
+  unsigned char* h_small = nullptr;  // host address of the pinned block
+  unsigned char* d_small = nullptr;  // its device alias
   int64_t host_chunk = 8192;  // records per H2D/kernel/D2H pipeline stage (QPB_HOST_CHUNK overrides)
   int zero_copy = 1;          // pinned host buffers are read/written by the kernel itself over PCIe (QPB_ZEROCOPY=0: always stage)
 };
@@ -136,6 +143,21 @@ int launch_swing(qpb_handle* h, int64_t n, const qpb_state_rec* d_states, const 
   return QPB_SUCCESS;
 }
 
+int ensure_small(qpb_handle* h) {
+  if (h->h_small) return QPB_SUCCESS;
+  void* p = nullptr;
+  QPB_CUDA(cudaHostAlloc(&p, kSmallBytes, cudaHostAllocMapped));
+  void* d = nullptr;
+  if (cudaHostGetDevicePointer(&d, p, 0) != cudaSuccess) {
+    cudaFreeHost(p);
+    return fail(QPB_ERR_CUDA, "cudaHostGetDevicePointer failed");
+  }
+  h->h_small = static_cast<unsigned char*>(p);
+  h->d_small = static_cast<unsigned char*>(d);
+  if (!h->streams[0]) QPB_CUDA(cudaStreamCreateWithFlags(&h->streams[0], cudaStreamNonBlocking));
+  return QPB_SUCCESS;
+}
+
 // Host-buffer path shared by qpb_control_batch_host and qpb_tick_batch_host.  Pinned buffers of the balance path are
 // handed to the kernel directly; otherwise stages of records are uploaded, solved and downloaded on a ring of
 // streams so the three overlap (the tick always stages: its second kernel would re-read the records over PCIe).
@@ -143,6 +165,24 @@ int host_pipeline(qpb_handle* h, int64_t n, const qpb_state_rec* h_states, const
   if (n == 0) return QPB_SUCCESS;
   DeviceGuard guard(h->device);
   if (!guard.ok) return fail(QPB_ERR_CUDA, "cudaSetDevice failed");
+  if (h->zero_copy && n <= kSmallCall) {
+    // Latency path for per-tick callers: stage through the handle's pinned block, kernels work on its device alias.
+    const int rc0 = ensure_small(h);
+    if (rc0 != QPB_SUCCESS) return rc0;
+    const size_t off_out = (size_t)kSmallCall * sizeof(qpb_state_rec), off_sw = off_out + (size_t)kSmallCall * sizeof(qpb_out_rec);
+    std::memcpy(h->h_small, h_states, (size_t)n * sizeof(qpb_state_rec));
+    if (h_swing) std::memcpy(h->h_small + off_sw, h_swing, (size_t)n * sizeof(qpb_swing_rec));
+    const qpb_state_rec* ds = reinterpret_cast<const qpb_state_rec*>(h->d_small);
+    qpb_out_rec* dout = reinterpret_cast<qpb_out_rec*>(h->d_small + off_out);
+    qpb::PackedIO io{ ds, dout };
+    int rc = launch_balance(h, io, n, h->ctas_per_sm_packed, h->streams[0]);
+    if (rc == QPB_SUCCESS && h_swing)
+      rc = launch_swing(h, n, ds, reinterpret_cast<const qpb_swing_rec*>(h->d_small + off_sw), dout, h->streams[0]);
+    if (rc != QPB_SUCCESS) return rc;
+    QPB_CUDA(cudaStreamSynchronize(h->streams[0]));
+    std::memcpy(h_out, h->h_small + off_out, (size_t)n * sizeof(qpb_out_rec));
+    return QPB_SUCCESS;
+  }
   if (h->zero_copy && !h_swing) {
     // Pinned (hence mapped) buffers: one launch reads the records and writes the results straight over PCIe.  No
     // staging copies, no pipeline fill/drain: 0.73 ms instead of 0.88 ms per 65 536 records (H2D alone takes 0.65 ms).
@@ -323,6 +363,7 @@ int qpb_destroy(qpb_handle* h) {
   if (h->d_tickets) cudaFree(h->d_tickets);
   if (h->d_gains) cudaFree(h->d_gains);
   if (h->d_plan) cudaFree(h->d_plan);
+  if (h->h_small) cudaFreeHost(h->h_small);
   delete h;
   return QPB_SUCCESS;
 }
@@ -429,6 +470,22 @@ int qpb_jt_batch_host(qpb_handle* h, int64_t n, const double* q, const double* g
   DeviceGuard guard(h->device);
   if (!guard.ok) return fail(QPB_ERR_CUDA, "cudaSetDevice failed");
   const size_t nb = (size_t)n * 12 * sizeof(double);
+  if (h->zero_copy && n <= kSmallCall) {  // latency path: pinned, mapped staging block, no cudaMalloc / cudaMemcpy
+    const int rc0 = ensure_small(h);
+    if (rc0 != QPB_SUCCESS) return rc0;
+    double* hs = reinterpret_cast<double*>(h->h_small);
+    double* dsm = reinterpret_cast<double*>(h->d_small);
+    std::memcpy(hs, q, nb);
+    std::memcpy(hs + (size_t)n * 12, grf_body, nb);
+    uint8_t* hc = reinterpret_cast<uint8_t*>(hs + 3 * (size_t)n * 12);
+    if (contact) std::memcpy(hc, contact, (size_t)n * 4);
+    const int rc = qpb_jt_batch(h, n, dsm, dsm + (size_t)n * 12, contact ? reinterpret_cast<uint8_t*>(dsm + 3 * (size_t)n * 12) : nullptr,
+                                dsm + 2 * (size_t)n * 12, h->streams[0]);
+    if (rc != QPB_SUCCESS) return rc;
+    QPB_CUDA(cudaStreamSynchronize(h->streams[0]));
+    std::memcpy(tau, hs + 2 * (size_t)n * 12, nb);
+    return QPB_SUCCESS;
+  }
   double* d = nullptr;  // [q | f | tau | contact]
   QPB_CUDA(cudaMalloc(&d, 3 * nb + (size_t)n * 4));
   uint8_t* dc = reinterpret_cast<uint8_t*>(d + 3 * (size_t)n * 12);
@@ -449,6 +506,18 @@ int qpb_fk_batch_host(qpb_handle* h, int64_t n, const double* q, double* feet_bo
   DeviceGuard guard(h->device);
   if (!guard.ok) return fail(QPB_ERR_CUDA, "cudaSetDevice failed");
   const size_t nb = (size_t)n * 12 * sizeof(double);
+  if (h->zero_copy && n <= kSmallCall) {  // latency path, as in qpb_jt_batch_host
+    const int rc0 = ensure_small(h);
+    if (rc0 != QPB_SUCCESS) return rc0;
+    double* hs = reinterpret_cast<double*>(h->h_small);
+    double* dsm = reinterpret_cast<double*>(h->d_small);
+    std::memcpy(hs, q, nb);
+    const int rc = qpb_fk_batch(h, n, dsm, dsm + (size_t)n * 12, h->streams[0]);
+    if (rc != QPB_SUCCESS) return rc;
+    QPB_CUDA(cudaStreamSynchronize(h->streams[0]));
+    std::memcpy(feet_body, hs + (size_t)n * 12, nb);
+    return QPB_SUCCESS;
+  }
   double* d = nullptr;
   QPB_CUDA(cudaMalloc(&d, 2 * nb));
   cudaError_t e = cudaMemcpy(d, q, nb, cudaMemcpyHostToDevice);

@@ -93,13 +93,16 @@ __global__ void plan_kernel(const qpb_plan_params* __restrict__ PP, const qpb_st
   if (cleared != replan) *reinterpret_cast<uint32_t*>(pl.replan) = cleared;
 }
 
+// One thread per robot.  The records are 16-byte aligned (ABI contract) and every field group written here starts on a
+// 16-byte boundary, so the state / swing records and the joint message are moved as double2 (half the L2 requests of
+// 8-byte accesses; the kernel is request-bound, not DRAM-bound).
 __global__ void adapt_kernel(const qpb_params* __restrict__ P, const qpb_com_msg* __restrict__ com,
                              const qpb_joint_msg* __restrict__ joints, qpb_state_rec* __restrict__ states,
                              qpb_swing_rec* __restrict__ swing, int64_t n) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const qpb_com_msg& c = com[i];
-  qpb_state_rec& s = states[i];
+  const qpb_com_msg& c = com[i];  // 104-byte stride: 8-byte loads
+  double2* sv = reinterpret_cast<double2*>(&states[i]);
   // stateCallback (commander_node.cpp:167-187): Quaternion(w, x, y, z).rotation().matrix(), i.e. Drake's
   // RotationMatrix(Eigen::Quaterniond): the 2/|q|^2 form, no normalisation of q
   const double x = c.orientation[0], y = c.orientation[1], z = c.orientation[2], w = c.orientation[3];
@@ -107,33 +110,55 @@ __global__ void adapt_kernel(const qpb_params* __restrict__ P, const qpb_com_msg
   const double sx = two * x, sy = two * y, sz = two * z;
   const double swx = sx * w, swy = sy * w, swz = sz * w, sxx = sx * x, sxy = sy * x, sxz = sz * x, syy = sy * y, syz = sz * y,
                szz = sz * z;
-  s.Rwb[0] = 1.0 - syy - szz; s.Rwb[1] = sxy - swz;       s.Rwb[2] = sxz + swy;
-  s.Rwb[3] = sxy + swz;       s.Rwb[4] = 1.0 - sxx - szz; s.Rwb[5] = syz - swx;
-  s.Rwb[6] = sxz - swy;       s.Rwb[7] = syz + swx;       s.Rwb[8] = 1.0 - sxx - syy;
-#pragma unroll
-  for (int k = 0; k < 3; k++) {
-    s.x[k] = c.position[k];
-    s.xdot[k] = c.linear[k];
-    s.w[k] = c.angular[k];
-  }
+  // Rwb = doubles 0..8 of the record
+  sv[0] = make_double2(1.0 - syy - szz, sxy - swz);
+  sv[1] = make_double2(sxz + swy, sxy + swz);
+  sv[2] = make_double2(1.0 - sxx - szz, syz - swx);
+  sv[3] = make_double2(sxz - swy, syz + swx);
+  states[i].Rwb[8] = 1.0 - sxx - syy;
+  // x, xdot, w = doubles 18..26
+  sv[9] = make_double2(c.position[0], c.position[1]);
+  sv[10] = make_double2(c.position[2], c.linear[0]);
+  sv[11] = make_double2(c.linear[1], c.linear[2]);
+  sv[12] = make_double2(c.angular[0], c.angular[1]);
+  states[i].w[2] = c.angular[2];
   // jointCallback (commander_node.cpp:127-165): message index 4 * joint + leg; forwardKinematics (kinematics.cpp:81-103)
-  const qpb_joint_msg& jm = joints[i];
+  const double2* jv = reinterpret_cast<const double2*>(&joints[i]);
+  double pos[12], vel[12];
+#pragma unroll
+  for (int k = 0; k < 6; k++) {
+    const double2 a = __ldg(jv + k), b = __ldg(jv + 6 + k);
+    pos[2 * k] = a.x;
+    pos[2 * k + 1] = a.y;
+    vel[2 * k] = b.x;
+    vel[2 * k + 1] = b.y;
+  }
+  double q[12], feet[12], qd[12];
+#pragma unroll
   for (int leg = 0; leg < 4; leg++) {
-    const double t1 = jm.position[leg], t2 = jm.position[4 + leg], t3 = jm.position[8 + leg];
-    s.q[3 * leg] = t1;
-    s.q[3 * leg + 1] = t2;
-    s.q[3 * leg + 2] = t3;
-    swing[i].qdot[3 * leg] = jm.velocity[leg];
-    swing[i].qdot[3 * leg + 1] = jm.velocity[4 + leg];
-    swing[i].qdot[3 * leg + 2] = jm.velocity[8 + leg];
+    const double t1 = pos[leg], t2 = pos[4 + leg], t3 = pos[8 + leg];
+    q[3 * leg] = t1;
+    q[3 * leg + 1] = t2;
+    q[3 * leg + 2] = t3;
+    qd[3 * leg] = vel[leg];
+    qd[3 * leg + 1] = vel[4 + leg];
+    qd[3 * leg + 2] = vel[8 + leg];
     const double l1 = P->link[3 * leg], l2 = P->link[3 * leg + 1], l3 = P->link[3 * leg + 2];
     double s1, c1, s2, c2, s23, c23;
     sincos(t1, &s1, &c1);
     sincos(t2, &s2, &c2);
     sincos(t2 + t3, &s23, &c23);
-    s.feet[3 * leg] = l2 * s2 + l3 * s23 + P->hip_offset[3 * leg];
-    s.feet[3 * leg + 1] = l1 * c1 - l2 * s1 * c2 - l3 * s1 * c23 + P->hip_offset[3 * leg + 1];
-    s.feet[3 * leg + 2] = l1 * s1 + l2 * c1 * c2 + l3 * c1 * c23 + P->hip_offset[3 * leg + 2];
+    feet[3 * leg] = l2 * s2 + l3 * s23 + P->hip_offset[3 * leg];
+    feet[3 * leg + 1] = l1 * c1 - l2 * s1 * c2 - l3 * s1 * c23 + P->hip_offset[3 * leg + 1];
+    feet[3 * leg + 2] = l1 * s1 + l2 * c1 * c2 + l3 * c1 * c23 + P->hip_offset[3 * leg + 2];
+  }
+  // feet = doubles 36..47, q = doubles 48..59 of the state record; qdot = doubles 24..35 of the swing record
+  double2* qv = reinterpret_cast<double2*>(&swing[i]) + 12;
+#pragma unroll
+  for (int k = 0; k < 6; k++) {
+    sv[18 + k] = make_double2(feet[2 * k], feet[2 * k + 1]);
+    sv[24 + k] = make_double2(q[2 * k], q[2 * k + 1]);
+    qv[k] = make_double2(qd[2 * k], qd[2 * k + 1]);
   }
 }
 

