@@ -96,6 +96,15 @@ def test_mpc_oracle_agrees_with_closed_form_restatement(built, mpc_params):
         assert st == 0 and rel_err(U[None], ref["U"][i][None]) <= 1e-9
 
 
+def test_mpc_oracle_reproduces_golden_fixture(built, mpc_params):
+    import oracle
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "mpc_golden.npz"))
+    R = np.ascontiguousarray(g["recs"]).view(MPC_REC_DTYPE).reshape(-1)
+    out = oracle.mpc_batch(mpc_params, R, NCPU)
+    assert np.array_equal(out["status"], g["status"]) and rel_err(out["U"], g["U"]) <= 1e-10
+
+
 def test_mpc_oracle_rejects_nonfinite(built, mpc_params):
     import oracle
 
@@ -223,6 +232,14 @@ def test_mpc_gpu_passes_kkt_certificate(mpc_solver, mpc_params):
         q = oracle.mpc_assemble(mpc_params, R[i])
         cert = kkt.certificate(q["Q"], q["c"], q["C"], q["lb"], q["ub"], out["U"][i])
         assert out["status"][i] == 0 and cert["infeas"] <= 1e-8 and cert["stat_rel"] <= 1e-9, (i, cert["infeas"], cert["stat_rel"])
+
+
+@pytest.mark.gpu
+def test_mpc_gpu_matches_golden_fixture(mpc_solver):
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "mpc_golden.npz"))
+    R = np.ascontiguousarray(g["recs"]).view(MPC_REC_DTYPE).reshape(-1)
+    out = mpc_solver.solve_host(R)
+    assert np.array_equal(out["status"], g["status"]) and rel_err(out["U"], g["U"]) <= TOL
 
 
 @pytest.mark.gpu

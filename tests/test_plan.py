@@ -96,6 +96,21 @@ def test_plan_oracle_matches_reference_sources(built, params06):
         assert np.array_equal(oracle.single_foot(pp, leg, S[5]), oracle.ref_single_foot(pp.t_stance, leg, S[5]))
 
 
+def test_plan_oracle_matches_golden_reference_outputs(built):
+    """tests/golden/plan_golden.npz holds outputs of the reference's own planner sources (generated where /root/reference
+    exists); the oracle port must reproduce them anywhere."""
+    import oracle
+
+    g = np.load(os.path.join(ROOT, "tests", "golden", "plan_golden.npz"))
+    S = np.ascontiguousarray(g["states"]).view(STATE_DTYPE).reshape(-1)
+    plan = np.ascontiguousarray(g["plan_in"]).view(PLAN_DTYPE).reshape(-1).copy()
+    want = np.ascontiguousarray(g["plan_out"]).view(PLAN_DTYPE).reshape(-1)
+    sw = np.zeros(len(S), dtype=SWING_DTYPE)
+    oracle.plan_batch(default_plan_params(), S, plan, sw)
+    assert plan.tobytes() == want.tobytes()
+    assert np.abs(sw["foot_ref_pos"] - g["foot_ref_pos"]).max() <= 1e-13 and np.abs(sw["foot_ref_vel"] - g["foot_ref_vel"]).max() <= 1e-12
+
+
 def test_trajectory_meets_its_own_constraints(built):
     """trajectory.cpp:256-296: s(0) = p0, s(1) = pf, s(1/2) = pc, zero velocity and acceleration at both ends; and the
     closed form the CUDA kernel uses equals the LU solution."""
@@ -189,6 +204,24 @@ def test_plan_gpu_matches_oracle(solver06, masks, seed):
     assert rel_err(got_sw["foot_ref_pos"], ref_sw["foot_ref_pos"]) <= 1e-9
     assert rel_err(got_sw["foot_ref_vel"], ref_sw["foot_ref_vel"]) <= 1e-9
     assert (got_sw["qdot"] == 3.0).all()
+
+
+@pytest.mark.gpu
+def test_plan_gpu_matches_golden_reference_outputs(solver06):
+    import torch
+
+    g = np.load(os.path.join(ROOT, "tests", "golden", "plan_golden.npz"))
+    S = np.ascontiguousarray(g["states"]).view(STATE_DTYPE).reshape(-1)
+    plan = np.ascontiguousarray(g["plan_in"]).view(PLAN_DTYPE).reshape(-1)
+    want = np.ascontiguousarray(g["plan_out"]).view(PLAN_DTYPE).reshape(-1)
+    d_S, d_plan = _dev(S), _dev(plan)
+    d_sw = torch.zeros(len(S) * SWING_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
+    solver06.plan(d_S, d_plan, d_sw, len(S), stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    got, sw = _host(d_plan, PLAN_DTYPE), _host(d_sw, SWING_DTYPE)
+    assert np.array_equal(got["replan"], want["replan"])
+    assert rel_err(got["p_start"], want["p_start"]) <= 1e-12 and rel_err(got["p_final"], want["p_final"]) <= 1e-12
+    assert rel_err(sw["foot_ref_pos"], g["foot_ref_pos"]) <= 1e-9 and rel_err(sw["foot_ref_vel"], g["foot_ref_vel"]) <= 1e-9
 
 
 @pytest.mark.gpu
