@@ -56,7 +56,7 @@ struct __align__(16) Smem {
   double E[NH * 12];    // weighted free-response error per step
   double Iinv[NH * 9];
   double Cs[NH], Ss[NH];
-  double col[2][128];   // Gauss-Jordan sweep: the pivot column, double-buffered
+  double col[2][160];   // Gauss-Jordan sweep: the pivot column, double-buffered; row R at (R & 15) * 10 + (R >> 4)
   double dval[128];     // pivots d_j
   double u[QCAP];
   double r[QCAP];
@@ -111,94 +111,106 @@ __device__ __forceinline__ double& ns_at(Smem& S, int k, int i) {
   return S.M[(119 - 2 * (k - QMAX) - h) * LD + (i - 60 * h)];
 }
 
-// Register tiling of the sweep: a 16 x TXN thread grid (TXN = NT/16 = 16 or 32 thread columns); thread (ty, tx) owns
-// the elements (ty + 16a, tx + TXN b), a < 8, b < CB = 128 / TXN.
-template <int NT>
-struct Tile {
-  static constexpr int TXN = NT / 16;
-  static constexpr int CB = 128 / TXN;
-};
+// Register tiling of the sweep: a 16 x 16 thread grid; thread (ty, tx) owns the elements (ty + 16a, tx + 16b), a, b < 8.
+// The pivot column travels through shared memory in a permuted layout -- row R at (R & 15) * 10 + (R >> 4) -- so that
+// the eight rows a thread owns (and the eight column multipliers it needs) are contiguous: publishing and reading a
+// column are 128-bit accesses, and the stride of 10 doubles keeps the quarter-warps of those accesses conflict-free.
+constexpr int CPAD = 10;
 
-template <int NT, int B, int NB>
-__device__ __forceinline__ void publish_col(const double (&m)[8][Tile<NT>::CB], double* dst, int ty) {
-  constexpr int BB = B < Tile<NT>::CB ? B : Tile<NT>::CB - 1;
+template <int B, int NB>
+__device__ __forceinline__ void publish_col(const double (&m)[8][8], double* dst, int ty) {
+  constexpr int BB = B < 8 ? B : 7;
+  double2* d2 = reinterpret_cast<double2*>(dst + CPAD * ty);
 #pragma unroll
-  for (int a = 0; a < NB; a++) dst[ty + 16 * a] = m[a][BB];
+  for (int a = 0; a < NB; a += 2) d2[a >> 1] = make_double2(m[a][BB], m[a + 1][BB]);
 }
 
 // Steps j = 16*BJ .. 16*BJ+15 of the Gauss-Jordan sweep over NB row blocks of 16 (see phase E).  The block index of
 // the pivot is a template parameter, so every register index is static and eliminated column blocks cost nothing.
-template <int NT, int NB, int BJ>
+template <int NB, int BJ>
 struct SweepBlock {
-  static constexpr int TXN = Tile<NT>::TXN, CB = Tile<NT>::CB;
-  static constexpr int NBC = (16 * NB + TXN - 1) / TXN;  // column blocks in use
-  static constexpr int CBJ = (16 * BJ) / TXN;            // column block of the pivots of this step group
-  static constexpr int TX0 = (16 * BJ) % TXN;            // thread column of its first pivot
-  static __device__ __forceinline__ bool run(double (&m)[8][CB], Smem& S, int n, int tx, int ty, int tid) {
-#pragma unroll 1
-    for (int tj = 0; tj < 16; tj++) {
-      const int j = 16 * BJ + tj, txj = TX0 + tj;
-      if (j >= n) return true;
-      const double* cur = S.col[j & 1];
-      double* nxt = S.col[(j + 1) & 1];
-      const double d = cur[j];
-      if (!(d > 0.0)) return false;  // uniform: every thread reads the same value
-      const double rd = rcp_fast(d);
-      if (tid == 0) S.dval[j] = d;
-      double ci[CB], cv[8];
+  // one step; CUR = parity of the buffer that holds pivot column j
+  template <int CUR>
+  static __device__ __forceinline__ void step(double (&m)[8][8], Smem& S, int tj, int tx, int ty, int tid, bool& ok) {
+    const double* cur = S.col[CUR];
+    double* nxt = S.col[CUR ^ 1];
+    const double d = cur[CPAD * tj + BJ];  // M[j][j], j = 16 BJ + tj
+    ok = ok && (d > 0.0);
+    const double rd = rcp_fast(d);
+    if (tid == 0) S.dval[16 * BJ + tj] = d;
+    double ci[8], cv[8];
+    const double2* cv2 = reinterpret_cast<const double2*>(cur + CPAD * ty);
+    const double2* ci2 = reinterpret_cast<const double2*>(cur + CPAD * tx);
 #pragma unroll
-      for (int a = 0; a < NB; a++) cv[a] = cur[ty + 16 * a];
-      if (ty == tj) cv[BJ] = 0.0;  // row j itself is assigned below
-#pragma unroll
-      for (int b = CBJ; b < NBC; b++) ci[b] = cur[tx + TXN * b] * rd;  // rows/columns >= n are zero already
-      if (tx <= txj) ci[CBJ] = 0.0;  // columns <= j are finished
-#pragma unroll
-      for (int b = CBJ; b < NBC; b++)
-#pragma unroll
-        for (int a = 0; a < NB; a++) m[a][b] = fma(-cv[a], ci[b], m[a][b]);
-      if (ty == tj) {
-        if (tx > txj) m[BJ][CBJ] = -ci[CBJ];
-#pragma unroll
-        for (int b = CBJ + 1; b < NBC; b++) m[BJ][b] = -ci[b];
-      }
-      if (tj < 15) {
-        if (tx == txj + 1) publish_col<NT, CBJ, NB>(m, nxt, ty);
-      } else if (BJ + 1 < NB) {
-        constexpr int CBN = (16 * (BJ + 1)) / TXN, TXN0 = (16 * (BJ + 1)) % TXN;
-        if (tx == TXN0) publish_col<NT, CBN, NB>(m, nxt, ty);
-      }
-      __syncthreads();
+    for (int a = 0; a < NB; a += 2) {
+      const double2 v = cv2[a >> 1];
+      cv[a] = v.x;
+      cv[a + 1] = v.y;
     }
-    return SweepBlock<NT, NB, BJ + 1>::run(m, S, n, tx, ty, tid);
+#pragma unroll
+    for (int b = BJ & ~1; b < NB; b += 2) {  // rows/columns >= n are zero already
+      const double2 v = ci2[b >> 1];
+      ci[b] = v.x * rd;
+      ci[b + 1] = v.y * rd;
+    }
+    const bool rowj = ty == tj;
+    if (rowj) cv[BJ] = 0.0;         // row j itself is assigned below
+    if (tx <= tj) ci[BJ] = 0.0;     // columns <= j are finished
+#pragma unroll
+    for (int b = BJ; b < NB; b++)
+#pragma unroll
+      for (int a = 0; a < NB; a++) m[a][b] = fma(-cv[a], ci[b], m[a][b]);
+    if (rowj) {
+      if (tx > tj) m[BJ][BJ] = -ci[BJ];
+#pragma unroll
+      for (int b = BJ + 1; b < NB; b++) m[BJ][b] = -ci[b];
+    }
+    if (tj < 15) {
+      if (tx == tj + 1) publish_col<BJ, NB>(m, nxt, ty);
+    } else if (BJ + 1 < NB) {
+      if (tx == 0) publish_col<BJ + 1, NB>(m, nxt, ty);
+    }
+    __syncthreads();
+  }
+  static __device__ __forceinline__ bool run(double (&m)[8][8], Smem& S, int n, int tx, int ty, int tid, bool ok) {
+#pragma unroll 1
+    for (int tj = 0; tj < 16; tj += 2) {  // 16 BJ is even: even steps read buffer 0, odd steps buffer 1
+      if (16 * BJ + tj >= n) return ok;
+      step<0>(m, S, tj, tx, ty, tid, ok);
+      if (16 * BJ + tj + 1 >= n) return ok;
+      step<1>(m, S, tj + 1, tx, ty, tid, ok);
+    }
+    return SweepBlock<NB, BJ + 1>::run(m, S, n, tx, ty, tid, ok);
   }
 };
-template <int NT, int NB>
-struct SweepBlock<NT, NB, NB> {
-  static __device__ __forceinline__ bool run(double (&)[8][Tile<NT>::CB], Smem&, int, int, int, int) { return true; }
+template <int NB>
+struct SweepBlock<NB, NB> {
+  static __device__ __forceinline__ bool run(double (&)[8][8], Smem&, int, int, int, int, bool ok) { return ok; }
 };
 
 // load the symmetric H into the register tiles, sweep, and store X^T above the diagonal of S.M
-template <int NT, int NB>
+template <int NB>
 __device__ __noinline__ bool sweep(Smem& S, int n, int tid) {
-  constexpr int TXN = Tile<NT>::TXN, CB = Tile<NT>::CB, NBC = (16 * NB + TXN - 1) / TXN;
-  const int tx = tid % TXN, ty = tid / TXN;
-  double m[8][CB];
+  const int tx = tid & 15, ty = tid >> 4;
+  double m[8][8];
 #pragma unroll
   for (int a = 0; a < NB; a++)
 #pragma unroll
-    for (int b = 0; b < NBC; b++) {
-      const int R = ty + 16 * a, C = tx + TXN * b;
+    for (int b = 0; b < NB; b++) {
+      const int R = ty + 16 * a, C = tx + 16 * b;
       m[a][b] = (R < n && C < n) ? (C <= R ? S.M[R * LD + C] : S.M[C * LD + R]) : 0.0;
     }
-  if (tx == 0) publish_col<NT, 0, NB>(m, S.col[0], ty);
+  if (tx == 0) publish_col<0, NB>(m, S.col[0], ty);
   __syncthreads();
-  const bool ok = SweepBlock<NT, NB, 0>::run(m, S, n, tx, ty, tid);
+  // a non-positive pivot (H not positive definite: only possible with non-finite or absurd inputs) poisons the rest of
+  // the sweep with NaN/Inf but cannot hang it; it is reported once at the end
+  const bool ok = SweepBlock<NB, 0>::run(m, S, n, tx, ty, tid, true);
   if (!__syncthreads_and(ok)) return false;
   if (tid < n) S.dinv[tid] = 1.0 / sqrt(S.dval[tid]);
   __syncthreads();
 #pragma unroll
-  for (int b = 0; b < NBC; b++) {
-    const int C = tx + TXN * b;
+  for (int b = 0; b < NB; b++) {
+    const int C = tx + 16 * b;
     const double sc = C < n ? S.dinv[C] : 0.0;
 #pragma unroll
     for (int a = 0; a < NB; a++) {
@@ -549,10 +561,11 @@ mpc_qp_kernel(const __grid_constant__ DevParams P, const qpb_mpc_rec* __restrict
       {
         const int nb = (n + 15) >> 4;
         bool ok;
-        if (nb <= 2) ok = sweep<NT, 2>(S, n, tid);
-        else if (nb <= 4) ok = sweep<NT, 4>(S, n, tid);
-        else if (nb <= 6) ok = sweep<NT, 6>(S, n, tid);
-        else ok = sweep<NT, 8>(S, n, tid);
+        static_assert(NT == 256, "the sweep is written for a 16 x 16 thread grid");
+        if (nb <= 2) ok = sweep<2>(S, n, tid);
+        else if (nb <= 4) ok = sweep<4>(S, n, tid);
+        else if (nb <= 6) ok = sweep<6>(S, n, tid);
+        else ok = sweep<8>(S, n, tid);
         if (!ok) status = QPB_BAD_INPUT;
       }
     }

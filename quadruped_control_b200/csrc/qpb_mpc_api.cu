@@ -51,7 +51,6 @@ struct qpb_mpc_handle {
   int device = 0;
   int num_sms = 0;
   qpbmpc::DevParams dp;
-  int threads = 256;  // threads per CTA: 256 or 512 (QPB_MPC_THREADS at qpb_mpc_create time)
   unsigned long long* d_tickets = nullptr;
   std::atomic<uint32_t> ticket_slot{ 0 };
   std::atomic<int64_t> launches{ 0 };
@@ -69,10 +68,7 @@ int launch_mpc(qpb_mpc_handle* h, int64_t n, const qpb_mpc_rec* d_recs, qpb_mpc_
   const uint32_t slot = h->ticket_slot.fetch_add(1, std::memory_order_relaxed) % kTicketSlots;
   unsigned long long* t0 = h->d_tickets + slot;
   unsigned long long* t1 = h->d_tickets + (slot + kTicketSlots / 2) % kTicketSlots;
-  if (h->threads == 512)
-    qpbmpc::mpc_qp_kernel<512><<<grid, 512, sizeof(qpbmpc::Smem), stream>>>(h->dp, d_recs, d_out, n, t0, t1);
-  else
-    qpbmpc::mpc_qp_kernel<256><<<grid, 256, sizeof(qpbmpc::Smem), stream>>>(h->dp, d_recs, d_out, n, t0, t1);
+  qpbmpc::mpc_qp_kernel<256><<<grid, 256, sizeof(qpbmpc::Smem), stream>>>(h->dp, d_recs, d_out, n, t0, t1);
   h->launches.fetch_add(1, std::memory_order_relaxed);
   MPC_CUDA(cudaGetLastError());
   return QPB_SUCCESS;
@@ -139,12 +135,7 @@ int qpb_mpc_create(const qpb_mpc_params* params, int device, qpb_mpc_handle** ou
   cudaError_t e = cudaGetDeviceProperties(&prop, device);
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(qpbmpc::mpc_qp_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(qpbmpc::Smem));
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(qpbmpc::mpc_qp_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(qpbmpc::Smem));
-  if (const char* env = std::getenv("QPB_MPC_THREADS")) {
-    const int v = std::atoi(env);
-    if (v == 256 || v == 512) h->threads = v;
-  }
+
   if (e == cudaSuccess) e = cudaMalloc(&h->d_tickets, kTicketSlots * sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaMemset(h->d_tickets, 0, kTicketSlots * sizeof(unsigned long long));
   if (e != cudaSuccess) {

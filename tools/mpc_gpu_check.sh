@@ -4,9 +4,3 @@ export QPB_LIB=$PWD/quadruped_control_b200/libqpb200_prof.so
 timeout 200 python tools/time_mpc.py 16384 mixed >> gpurun_out/mpc_time.log 2>&1
 for g in stand trot crawl; do timeout 200 python tools/time_mpc.py 8192 $g >> gpurun_out/mpc_time.log 2>&1; done
 cat gpurun_out/mpc_tests.log gpurun_out/mpc_time.log
-echo "---- 512 threads per CTA"
-export QPB_MPC_THREADS=512
-timeout 200 python tools/time_mpc.py 16384 mixed 2>&1
-for g in stand trot crawl; do timeout 200 python tools/time_mpc.py 8192 $g 2>&1; done
-unset QPB_LIB
-timeout 200 python tools/time_mpc.py 65536 mixed 2>&1
