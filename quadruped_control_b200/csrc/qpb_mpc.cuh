@@ -29,6 +29,7 @@ constexpr int NV = 120;   // variables before compaction
 constexpr int LD = 121;   // odd leading dimension: row- and column-wise sweeps are both bank-conflict free
 constexpr int QMAX = 90;  // rows of N* with their own storage; rows 90..119 live in the dead lower triangle of M
 constexpr int QCAP = 120; // working-set capacity = the largest possible number of independent rows
+constexpr int QSPARSE = 32; // up to this many active rows z~ = n~ - sum_k r_k n~_k is formed slot by slot (no mat-vec)
 constexpr int MROWS = 240;
 constexpr unsigned FULL = 0xffffffffu;
 
@@ -62,6 +63,8 @@ struct __align__(16) Smem {
   double r[QCAP];
   double dd[QCAP];
   double ratio[QCAP];   // max(u_k, 0) / r_k where r_k > 0, else +inf
+  double scv[QCAP], scz[QCAP];          // per working-set slot: coefficients of its row on the lateral and the z variable
+  unsigned char sv[QCAP], sz[QCAP];     // ... and the indices of those two variables
   double part[2][NWMAX];   // per-warp partial sums of |n~|^2 and n~.z~
   int A[QCAP];
   unsigned red[NWMAX];
@@ -651,33 +654,50 @@ mpc_qp_kernel(const __grid_constant__ DevParams P, const qpb_mpc_rec* __restrict
             }
             __syncthreads();
             MPC_TICK(9);
-            // (3) w = N r gathered through the sparse rows in a fixed order (an atomic scatter would be one barrier
-            //     cheaper but not bitwise reproducible), then z~ = n~ - X w and per-warp partials of zeta = n~.z~
-            if (tid < n) {
-              const int c = tid / 3, comp = tid - 3 * c;
-              double a = 0.0;
-#pragma unroll
-              for (int t = 0; t < 6; t++) {
-                const int row = 6 * c + t;
-                if (S.act[row] == 1) a = fma(row_coef(t, comp, P.mu), S.r[S.slot_of_row[row]], a);
-              }
-              S.w[tid] = a;
-            }
-            __syncthreads();
-            MPC_TICK(10);
-            double xa, xb;
-            tri_X8<NT>(S, S.w, tm, xa, xb);
             double zp = 0.0;
-            if (wrA) {
-              const double za = S.nt[tm.iA] - xa;
-              S.zt[tm.iA] = za;
-              zp = za * S.nt[tm.iA];
+            if (q <= QSPARSE) {
+              // (3a) few active rows: z~_i = n~_i - sum_k r_k n~_k[i] with n~_k = X n_k rebuilt from two columns of X;
+              //      two threads per i (slot parity), combined in a fixed order
+              const int i = tid >> 1, par = tid & 1;
+              double acc = 0.0;
+              if (i < n)
+                for (int k = par; k < q; k += 2)
+                  acc = fma(S.r[k], fma(S.scv[k], X_at(S, i, S.sv[k]), S.scz[k] * X_at(S, i, S.sz[k])), acc);
+              acc += __shfl_xor_sync(FULL, acc, 1);
+              if (i < n && par == 0) {
+                const double nti = S.nt[i], z = nti - acc;
+                S.zt[i] = z;
+                zp = z * nti;
+              }
+            } else {
+              // (3b) w = N r gathered through the sparse rows in a fixed order (an atomic scatter would be one barrier
+              //      cheaper but not bitwise reproducible), then z~ = n~ - X w
+              if (tid < n) {
+                const int c = tid / 3, comp = tid - 3 * c;
+                double a = 0.0;
+#pragma unroll
+                for (int t = 0; t < 6; t++) {
+                  const int row = 6 * c + t;
+                  if (S.act[row] == 1) a = fma(row_coef(t, comp, P.mu), S.r[S.slot_of_row[row]], a);
+                }
+                S.w[tid] = a;
+              }
+              __syncthreads();
+              MPC_TICK(10);
+              double xa, xb;
+              tri_X8<NT>(S, S.w, tm, xa, xb);
+              if (wrA) {
+                const double za = S.nt[tm.iA] - xa;
+                S.zt[tm.iA] = za;
+                zp = za * S.nt[tm.iA];
+              }
+              if (wrB) {
+                const double zb = S.nt[tm.iB] - xb;
+                S.zt[tm.iB] = zb;
+                zp = fma(zb, S.nt[tm.iB], zp);
+              }
             }
-            if (wrB) {
-              const double zb = S.nt[tm.iB] - xb;
-              S.zt[tm.iB] = zb;
-              zp = fma(zb, S.nt[tm.iB], zp);
-            }
+            // per-warp partials of zeta = n~.z~
             zp = warp_sum(zp);
             if (lane == 0) S.part[1][warp] = zp;
             __syncthreads();
@@ -747,6 +767,10 @@ mpc_qp_kernel(const __grid_constant__ DevParams P, const qpb_mpc_rec* __restrict
               S.u[q] = up;
               S.slot_of_row[p] = (unsigned char)q;
               S.act[p] = 1;
+              S.sv[q] = (unsigned char)vv;
+              S.sz[q] = (unsigned char)zz;
+              S.scv[q] = cvv;
+              S.scz[q] = czz;
             }
             q++;
             __syncthreads();
@@ -782,6 +806,10 @@ mpc_qp_kernel(const __grid_constant__ DevParams P, const qpb_mpc_rec* __restrict
               S.A[ks] = S.A[last];
               S.u[ks] = S.u[last];
               S.slot_of_row[S.A[last]] = (unsigned char)ks;
+              S.sv[ks] = S.sv[last];
+              S.sz[ks] = S.sz[last];
+              S.scv[ks] = S.scv[last];
+              S.scz[ks] = S.scz[last];
             }
           }
           q--;
