@@ -159,10 +159,14 @@ struct SweepBlock {
     const bool rowj = ty == tj;
     if (rowj) cv[BJ] = 0.0;         // row j itself is assigned below
     if (tx <= tj) ci[BJ] = 0.0;     // columns <= j are finished
+    // Row blocks a <= BJ hold rows of the inverse (all columns right of the pivot change); row blocks a > BJ hold the
+    // trailing Hessian, of which only the lower triangle (b <= a) is ever read again -- the tiles above it are skipped
+    // and simply overwritten when their rows become pivot rows.
 #pragma unroll
     for (int b = BJ; b < NB; b++)
 #pragma unroll
-      for (int a = 0; a < NB; a++) m[a][b] = fma(-cv[a], ci[b], m[a][b]);
+      for (int a = 0; a < NB; a++)
+        if (a <= BJ || b <= a) m[a][b] = fma(-cv[a], ci[b], m[a][b]);
     if (rowj) {
       if (tx > tj) m[BJ][BJ] = -ci[BJ];
 #pragma unroll
