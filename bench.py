@@ -470,16 +470,175 @@ def run_mpc(args):
         dist.destroy_process_group()
 
 
+def run_tick(args):
+    """--workload tick: the whole controller tick per robot on the device (SURVEY.md 8f ranks 1, 3, 4 around the hot path):
+    CoMState/JointState messages -> adapter -> foothold planner + swing-foot reference -> balance QP + J^T f + swing-leg PD
+    -> JointTorqueCmd, five launches on one stream, 1 048 576 mixed-contact robots per GPU."""
+    import torch
+
+    from quadruped_control_b200 import lib
+    from quadruped_control_b200.records import (COM_MSG_DTYPE, JOINT_MSG_DTYPE, PLAN_DTYPE, SWING_DTYPE, TORQUE_CMD_DTYPE,
+                                                default_joint_gains, default_plan_params)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback for the product path)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    n = 1048576
+    params = default_params(MU)
+    solver = lib.BalanceSolver(params, device=local_rank)
+    S = states.generate_states(n, 20260103, lo=rank * n, profile="light", masks="mixed")
+    rng = np.random.default_rng(7 + rank)
+    com = np.zeros(n, dtype=COM_MSG_DTYPE)
+    from scipy.spatial.transform import Rotation
+
+    com["orientation"] = Rotation.from_matrix(S["Rwb"].reshape(n, 3, 3)).as_quat()
+    com["position"], com["linear"], com["angular"] = S["x"], S["xdot"], S["w"]
+    js = np.zeros(n, dtype=JOINT_MSG_DTYPE)
+    js["position"] = S["q"].reshape(n, 4, 3).transpose(0, 2, 1).reshape(n, 12)
+    js["velocity"] = rng.normal(0, 1.0, size=(n, 12))
+    plan = np.zeros(n, dtype=PLAN_DTYPE)
+    plan["phase"] = rng.uniform(0.83, 1.0, size=(n, 4))
+    plan["replan"] = 1
+
+    def pin(a):
+        return torch.from_numpy(a.view(np.uint8).reshape(-1)).pin_memory()
+
+    h_com, h_js, h_plan = pin(com), pin(js), pin(plan)
+    d_com, d_js, d_S = h_com.to(dev), h_js.to(dev), torch.from_numpy(S.view(np.uint8).reshape(-1)).to(dev)
+    d_plan0 = h_plan.to(dev)
+    d_plan = d_plan0.clone()
+    d_sw = torch.zeros(n * SWING_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+    d_out = torch.zeros(n * OUT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+    d_cmd = torch.zeros(n * TORQUE_CMD_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+    h_cmd = torch.empty(n * TORQUE_CMD_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+    h_plan_out = torch.empty(n * PLAN_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+    stream = torch.cuda.current_stream()
+    st = stream.cuda_stream
+
+    def tick():
+        solver.adapt_inputs(d_com, d_js, d_S, d_sw, n, stream=st)
+        solver.plan(d_S, d_plan, d_sw, n, stream=st)
+        solver.tick_packed(d_S, d_sw, d_out, n, stream=st)
+        solver.torque_cmd(d_S, d_out, d_cmd, n, stream=st)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        tick()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    barrier()
+    launches0 = solver.launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_begin = time.perf_counter()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        tick()
+    ev1.record(stream)
+    barrier()
+    t_end = time.perf_counter()
+    launches = solver.launches - launches0
+    clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
+    out = d_out.cpu().numpy().view(OUT_DTYPE)
+    failed = int((out["status"] != 0).sum())
+    elapsed_ms, (tot_launches, tot_failed) = reduce_report(ev0.elapsed_time(ev1), [launches, failed], dist, dev)
+    total = world * n * args.steps / (elapsed_ms * 1e-3)
+
+    # end to end: messages and plan records up from pinned host memory, torque commands and plan records back
+    e2e_steps = max(3, min(args.steps, 10))
+
+    def tick_e2e():
+        d_com.copy_(h_com, non_blocking=True)
+        d_js.copy_(h_js, non_blocking=True)
+        d_plan.copy_(h_plan, non_blocking=True)
+        tick()
+        h_cmd.copy_(d_cmd, non_blocking=True)
+        h_plan_out.copy_(d_plan, non_blocking=True)
+        torch.cuda.synchronize()
+
+    tick_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        tick_e2e()
+    e2e_local = (time.perf_counter() - t0) * 1e3
+    barrier()
+    e2e_ms, _ = reduce_report(e2e_local, [0], dist, dev)
+    e2e = world * n * e2e_steps / (e2e_ms * 1e-3)
+
+    if rank == 0:
+        import oracle
+
+        cores = os.cpu_count() or 1
+        m = 65536
+        S_ref, plan_ref = S[:m].copy(), plan[:m].copy()
+        sw_ref = np.zeros(m, dtype=SWING_DTYPE)
+        gains, pp = default_joint_gains(), default_plan_params()
+        t0 = time.perf_counter()
+        oracle.adapt_inputs(params, com[:4096], js[:4096], S_ref[:4096], sw_ref[:4096])
+        t_adapt = (time.perf_counter() - t0) / 4096  # python loop over a C call: an upper bound, reported separately
+        t0 = time.perf_counter()
+        oracle.plan_batch(pp, S_ref, plan_ref, sw_ref)
+        t_plan = (time.perf_counter() - t0) / m
+        t0 = time.perf_counter()
+        ref = oracle.tick_batch(params, gains, S_ref, sw_ref, cores)
+        t_tick = (time.perf_counter() - t0) / m
+        cpu_rate = 1.0 / (t_plan / 1.0 + t_tick)  # planner single-threaded + tick on all cores, adapter excluded
+        ok = np.isfinite(ref["tau"]).all(axis=1) & (np.abs(ref["tau"]).max(axis=1) < 1e3)
+        err = float((np.abs(out["grf_body"][:m] - ref["grf_body"]).max(axis=1) / np.maximum(np.abs(ref["grf_body"]).max(axis=1), 1.0))[ok].max())
+        bytes_per_robot = 104 + 192 + 240 + 240 + 512 + 288 + 256 + 112  # messages, plan in/out, state, swing, result, command
+        peak, peak_src = measured_peak_hbm()
+        kernel_ms = elapsed_ms / args.steps
+        achieved = bytes_per_robot * n / (kernel_ms * 1e-3) / 1e9
+        print(json.dumps({
+            "metric": "control ticks/sec (messages -> torque commands, batched)", "value": total, "unit": "ticks/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "tick: 1048576 mixed 2/3/4-foot robots per GPU, light profile; adapter + planner (footholds planned on the first tick, swing-foot references every tick; the end-to-end leg re-plans every tick) + balance QP + swing PD + torque command",
+                       "robots_per_step_per_gpu": n, "parallelism": f"batch-sharded x{world}", "l2": "inputs larger than L2 (1.9 GB of records per step)"},
+            "max_rel_grf_err_vs_oracle": err, "failed_qps": int(tot_failed),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "peak_source": peak_src, "algorithmic_bytes_per_robot": bytes_per_robot, "kernel": "adapt + plan + balance_qp_kernel16 + swing + torque_cmd",
+                         "kernel_ms": kernel_ms, "note": "five launches; the balance kernel is about three quarters of the step and is FP64-issue bound"},
+            "cpu_baseline": {"value": cpu_rate, "unit": "ticks/s", "cores": cores, "kind": "port",
+                             "sample": f"first {m} robots: oracle planner (1 thread) + oracle tick ({cores} threads); message adapter not included ({t_adapt * 1e6:.1f} us per robot through a python loop)"},
+            "e2e": {"value": e2e, "unit": "ticks/s", "h2d_bytes_per_step": n * (104 + 192 + 240), "d2h_bytes_per_step": n * (112 + 240), "steps": e2e_steps,
+                    "api": "qpb_adapt_inputs_batch + qpb_plan_batch + qpb_tick_batch_packed + qpb_torque_cmd_batch around pinned-memory copies"},
+            "gpu_launches": int(tot_launches), "clocks": clocks}), flush=True)
+    solver.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=("ours", "reference"), default="ours")
-    ap.add_argument("--workload", choices=sorted(WORKLOADS) + ["cfg4"], default="cfg2")
+    ap.add_argument("--workload", choices=sorted(WORKLOADS) + ["cfg4", "tick"], default="cfg2")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
-    if args.workload == "cfg4":
+    if args.workload == "tick":
+        if args.impl == "reference":
+            raise SystemExit("--workload tick has no reference arm (use the default workload)")
+        run_tick(args)
+    elif args.workload == "cfg4":
         (run_mpc_reference if args.impl == "reference" else run_mpc)(args)
     elif args.impl == "reference":
         run_reference(args)
