@@ -50,7 +50,8 @@ struct __align__(16) Smem {
   double rec[272];      // staged record; reused as the output record
   double G[NV * 3];     // g_a = I_k^-1 (r x e_c)
   double dinv[NV];      // 1 / L_jj  (= X_jj)
-  double f[NV];
+  double f[NV];         // primal iterate = f + f2: the two halves of the step mat-vec accumulate into their own array
+  double f2[NV];
   double nt[NV];
   double zt[NV];
   double w[NV];         // gradient during assembly, N r in the loop
@@ -592,6 +593,7 @@ mpc_qp_kernel(const __grid_constant__ DevParams P, const qpb_mpc_rec* __restrict
         tri_XT8<NT>(S, S.zt, n, tm, ya, yb);
         if (wrA) S.f[tm.iA] = ya;
         if (wrB) S.f[tm.iB] = yb;
+        if (tid < NV) S.f2[tid] = 0.0;
         __syncthreads();
       }
 
@@ -607,7 +609,7 @@ mpc_qp_kernel(const __grid_constant__ DevParams P, const qpb_mpc_rec* __restrict
         unsigned key = 0;
         if (tid < m && S.act[tid] == 0) {
           const int c = tid / 6, t = tid - 6 * c;
-          const double s = row_slack(t, S.f[3 * c], S.f[3 * c + 1], S.f[3 * c + 2], P);
+          const double s = row_slack(t, S.f[3 * c] + S.f2[3 * c], S.f[3 * c + 1] + S.f2[3 * c + 1], S.f[3 * c + 2] + S.f2[3 * c + 2], P);
           const double tol = t < 4 ? 1e-9 : 1e-9 * fzs;
           if (s < -tol) key = ((unsigned)__double2hiint(-s) & 0xffffff00u) | (unsigned)tid;
         }
@@ -623,7 +625,7 @@ mpc_qp_kernel(const __grid_constant__ DevParams P, const qpb_mpc_rec* __restrict
         const int pc = p / 6, pt = p - 6 * pc;
         const int zz = 3 * pc + 2, vv = (pt == 0 || pt == 3) ? 3 * pc : ((pt == 1 || pt == 2) ? 3 * pc + 1 : zz);
         const double cvv = pt < 4 ? row_coef(pt, vv - 3 * pc, P.mu) : 0.0, czz = row_coef(pt, 2, P.mu);
-        double sp = row_slack(pt, S.f[3 * pc], S.f[3 * pc + 1], S.f[3 * pc + 2], P);
+        double sp = row_slack(pt, S.f[3 * pc] + S.f2[3 * pc], S.f[3 * pc + 1] + S.f2[3 * pc + 1], S.f[3 * pc + 2] + S.f2[3 * pc + 2], P);
         double up = 0.0;
         bool stop = false;
         for (;;) {  // steps towards row p until it joins the working set
@@ -747,10 +749,47 @@ mpc_qp_kernel(const __grid_constant__ DevParams P, const qpb_mpc_rec* __restrict
           MPC_TICK(12);
           // (5) primal and dual step
           if (!dep) {
-            double da, db;
-            tri_XT8<NT>(S, ztp, n, tm, da, db);
-            if (wrA) S.f[tm.iA] = fma(t, da, S.f[tm.iA]);
-            if (wrB) S.f[tm.iB] = fma(t, db, S.f[tm.iB]);
+            // delta f = X^T z~, one lane per column and half of the inner indices (even / odd): no cross-lane reduction,
+            // z~_i is a broadcast load, rows of M are read with the conflict-free stride LD.  Column block wc has about
+            // (n - 32 wc) / 2 terms per lane, and warps w and w + 4 share a scheduler, so warp w takes block w and warp
+            // w + 4 block 3 - w: every scheduler gets a long and a short one.  Each half accumulates into its own copy of
+            // the iterate (f and f2).
+            {
+              const int hf = warp >> 2, wc = hf ? 3 - (warp & 3) : warp, c0 = 32 * wc, c = c0 + lane;
+              double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+              if (c0 < n) {
+                const double* row = &S.M[(c < n ? c : 0) * LD];
+                int i = c0 + 1 + ((c0 + 1 + hf) & 1);  // first inner index > c0 with the parity of this half
+                // head: lanes join as i passes their column; entries at or left of the diagonal (finite leftovers of the
+                // assembly) are loaded unconditionally and masked to zero so that the loads pipeline
+                for (; i <= c0 + 32 && i + 6 < n; i += 8) {
+                  const double m0 = row[i], m1 = row[i + 2], m2 = row[i + 4], m3 = row[i + 6];
+                  a0 = fma(i > c ? m0 : 0.0, ztp[i], a0);
+                  a1 = fma(i + 2 > c ? m1 : 0.0, ztp[i + 2], a1);
+                  a2 = fma(i + 4 > c ? m2 : 0.0, ztp[i + 4], a2);
+                  a3 = fma(i + 6 > c ? m3 : 0.0, ztp[i + 6], a3);
+                }
+                for (; i + 6 < n; i += 8) {
+                  a0 = fma(row[i], ztp[i], a0);
+                  a1 = fma(row[i + 2], ztp[i + 2], a1);
+                  a2 = fma(row[i + 4], ztp[i + 4], a2);
+                  a3 = fma(row[i + 6], ztp[i + 6], a3);
+                }
+                {  // tail: at most three more indices of this parity
+                  const double m0 = i < n ? row[i] : 0.0, m1 = i + 2 < n ? row[i + 2] : 0.0, m2 = i + 4 < n ? row[i + 4] : 0.0;
+                  const double v0 = i < n ? ztp[i] : 0.0, v1 = i + 2 < n ? ztp[i + 2] : 0.0, v2 = i + 4 < n ? ztp[i + 4] : 0.0;
+                  a0 = fma(i > c ? m0 : 0.0, v0, a0);
+                  a1 = fma(i + 2 > c ? m1 : 0.0, v1, a1);
+                  a2 = fma(i + 4 > c ? m2 : 0.0, v2, a2);
+                }
+              }
+              if (c < n) {
+                double a = (a0 + a1) + (a2 + a3);
+                if (hf == 0) a = fma(S.dinv[c], ztp[c], a);
+                double* fa = hf ? S.f2 : S.f;
+                fa[c] = fma(t, a, fa[c]);
+              }
+            }
             sp = fma(t, zeta, sp);
           }
           if (tid < q) S.u[tid] = fma(-t, S.r[tid], S.u[tid]);
@@ -831,7 +870,7 @@ mpc_qp_kernel(const __grid_constant__ DevParams P, const qpb_mpc_rec* __restrict
     __syncthreads();
     if (status == QPB_OK && tid < n) {
       const int c = tid / 3, comp = tid - 3 * c;
-      S.rec[12 * S.sfk[c] + 3 * S.sff[c] + comp] = S.f[tid];
+      S.rec[12 * S.sfk[c] + 3 * S.sff[c] + comp] = S.f[tid] + S.f2[tid];
     }
     if (tid == 0) {
       int* tail = reinterpret_cast<int*>(&S.rec[120]);
