@@ -638,8 +638,10 @@ mpc_qp_kernel(const __grid_constant__ DevParams P, const qpb_mpc_rec* __restrict
               v = cvv * X_at(S, tid, vv) + czz * X_at(S, tid, zz);
               S.nt[tid] = v;
             }
-            v = warp_sum(v * v);
-            if (lane == 0) S.part[0][warp] = v;
+            if (q == 0) {  // with an empty working set zeta = |n~|^2 is needed right away; otherwise stage (3) forms it
+              v = warp_sum(v * v);
+              if (lane == 0) S.part[0][warp] = v;
+            }
           }
           __syncthreads();
           MPC_TICK(8);
@@ -650,8 +652,23 @@ mpc_qp_kernel(const __grid_constant__ DevParams P, const qpb_mpc_rec* __restrict
               const int k = k0 + hh;
               const bool valid = k < q;
               double a = 0.0;
-              if (valid)
-                for (int i = hl; i < n; i += 16) a = fma(ns_at(S, k, i), S.nt[i], a);
+              if (valid) {
+                if (k < QMAX) {  // the row has its own storage: eight masked terms per lane, loads issued up front
+                  const double* row = &S.NS[k * NV];
+                  double a1 = 0.0;
+#pragma unroll
+                  for (int j = 0; j < 8; j += 2) {
+                    const int i0 = hl + 16 * j, i1 = i0 + 16;
+                    const double m0 = i0 < n ? row[i0] : 0.0, m1 = i1 < n ? row[i1] : 0.0;
+                    const double v0 = i0 < n ? S.nt[i0] : 0.0, v1 = i1 < n ? S.nt[i1] : 0.0;
+                    a = fma(m0, v0, a);
+                    a1 = fma(m1, v1, a1);
+                  }
+                  a += a1;
+                } else {
+                  for (int i = hl; i < n; i += 16) a = fma(ns_at(S, k, i), S.nt[i], a);
+                }
+              }
               a = half_sum(a);
               if (valid && hl == 0) {
                 S.r[k] = a;
@@ -660,7 +677,7 @@ mpc_qp_kernel(const __grid_constant__ DevParams P, const qpb_mpc_rec* __restrict
             }
             __syncthreads();
             MPC_TICK(9);
-            double zp = 0.0;
+            double zp = 0.0, np = 0.0;
             if (q <= QSPARSE) {
               // (3a) few active rows: z~_i = n~_i - sum_k r_k n~_k[i] with n~_k = X n_k rebuilt from two columns of X;
               //      two threads per i (slot parity), combined in a fixed order
@@ -674,6 +691,7 @@ mpc_qp_kernel(const __grid_constant__ DevParams P, const qpb_mpc_rec* __restrict
                 const double nti = S.nt[i], z = nti - acc;
                 S.zt[i] = z;
                 zp = z * nti;
+                np = nti * nti;
               }
             } else {
               // (3b) w = N r gathered through the sparse rows in a fixed order (an atomic scatter would be one barrier
@@ -693,19 +711,25 @@ mpc_qp_kernel(const __grid_constant__ DevParams P, const qpb_mpc_rec* __restrict
               double xa, xb;
               tri_X8<NT>(S, S.w, tm, xa, xb);
               if (wrA) {
-                const double za = S.nt[tm.iA] - xa;
+                const double na = S.nt[tm.iA], za = na - xa;
                 S.zt[tm.iA] = za;
-                zp = za * S.nt[tm.iA];
+                zp = za * na;
+                np = na * na;
               }
               if (wrB) {
-                const double zb = S.nt[tm.iB] - xb;
+                const double nb_ = S.nt[tm.iB], zb = nb_ - xb;
                 S.zt[tm.iB] = zb;
-                zp = fma(zb, S.nt[tm.iB], zp);
+                zp = fma(zb, nb_, zp);
+                np = fma(nb_, nb_, np);
               }
             }
-            // per-warp partials of zeta = n~.z~
+            // per-warp partials of zeta = n~.z~ and of |n~|^2 (two independent shuffle chains)
             zp = warp_sum(zp);
-            if (lane == 0) S.part[1][warp] = zp;
+            np = warp_sum(np);
+            if (lane == 0) {
+              S.part[1][warp] = zp;
+              S.part[0][warp] = np;
+            }
             __syncthreads();
             ztp = S.zt;
           }
