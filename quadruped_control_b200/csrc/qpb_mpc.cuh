@@ -78,7 +78,7 @@ struct __align__(16) Smem {
 
 #ifdef QPB_MPC_PROFILE
 // developer build only (tools/time_mpc.py): cycles per phase summed over all QPs, [assembly, sweep, start, loop, io, count]
-__device__ unsigned long long g_mpc_prof[16];
+__device__ unsigned long long g_mpc_prof[24];
 #define MPC_TICK(slot)                                              \
   do {                                                              \
     if (tid == 0) {                                                 \
@@ -389,6 +389,7 @@ mpc_qp_kernel(const __grid_constant__ DevParams P, const qpb_mpc_rec* __restrict
     int status = bad ? QPB_BAD_INPUT : QPB_OK, iters = 0, n = 0;
 
     if (!bad) {
+      MPC_TICK(16);
       // ---- phase A: compaction of the stance foot-steps (warp 0); per-step trigonometry and inertia (warp 1) --
       const unsigned char* cb = reinterpret_cast<const unsigned char*>(&S.rec[263]);
       if (warp == 0) {
@@ -439,6 +440,7 @@ mpc_qp_kernel(const __grid_constant__ DevParams P, const qpb_mpc_rec* __restrict
       n = 3 * ns;
       const double dt = P.dt, dt2 = dt * dt, im = 1.0 / P.mass;
 
+      MPC_TICK(17);
       // ---- phase B: torque arms g_a (threads < n); weighted free-response error (threads 128..137) ----------
       if (tid < n) {
         const int c = tid / 3, comp = tid - 3 * c, k = S.sfk[c], foot = S.sff[c];
@@ -466,28 +468,69 @@ mpc_qp_kernel(const __grid_constant__ DevParams P, const qpb_mpc_rec* __restrict
         fr[9] = x0[9]; fr[10] = x0[10];
         fr[11] = x0[11] + k1 * dt * g;
 #pragma unroll
-        for (int s = 0; s < 12; s++) S.E[12 * k + s] = (s < 3 ? P.sLw[s] : P.Lw[s]) * (fr[s] - xr[s]);
+        for (int s = 0; s < 12; s++) S.E[12 * k + s] = P.Lw[s] * (fr[s] - xr[s]);
       }
       __syncthreads();
 
-      // ---- phase C: attitude response table, sqrt-weighted: ThW[a][k][s], k > step(a) ------------------------
-      double* ThW = S.NS;
-      for (int idx = tid; idx < n * NH; idx += NT) {
-        const int a = idx / NH, k = idx - a * NH, j = S.sfk[a / 3];
-        double t0 = 0.0, t1 = 0.0, t2 = 0.0;
-        if (k > j) {
-          const double C = S.Cs[k] - S.Cs[j], Sn = S.Ss[k] - S.Ss[j];
-          const double g0 = S.G[3 * a], g1 = S.G[3 * a + 1], g2 = S.G[3 * a + 2];
-          t0 = P.sLw[0] * dt2 * (C * g0 + Sn * g1);
-          t1 = P.sLw[1] * dt2 * (-Sn * g0 + C * g1);
-          t2 = P.sLw[2] * dt2 * (double)(k - j) * g2;
+      MPC_TICK(18);
+      // ---- phase C: per-step-pair kernels of the Hessian and per-step vectors of the gradient -------------------
+      // With P_k = sum_{l<=k} T_l and S_kj = P_k - P_j (the attitude response of step k to a torque impulse at step j),
+      //   H[a][b] = 2 g_a' Kf(ja, jb) g_b + (a diagonal term when a and b are the same force component) + 2 alpha [a==b],
+      //   Kf(ja, jb) = dt^4 sum_{k>ja} S_kja' diag(Lw_att) S_kjb + dt^2 (10 - ja) diag(Lw_omega)        (jb <= ja)
+      //   gvec[a] = 2 ( g_a' (qa(ja) + dt qw(ja)) + dt^2/m qp(ja)[c] + dt/m qv(ja)[c] ),
+      //   qa(j) = dt^2 sum_{k>j} S_kj' e_att(k), qw(j) = sum_{k>=j} e_omega(k), qp(j) = sum_{k>=j} (k-j) e_p(k), qv(j) = sum_{k>=j} e_v(k)
+      // with e(k) the weighted free-response error of step k.  55 step pairs and 10 steps: no per-variable table at all.
+      double* Kf = S.NS;             // [ja][jb][9]
+      double* Qv = S.NS + 900;       // [j][12]: qa + dt qw | qp | qv | (unused)
+      if (tid < 100) {
+        const int ja = tid / NH, jb = tid - NH * ja;
+        if (jb <= ja) {
+          double k00 = 0.0, k01 = 0.0, k10 = 0.0, k11 = 0.0, k22 = 0.0;
+          const double Ca0 = S.Cs[ja], Sa0 = S.Ss[ja], Cb0 = S.Cs[jb], Sb0 = S.Ss[jb];
+          for (int k = ja + 1; k < NH; k++) {
+            const double Ck = S.Cs[k], Sk = S.Ss[k];
+            const double Ca = Ck - Ca0, Sa = Sk - Sa0, Cb = Ck - Cb0, Sb = Sk - Sb0;
+            k00 += P.Lw[0] * Ca * Cb + P.Lw[1] * Sa * Sb;
+            k01 += P.Lw[0] * Ca * Sb - P.Lw[1] * Sa * Cb;
+            k10 += P.Lw[0] * Sa * Cb - P.Lw[1] * Ca * Sb;
+            k11 += P.Lw[0] * Sa * Sb + P.Lw[1] * Ca * Cb;
+            k22 += P.Lw[2] * (double)((k - ja) * (k - jb));
+          }
+          const double dt4 = dt2 * dt2, cw = dt2 * (double)(NH - ja);
+          double* o = &Kf[9 * tid];
+          o[0] = dt4 * k00 + cw * P.Lw[6]; o[1] = dt4 * k01;               o[2] = 0.0;
+          o[3] = dt4 * k10;               o[4] = dt4 * k11 + cw * P.Lw[7]; o[5] = 0.0;
+          o[6] = 0.0;                     o[7] = 0.0;                     o[8] = dt4 * k22 + cw * P.Lw[8];
         }
-        ThW[3 * idx] = t0;
-        ThW[3 * idx + 1] = t1;
-        ThW[3 * idx + 2] = t2;
+      } else if (tid >= 128 && tid < 128 + NH) {
+        const int j = tid - 128;
+        double qa0 = 0.0, qa1 = 0.0, qa2 = 0.0, qw[3] = { 0.0, 0.0, 0.0 }, qp[3] = { 0.0, 0.0, 0.0 }, qv[3] = { 0.0, 0.0, 0.0 };
+        for (int k = j; k < NH; k++) {
+          const double* e = &S.E[12 * k];
+          const double C = S.Cs[k] - S.Cs[j], Sn = S.Ss[k] - S.Ss[j], dk = (double)(k - j);
+          qa0 += C * e[0] - Sn * e[1];  // S_kj' e_att  (zero for k == j)
+          qa1 += Sn * e[0] + C * e[1];
+          qa2 += dk * e[2];
+#pragma unroll
+          for (int c = 0; c < 3; c++) {
+            qp[c] += dk * e[3 + c];
+            qw[c] += e[6 + c];
+            qv[c] += e[9 + c];
+          }
+        }
+        double* o = &Qv[12 * j];
+        o[0] = dt2 * qa0 + dt * qw[0];
+        o[1] = dt2 * qa1 + dt * qw[1];
+        o[2] = dt2 * qa2 + dt * qw[2];
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+          o[3 + c] = dt2 * im * qp[c];
+          o[6 + c] = dt * im * qv[c];
+        }
       }
       __syncthreads();
 
+      MPC_TICK(19);
       // ---- phase D: H in 3x3 blocks (foot-step fa x foot-step fb, fb <= fa) and the gradient ------------------
       // Rows fa' and ns-1-fa' of the block triangle together hold ns+1 blocks, so idx -> (fa, fb) needs one division
       // and no thread draws a block above the diagonal.
@@ -499,63 +542,40 @@ mpc_qp_kernel(const __grid_constant__ DevParams P, const qpb_mpc_rec* __restrict
           if (!lowrow && 2 * rp == ns - 1) continue;  // odd ns: the middle row is its own partner
           const int fa = lowrow ? rp : ns - 1 - rp, fb = lowrow ? t : t - rp - 1;
           const int ja = S.sfk[fa], jb = S.sfk[fb];  // jb <= ja: the compact order is step-major
-          const double* Ta = &ThW[9 * NH * fa];      // [i][k][s] for the three variables of the foot-step
-          const double* Tb = &ThW[9 * NH * fb];
-          double acc[3][3];
+          const double* K = &Kf[9 * (NH * ja + jb)];
+          const double k00 = K[0], k01 = K[1], k10 = K[3], k11 = K[4], k22 = K[8];
+          double A[3][3], T[3][3];  // T[l] = Kf g_b,l
+#pragma unroll
+          for (int i = 0; i < 3; i++) {
+            const double b0 = S.G[9 * fb + 3 * i], b1 = S.G[9 * fb + 3 * i + 1], b2 = S.G[9 * fb + 3 * i + 2];
+            T[i][0] = k00 * b0 + k01 * b1;
+            T[i][1] = k10 * b0 + k11 * b1;
+            T[i][2] = k22 * b2;
+#pragma unroll
+            for (int c = 0; c < 3; c++) A[i][c] = S.G[9 * fa + 3 * i + c];
+          }
           const double cnt = (double)(NH - ja);
-          {
-            double A[3][3], B[3][3];
-#pragma unroll
-            for (int i = 0; i < 3; i++)
-#pragma unroll
-              for (int c = 0; c < 3; c++) {
-                A[i][c] = S.G[9 * fa + 3 * i + c];
-                B[i][c] = dt2 * cnt * P.Lw[6 + c] * S.G[9 * fb + 3 * i + c];
-              }
-#pragma unroll
-            for (int i = 0; i < 3; i++)
-#pragma unroll
-              for (int l = 0; l < 3; l++) acc[i][l] = A[i][0] * B[l][0] + A[i][1] * B[l][1] + A[i][2] * B[l][2];
-          }
-          for (int k = ja + 1; k < NH; k++) {
-            double A[3][3], B[3][3];
-#pragma unroll
-            for (int i = 0; i < 3; i++)
-#pragma unroll
-              for (int c = 0; c < 3; c++) {
-                A[i][c] = Ta[(i * NH + k) * 3 + c];
-                B[i][c] = Tb[(i * NH + k) * 3 + c];
-              }
-#pragma unroll
-            for (int i = 0; i < 3; i++)
-#pragma unroll
-              for (int l = 0; l < 3; l++)
-                acc[i][l] = fma(A[i][0], B[l][0], fma(A[i][1], B[l][1], fma(A[i][2], B[l][2], acc[i][l])));
-          }
           const double s1 = 0.5 * (cnt - 1.0) * cnt, s2 = (cnt - 1.0) * cnt * (2.0 * cnt - 1.0) * (1.0 / 6.0);
           const double lin = (dt * im) * (dt * im) * cnt, quad = (dt2 * im) * (dt2 * im) * (s2 + (double)(ja - jb) * s1);
 #pragma unroll
-          for (int i = 0; i < 3; i++) {
-            acc[i][i] += P.Lw[9 + i] * lin + P.Lw[3 + i] * quad;
-            if (fa == fb) acc[i][i] += P.alpha;
+          for (int i = 0; i < 3; i++)
 #pragma unroll
-            for (int l = 0; l < 3; l++) S.M[(3 * fa + i) * LD + 3 * fb + l] = 2.0 * acc[i][l];  // diagonal blocks: all 9
-          }
+            for (int l = 0; l < 3; l++) {
+              double v = A[i][0] * T[l][0] + A[i][1] * T[l][1] + A[i][2] * T[l][2];
+              if (i == l) {
+                v += P.Lw[9 + i] * lin + P.Lw[3 + i] * quad;
+                if (fa == fb) v += P.alpha;
+              }
+              S.M[(3 * fa + i) * LD + 3 * fb + l] = 2.0 * v;  // diagonal blocks: all 9
+            }
         }
       }
+      MPC_TICK(20);
       if (tid < n) {
         const int a = tid, fa = a / 3, ca = a - 3 * fa, ja = S.sfk[fa];
-        const double* Ta = &ThW[3 * NH * a];
         const double* ga = &S.G[3 * a];
-        double t = 0.0;
-        for (int k = ja; k < NH; k++) {
-          const double* e = &S.E[12 * k];
-          t += Ta[3 * k] * e[0] + Ta[3 * k + 1] * e[1] + Ta[3 * k + 2] * e[2];
-          t += (double)(k - ja) * dt2 * im * e[3 + ca];
-          t += dt * (ga[0] * e[6] + ga[1] * e[7] + ga[2] * e[8]);
-          t += dt * im * e[9 + ca];
-        }
-        S.w[a] = 2.0 * t;
+        const double* qj = &Qv[12 * ja];
+        S.w[a] = 2.0 * (ga[0] * qj[0] + ga[1] * qj[1] + ga[2] * qj[2] + qj[3 + ca] + qj[6 + ca]);
       }
       __syncthreads();
 

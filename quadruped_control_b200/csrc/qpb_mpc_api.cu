@@ -197,10 +197,10 @@ int qpb_mpc_batch_host(qpb_mpc_handle* h, int64_t n, const qpb_mpc_rec* h_recs, 
 
 #ifdef QPB_MPC_PROFILE
 // developer build only: read and reset the per-phase cycle counters (not declared in qpb200.h)
-int qpb_mpc_debug_profile(unsigned long long out[16]) {
+int qpb_mpc_debug_profile(unsigned long long out[24]) {
   MPC_CUDA(cudaDeviceSynchronize());
-  MPC_CUDA(cudaMemcpyFromSymbol(out, qpbmpc::g_mpc_prof, 16 * sizeof(unsigned long long)));
-  unsigned long long zero[16] = {};
+  MPC_CUDA(cudaMemcpyFromSymbol(out, qpbmpc::g_mpc_prof, 24 * sizeof(unsigned long long)));
+  unsigned long long zero[24] = {};
   MPC_CUDA(cudaMemcpyToSymbol(qpbmpc::g_mpc_prof, zero, sizeof(zero)));
   return QPB_SUCCESS;
 }

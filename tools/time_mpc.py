@@ -24,7 +24,7 @@ prof = hasattr(L, "qpb_mpc_debug_profile")
 for _ in range(2):
     s.solve_packed(d_in, d_out, n, stream=st)
 torch.cuda.synchronize()
-buf = (ctypes.c_ulonglong * 16)()
+buf = (ctypes.c_ulonglong * 24)()
 if prof:
     L.qpb_mpc_debug_profile(buf)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -42,7 +42,7 @@ if prof:
     L.qpb_mpc_debug_profile(buf)
     v = np.array(list(buf), dtype=np.float64)
     cnt = max(v[5], 1.0)
-    names = {0: "assembly", 1: "sweep", 2: "start", 3: "loop-rest", 4: "io", 6: "select", 8: "nt", 9: "r", 10: "w", 11: "zt",
+    names = {16: "load", 17: "A", 18: "B", 19: "C", 20: "D", 0: "grad", 1: "sweep", 2: "start", 3: "loop-rest", 4: "io", 6: "select", 8: "nt", 9: "r", 10: "w", 11: "zt",
              12: "scalars", 13: "step", 14: "add", 15: "drop"}
     tot = sum(v[i] for i in names)
     print("cycles per QP: " + ", ".join(f"{nm} {v[i] / cnt:.0f} ({100 * v[i] / tot:.0f}%)" for i, nm in names.items()) + f"; total {tot / cnt:.0f}")
