@@ -154,12 +154,33 @@ int qpb_tick_batch_packed(qpb_handle* h, int64_t n, const qpb_state_rec* d_state
 int qpb_tick_batch_host(qpb_handle* h, int64_t n, const qpb_state_rec* h_states, const qpb_swing_rec* h_swing,
                         qpb_out_rec* h_out);
 
-/* Pinned host memory for qpb_control_batch_host callers. */
+/* Pinned host memory for qpb_control_batch_host callers (portable: every device can read and write it). */
 int qpb_host_alloc(void** ptr, size_t bytes);
 int qpb_host_free(void* ptr);
 
 /* Number of CUDA kernels this handle has launched so far (for the benchmark's gpu_launches). */
 int64_t qpb_launch_count(const qpb_handle* h);
+
+/* ---- Single-process multi-GPU form of the host-buffer calls ---------------------------------------
+ * Every QP is independent: the batch is cut into contiguous shards, shard r = records [lo_r, hi_r) with remainders
+ * going to the lowest shards (the same ranges the one-process-per-GPU path uses), each solved on its own device by a
+ * persistent host thread through that device's qpb_handle.  No data-path collective, no launcher.  The reference runs
+ * one BalanceController per process (commander_node.cpp:337); this is what a bridge stepping a fleet on an 8-GPU box
+ * binds instead of eight of them. */
+typedef struct qpb_multi_handle qpb_multi_handle;
+int qpb_device_count(int* count);
+/* devices == NULL: one shard per visible device; otherwise devices[0..num_devices) (a device may be listed twice). */
+int qpb_multi_create(const qpb_params* params, const int* devices, int num_devices, qpb_multi_handle** out);
+int qpb_multi_destroy(qpb_multi_handle* m);
+int qpb_multi_num_shards(const qpb_multi_handle* m);
+int qpb_multi_shard_range(int64_t n, int shard, int num_shards, int64_t* lo, int64_t* hi);
+int qpb_multi_set_joint_gains(qpb_multi_handle* m, const qpb_joint_gains* gains);
+/* qpb_control_batch_host / qpb_tick_batch_host over all shards; return when h_out is complete.  On failure the
+ * first failing shard's code is returned and qpb_last_error() names the shard and device. */
+int qpb_multi_control_batch_host(qpb_multi_handle* m, int64_t n, const qpb_state_rec* h_states, qpb_out_rec* h_out);
+int qpb_multi_tick_batch_host(qpb_multi_handle* m, int64_t n, const qpb_state_rec* h_states, const qpb_swing_rec* h_swing,
+                              qpb_out_rec* h_out);
+int64_t qpb_multi_launch_count(const qpb_multi_handle* m);
 
 /* ---- The caller code either side of the tick -----------------------------------------
  * Foothold planner + swing-foot trajectory: FootPlanner::singleFoot (foot_planner.cpp:76-104) when a leg switches

@@ -605,7 +605,7 @@ int qpb_torque_cmd_batch(qpb_handle* h, int64_t n, const qpb_state_rec* d_states
 
 int qpb_host_alloc(void** ptr, size_t bytes) {
   if (!ptr) return fail(QPB_ERR_INVALID_ARG, "qpb_host_alloc: null pointer");
-  QPB_CUDA(cudaHostAlloc(ptr, bytes, cudaHostAllocDefault));
+  QPB_CUDA(cudaHostAlloc(ptr, bytes, cudaHostAllocPortable | cudaHostAllocMapped));  // visible to every device (qpb_multi_*)
   return QPB_SUCCESS;
 }
 

@@ -45,6 +45,15 @@ EXPORTS = (
     "qpb_mpc_batch_packed",
     "qpb_mpc_batch_host",
     "qpb_mpc_launch_count",
+    "qpb_device_count",
+    "qpb_multi_create",
+    "qpb_multi_destroy",
+    "qpb_multi_num_shards",
+    "qpb_multi_shard_range",
+    "qpb_multi_set_joint_gains",
+    "qpb_multi_control_batch_host",
+    "qpb_multi_tick_batch_host",
+    "qpb_multi_launch_count",
 )
 
 _lib = None
@@ -94,6 +103,16 @@ def load():
     L.qpb_mpc_batch_host.argtypes = [vp, i64, vp, vp]
     L.qpb_mpc_launch_count.argtypes = [vp]
     L.qpb_mpc_launch_count.restype = i64
+    L.qpb_device_count.argtypes = [ctypes.POINTER(ctypes.c_int)]
+    L.qpb_multi_create.argtypes = [ctypes.POINTER(Params), ctypes.POINTER(ctypes.c_int), ctypes.c_int, ctypes.POINTER(vp)]
+    L.qpb_multi_destroy.argtypes = [vp]
+    L.qpb_multi_num_shards.argtypes = [vp]
+    L.qpb_multi_shard_range.argtypes = [i64, ctypes.c_int, ctypes.c_int, ctypes.POINTER(i64), ctypes.POINTER(i64)]
+    L.qpb_multi_set_joint_gains.argtypes = [vp, ctypes.POINTER(JointGains)]
+    L.qpb_multi_control_batch_host.argtypes = [vp, i64, vp, vp]
+    L.qpb_multi_tick_batch_host.argtypes = [vp, i64, vp, vp, vp]
+    L.qpb_multi_launch_count.argtypes = [vp]
+    L.qpb_multi_launch_count.restype = i64
     for name in EXPORTS:
         getattr(L, name)
     _lib = L
@@ -139,6 +158,72 @@ class PinnedBuffer:
             self.array = None
             load().qpb_host_free(self.ptr)
             self.ptr = None
+
+
+def multi_shard_range(n, shard, num_shards):
+    """[lo, hi) of ``shard`` as libqpb200's single-process multi-GPU calls cut the batch (no device needed)."""
+    lo, hi = ctypes.c_int64(), ctypes.c_int64()
+    _check(load().qpb_multi_shard_range(int(n), int(shard), int(num_shards), ctypes.byref(lo), ctypes.byref(hi)),
+           "qpb_multi_shard_range")
+    return lo.value, hi.value
+
+
+class MultiBalanceSolver:
+    """Owns one ``qpb_multi_handle``: the host-buffer calls sharded over several devices inside one process
+    (one persistent host thread and one qpb_handle per device, no data-path collective)."""
+
+    def __init__(self, params: Params = None, devices=None):
+        L = load()
+        self.params = params.copy() if params is not None else default_params()
+        h = ctypes.c_void_p()
+        if devices is None:
+            arr, nd = None, 0
+        else:
+            nd = len(devices)
+            arr = (ctypes.c_int * nd)(*[int(d) for d in devices])
+        _check(L.qpb_multi_create(ctypes.byref(self.params), arr, nd, ctypes.byref(h)), "qpb_multi_create")
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load().qpb_multi_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def num_shards(self):
+        return int(load().qpb_multi_num_shards(self._h))
+
+    @property
+    def launches(self):
+        return int(load().qpb_multi_launch_count(self._h))
+
+    def set_joint_gains(self, gains: JointGains):
+        _check(load().qpb_multi_set_joint_gains(self._h, ctypes.byref(gains)), "qpb_multi_set_joint_gains")
+
+    def control_host(self, states: np.ndarray, out: np.ndarray = None):
+        states = np.ascontiguousarray(states)
+        assert states.dtype == STATE_DTYPE
+        if out is None:
+            out = np.empty(states.shape[0], dtype=OUT_DTYPE)
+        assert out.dtype == OUT_DTYPE and out.shape[0] == states.shape[0] and out.flags.c_contiguous
+        _check(load().qpb_multi_control_batch_host(self._h, states.shape[0], states.ctypes.data, out.ctypes.data),
+               "qpb_multi_control_batch_host")
+        return out
+
+    def tick_host(self, states: np.ndarray, swing: np.ndarray, out: np.ndarray = None):
+        states, swing = np.ascontiguousarray(states), np.ascontiguousarray(swing)
+        assert states.dtype == STATE_DTYPE and swing.dtype == SWING_DTYPE and len(states) == len(swing)
+        if out is None:
+            out = np.empty(states.shape[0], dtype=OUT_DTYPE)
+        _check(load().qpb_multi_tick_batch_host(self._h, states.shape[0], states.ctypes.data, swing.ctypes.data,
+                                                out.ctypes.data), "qpb_multi_tick_batch_host")
+        return out
 
 
 class BalanceSolver:

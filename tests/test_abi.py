@@ -117,3 +117,34 @@ def test_cpp_shim_compiles_against_the_abi(built):
 
     exe = g.build_cpp_shim_check()
     assert exe and os.path.exists(exe)
+
+
+def test_multi_shard_ranges_match_the_torchrun_sharding(built):
+    """The single-process multi-GPU calls (qpb_multi_*) cut the batch exactly as sharding.shard_range does."""
+    from quadruped_control_b200.sharding import shard_range
+
+    for n in (0, 1, 7, 8, 1001, 65536, 8388608 + 3):
+        for g in (1, 2, 3, 8):
+            got = [lib.multi_shard_range(n, r, g) for r in range(g)]
+            assert got == [shard_range(n, r, g) for r in range(g)]
+            assert got[0][0] == 0 and got[-1][1] == n and all(got[r][1] == got[r + 1][0] for r in range(g - 1))
+    L = lib.load()
+    lo, hi = ctypes.c_int64(), ctypes.c_int64()
+    assert L.qpb_multi_shard_range(10, 2, 2, ctypes.byref(lo), ctypes.byref(hi)) == -1
+    assert L.qpb_multi_shard_range(-1, 0, 2, ctypes.byref(lo), ctypes.byref(hi)) == -1
+
+
+def test_multi_create_fails_loudly_without_a_gpu(built):
+    import torch
+
+    L = lib.load()
+    assert L.qpb_multi_create(None, None, 0, None) == -1
+    assert L.qpb_multi_destroy(None) == 0 and L.qpb_multi_num_shards(None) == 0 and L.qpb_multi_launch_count(None) == 0
+    assert L.qpb_multi_control_batch_host(None, 1, None, None) == -1
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: covered by the -m gpu tests")
+    with pytest.raises(lib.QpbError) as ei:
+        lib.MultiBalanceSolver(default_params(0.6))
+    assert "(-3)" in str(ei.value)
+    with pytest.raises(lib.QpbError):
+        lib.MultiBalanceSolver(default_params(0.6), devices=[0, 0])

@@ -380,3 +380,37 @@ def test_randomised_parameter_sets(built):
     assert res.returncode == 0, res.stderr[-2000:]
     last = res.stdout.strip().splitlines()[-1]
     assert "failures 0" in last, res.stdout[-3000:]
+
+
+def test_single_process_multi_device_sharding(solver06, params06):
+    """qpb_multi_*: the host-buffer calls sharded over devices inside one process.  Every visible device
+    plus a second shard on device 0, so the shard bookkeeping is exercised even on a one-GPU box; results must be
+    byte-identical to the single-handle call (same kernels, same records)."""
+    torch = _torch()
+    devices = list(range(torch.cuda.device_count())) + [0]
+    multi = lib.MultiBalanceSolver(params06, devices=devices)
+    assert multi.num_shards == len(devices)
+    assert len(multi.control_host(np.zeros(0, dtype=STATE_DTYPE))) == 0
+    for n in (1, 2, 5, 1001, 50001):  # fewer records than shards, ragged remainders, beyond the latency path
+        S = states.generate_states(n, 77 + n, masks="mixed")
+        assert multi.control_host(S).tobytes() == solver06.control_host(S).tobytes()
+    n = 40000
+    S = states.generate_states(n, 9)
+    pin_in, pin_out = lib.PinnedBuffer(n, STATE_DTYPE), lib.PinnedBuffer(n, OUT_DTYPE)
+    pin_in.array[:] = S
+    multi.control_host(pin_in.array, pin_out.array)  # pinned: each shard's kernel reads its slice over PCIe
+    assert pin_out.array.tobytes() == solver06.control_host(S).tobytes()
+    ref = oracle.control_batch(params06, S[:2048], NCPU)
+    _compare(pin_out.array[:2048], ref)
+    pin_in.free()
+    pin_out.free()
+    # whole tick through the sharded call
+    Sm = states.generate_states(3001, 11, masks="mixed")
+    sw = states.generate_swing(Sm, 12)
+    assert multi.tick_host(Sm, sw).tobytes() == solver06.tick_host(Sm, sw).tobytes()
+    assert multi.launches > 0
+    all_dev = lib.MultiBalanceSolver(params06)  # devices = NULL: one shard per visible device
+    assert all_dev.num_shards == torch.cuda.device_count()
+    assert all_dev.control_host(Sm).tobytes() == solver06.control_host(Sm).tobytes()
+    all_dev.close()
+    multi.close()
