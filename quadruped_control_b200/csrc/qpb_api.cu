@@ -581,9 +581,17 @@ int qpb_adapt_inputs_batch(qpb_handle* h, int64_t n, const qpb_com_msg* d_com, c
   if (n == 0) return QPB_SUCCESS;
   DeviceGuard guard(h->device);
   if (!guard.ok) return fail(QPB_ERR_CUDA, "cudaSetDevice failed");
-  const int threads = 128;
-  qpb::adapt_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, static_cast<cudaStream_t>(stream)>>>(
-      h->d_params, d_com, d_joints, d_states, d_swing, n);
+  const int threads = qpb::kXformThreads;
+  const unsigned grid = (unsigned)((n + threads - 1) / threads);
+  // 32-byte-aligned arrays (any cudaMalloc'd buffer): 256-bit loads/stores; otherwise the 16-byte ABI minimum
+  const bool v256 = ((reinterpret_cast<uintptr_t>(d_com) | reinterpret_cast<uintptr_t>(d_joints) |
+                      reinterpret_cast<uintptr_t>(d_states) | reinterpret_cast<uintptr_t>(d_swing)) & 31u) == 0;
+  if ((reinterpret_cast<uintptr_t>(d_states) | reinterpret_cast<uintptr_t>(d_swing) | reinterpret_cast<uintptr_t>(d_joints)) & 15u)
+    return fail(QPB_ERR_INVALID_ARG, "qpb_adapt_inputs_batch: records must be 16-byte aligned");
+  if (v256)
+    qpb::adapt_kernel<true><<<grid, threads, 0, static_cast<cudaStream_t>(stream)>>>(h->d_params, d_com, d_joints, d_states, d_swing, n);
+  else
+    qpb::adapt_kernel<false><<<grid, threads, 0, static_cast<cudaStream_t>(stream)>>>(h->d_params, d_com, d_joints, d_states, d_swing, n);
   h->launches.fetch_add(1, std::memory_order_relaxed);
   QPB_CUDA(cudaGetLastError());
   return QPB_SUCCESS;
@@ -595,9 +603,15 @@ int qpb_torque_cmd_batch(qpb_handle* h, int64_t n, const qpb_state_rec* d_states
   if (n == 0) return QPB_SUCCESS;
   DeviceGuard guard(h->device);
   if (!guard.ok) return fail(QPB_ERR_CUDA, "cudaSetDevice failed");
-  const int threads = 128;
-  qpb::torque_cmd_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, static_cast<cudaStream_t>(stream)>>>(
-      h->d_params, d_states, d_out, d_cmd, n);
+  const int threads = qpb::kXformThreads;
+  const unsigned grid = (unsigned)((n + threads - 1) / threads);
+  if ((reinterpret_cast<uintptr_t>(d_states) | reinterpret_cast<uintptr_t>(d_out) | reinterpret_cast<uintptr_t>(d_cmd)) & 15u)
+    return fail(QPB_ERR_INVALID_ARG, "qpb_torque_cmd_batch: records must be 16-byte aligned");
+  const bool v256 = ((reinterpret_cast<uintptr_t>(d_out) | reinterpret_cast<uintptr_t>(d_cmd)) & 31u) == 0;
+  if (v256)
+    qpb::torque_cmd_kernel<true><<<grid, threads, 0, static_cast<cudaStream_t>(stream)>>>(h->d_params, d_states, d_out, d_cmd, n);
+  else
+    qpb::torque_cmd_kernel<false><<<grid, threads, 0, static_cast<cudaStream_t>(stream)>>>(h->d_params, d_states, d_out, d_cmd, n);
   h->launches.fetch_add(1, std::memory_order_relaxed);
   QPB_CUDA(cudaGetLastError());
   return QPB_SUCCESS;

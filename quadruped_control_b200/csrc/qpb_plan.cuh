@@ -4,7 +4,8 @@
 //                      323-324, 366-388), as the tick uses them at commander_node.cpp:429-461, 482-488
 //   adapt_kernel       stateCallback + jointCallback + forwardKinematics (commander_node.cpp:127-187, 383-384)
 //   torque_cmd_kernel  JointTorqueCmd assembly (commander_node.cpp:517-533)
-// All three are HBM-bound record transforms: one thread per robot, every record touched once.
+// All three are HBM-bound record transforms: one thread per robot, every record touched once; on 32-byte-aligned arrays
+// the adapter and the command kernel move their records with 256-bit accesses (one request per 32-byte sector).
 #pragma once
 
 #include <cuda_runtime.h>
@@ -36,11 +37,18 @@ __global__ void plan_kernel(const qpb_plan_params* __restrict__ PP, const qpb_st
   const uint32_t replan = *reinterpret_cast<const uint32_t*>(pl.replan);
   const double stance_phase = PP->t_stance / (PP->t_swing + PP->t_stance);  // trajectory.cpp:300-307
   const double slope = 1.0 / (1.0 - stance_phase), y0 = 1.0 - slope;
-  double R[9], x[3];
+  // swing legs flagged for re-planning (one bit per byte lane); the pose is only needed for those
+  const uint32_t sw_b = ~(contact | (contact >> 1) | (contact >> 2) | (contact >> 3) | (contact >> 4) | (contact >> 5) |
+                          (contact >> 6) | (contact >> 7)) & 0x01010101u;
+  const uint32_t rp_b = (replan | (replan >> 1) | (replan >> 2) | (replan >> 3) | (replan >> 4) | (replan >> 5) |
+                         (replan >> 6) | (replan >> 7)) & 0x01010101u;
+  double R[9] = { 0, 0, 0, 0, 0, 0, 0, 0, 0 }, x[3] = { 0, 0, 0 };
+  if (sw_b & rp_b) {
 #pragma unroll
-  for (int k = 0; k < 9; k++) R[k] = s.Rwb[k];
+    for (int k = 0; k < 9; k++) R[k] = s.Rwb[k];
 #pragma unroll
-  for (int k = 0; k < 3; k++) x[k] = s.x[k];
+    for (int k = 0; k < 3; k++) x[k] = s.x[k];
+  }
   uint32_t cleared = replan;
   for (int leg = 0; leg < 4; leg++) {
     if ((contact >> (8 * leg)) & 0xffu) continue;
@@ -93,45 +101,113 @@ __global__ void plan_kernel(const qpb_plan_params* __restrict__ PP, const qpb_st
   if (cleared != replan) *reinterpret_cast<uint32_t*>(pl.replan) = cleared;
 }
 
-// One thread per robot.  The records are 16-byte aligned (ABI contract) and every field group written here starts on a
-// 16-byte boundary, so the state / swing records and the joint message are moved as double2 (half the L2 requests of
-// 8-byte accesses; the kernel is request-bound, not DRAM-bound).
-__global__ void adapt_kernel(const qpb_params* __restrict__ P, const qpb_com_msg* __restrict__ com,
-                             const qpb_joint_msg* __restrict__ joints, qpb_state_rec* __restrict__ states,
-                             qpb_swing_rec* __restrict__ swing, int64_t n) {
+// ---- 256-bit global accesses (sm_100a: LDG.E.256 / STG.E.256) ----------------------------------------------------
+// These record transforms are bound by the number of 32-byte sectors their requests touch, not by DRAM bytes: a
+// thread that walks its own record with 8- or 16-byte accesses touches every sector two to four times.  With
+// 32-byte accesses on 32-byte-aligned fields each sector is touched once.
+struct d4 { double a, b, c, d; };
+__device__ __forceinline__ d4 ldg256(const void* p) {
+  d4 v;
+  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.a), "=d"(v.b), "=d"(v.c), "=d"(v.d) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void stg256(void* p, double a, double b, double c, double d) {
+  asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+
+constexpr int kXformThreads = 128;  // CTA size of adapt_kernel / torque_cmd_kernel (4 warps, one 32-robot tile each)
+
+// One thread per robot.  V256 (all four array bases 32-byte aligned; qpb_adapt_inputs_batch checks): the 104-byte
+// CoM messages of a warp's 32 robots are fetched as one contiguous 3 328-byte run of 32-byte chunks and handed to
+// their owners through shared memory (stride 13 doubles: conflict-free), the joint message is six 32-byte loads,
+// and the record fields are written with 32-byte stores wherever a field group covers a whole sector: 10 loads and
+// 16 stores per robot instead of 25 and 28.  !V256: records only 16-byte aligned (the ABI minimum), double2 accesses.
+template <bool V256>
+__global__ void __launch_bounds__(kXformThreads)
+adapt_kernel(const qpb_params* __restrict__ P, const qpb_com_msg* __restrict__ com,
+             const qpb_joint_msg* __restrict__ joints, qpb_state_rec* __restrict__ states,
+             qpb_swing_rec* __restrict__ swing, int64_t n) {
+  __shared__ __align__(16) double com_s[V256 ? (kXformThreads / 32) * 32 * 13 : 2];
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const qpb_com_msg& c = com[i];  // 104-byte stride: 8-byte loads
-  double2* sv = reinterpret_cast<double2*>(&states[i]);
+  double cm[13];  // position[3] orientation[4] linear[3] angular[3]
+  bool staged = false;
+  if (V256) {
+    const int lane = threadIdx.x & 31;
+    const int64_t tile0 = i - lane;
+    if (tile0 + 32 <= n) {  // full tile: cooperative fetch
+      double* cs = com_s + (threadIdx.x >> 5) * (32 * 13);
+      const char* src = reinterpret_cast<const char*>(com + tile0);
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const int c = lane + 32 * k;
+        if (c < 104) {
+          const d4 v = ldg256(src + 32 * c);
+          reinterpret_cast<double2*>(cs)[2 * c] = make_double2(v.a, v.b);
+          reinterpret_cast<double2*>(cs)[2 * c + 1] = make_double2(v.c, v.d);
+        }
+      }
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 13; j++) cm[j] = cs[13 * lane + j];
+      staged = true;
+    }
+  }
+  if (!staged) {
+    if (i >= n) return;
+    const double* c = reinterpret_cast<const double*>(com + i);  // 104-byte stride: 8-byte loads
+#pragma unroll
+    for (int j = 0; j < 13; j++) cm[j] = __ldg(c + j);
+  }
+  double* sp = reinterpret_cast<double*>(&states[i]);
+  double2* sv = reinterpret_cast<double2*>(sp);
   // stateCallback (commander_node.cpp:167-187): Quaternion(w, x, y, z).rotation().matrix(), i.e. Drake's
   // RotationMatrix(Eigen::Quaterniond): the 2/|q|^2 form, no normalisation of q
-  const double x = c.orientation[0], y = c.orientation[1], z = c.orientation[2], w = c.orientation[3];
+  const double x = cm[3], y = cm[4], z = cm[5], w = cm[6];
   const double two = 2.0 / (w * w + x * x + y * y + z * z);
   const double sx = two * x, sy = two * y, sz = two * z;
   const double swx = sx * w, swy = sy * w, swz = sz * w, sxx = sx * x, sxy = sy * x, sxz = sz * x, syy = sy * y, syz = sz * y,
                szz = sz * z;
-  // Rwb = doubles 0..8 of the record
-  sv[0] = make_double2(1.0 - syy - szz, sxy - swz);
-  sv[1] = make_double2(sxz + swy, sxy + swz);
-  sv[2] = make_double2(1.0 - sxx - szz, syz - swx);
-  sv[3] = make_double2(sxz - swy, syz + swx);
-  states[i].Rwb[8] = 1.0 - sxx - syy;
-  // x, xdot, w = doubles 18..26
-  sv[9] = make_double2(c.position[0], c.position[1]);
-  sv[10] = make_double2(c.position[2], c.linear[0]);
-  sv[11] = make_double2(c.linear[1], c.linear[2]);
-  sv[12] = make_double2(c.angular[0], c.angular[1]);
-  states[i].w[2] = c.angular[2];
+  // Rwb = doubles 0..8 of the record; x, xdot, w = doubles 18..26
+  if (V256) {
+    stg256(sp, 1.0 - syy - szz, sxy - swz, sxz + swy, sxy + swz);
+    stg256(sp + 4, 1.0 - sxx - szz, syz - swx, sxz - swy, syz + swx);
+    sp[8] = 1.0 - sxx - syy;
+    sv[9] = make_double2(cm[0], cm[1]);
+    stg256(sp + 20, cm[2], cm[7], cm[8], cm[9]);
+    sv[12] = make_double2(cm[10], cm[11]);
+    sp[26] = cm[12];
+  } else {
+    sv[0] = make_double2(1.0 - syy - szz, sxy - swz);
+    sv[1] = make_double2(sxz + swy, sxy + swz);
+    sv[2] = make_double2(1.0 - sxx - szz, syz - swx);
+    sv[3] = make_double2(sxz - swy, syz + swx);
+    sp[8] = 1.0 - sxx - syy;
+    sv[9] = make_double2(cm[0], cm[1]);
+    sv[10] = make_double2(cm[2], cm[7]);
+    sv[11] = make_double2(cm[8], cm[9]);
+    sv[12] = make_double2(cm[10], cm[11]);
+    sp[26] = cm[12];
+  }
   // jointCallback (commander_node.cpp:127-165): message index 4 * joint + leg; forwardKinematics (kinematics.cpp:81-103)
-  const double2* jv = reinterpret_cast<const double2*>(&joints[i]);
   double pos[12], vel[12];
+  if (V256) {
+    const double* jp = reinterpret_cast<const double*>(&joints[i]);
 #pragma unroll
-  for (int k = 0; k < 6; k++) {
-    const double2 a = __ldg(jv + k), b = __ldg(jv + 6 + k);
-    pos[2 * k] = a.x;
-    pos[2 * k + 1] = a.y;
-    vel[2 * k] = b.x;
-    vel[2 * k + 1] = b.y;
+    for (int k = 0; k < 3; k++) {
+      const d4 a = ldg256(jp + 4 * k), b = ldg256(jp + 12 + 4 * k);
+      pos[4 * k] = a.a; pos[4 * k + 1] = a.b; pos[4 * k + 2] = a.c; pos[4 * k + 3] = a.d;
+      vel[4 * k] = b.a; vel[4 * k + 1] = b.b; vel[4 * k + 2] = b.c; vel[4 * k + 3] = b.d;
+    }
+  } else {
+    const double2* jv = reinterpret_cast<const double2*>(&joints[i]);
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+      const double2 a = __ldg(jv + k), b = __ldg(jv + 6 + k);
+      pos[2 * k] = a.x;
+      pos[2 * k + 1] = a.y;
+      vel[2 * k] = b.x;
+      vel[2 * k + 1] = b.y;
+    }
   }
   double q[12], feet[12], qd[12];
 #pragma unroll
@@ -153,45 +229,96 @@ __global__ void adapt_kernel(const qpb_params* __restrict__ P, const qpb_com_msg
     feet[3 * leg + 2] = l1 * s1 + l2 * c1 * c2 + l3 * c1 * c23 + P->hip_offset[3 * leg + 2];
   }
   // feet = doubles 36..47, q = doubles 48..59 of the state record; qdot = doubles 24..35 of the swing record
-  double2* qv = reinterpret_cast<double2*>(&swing[i]) + 12;
+  if (V256) {
+    double* wp = reinterpret_cast<double*>(&swing[i]) + 24;
 #pragma unroll
-  for (int k = 0; k < 6; k++) {
-    sv[18 + k] = make_double2(feet[2 * k], feet[2 * k + 1]);
-    sv[24 + k] = make_double2(q[2 * k], q[2 * k + 1]);
-    qv[k] = make_double2(qd[2 * k], qd[2 * k + 1]);
+    for (int k = 0; k < 3; k++) {
+      stg256(sp + 36 + 4 * k, feet[4 * k], feet[4 * k + 1], feet[4 * k + 2], feet[4 * k + 3]);
+      stg256(sp + 48 + 4 * k, q[4 * k], q[4 * k + 1], q[4 * k + 2], q[4 * k + 3]);
+      stg256(wp + 4 * k, qd[4 * k], qd[4 * k + 1], qd[4 * k + 2], qd[4 * k + 3]);
+    }
+  } else {
+    double2* qv = reinterpret_cast<double2*>(&swing[i]) + 12;
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+      sv[18 + k] = make_double2(feet[2 * k], feet[2 * k + 1]);
+      sv[24 + k] = make_double2(q[2 * k], q[2 * k + 1]);
+      qv[k] = make_double2(qd[2 * k], qd[2 * k + 1]);
+    }
   }
 }
 
-__global__ void torque_cmd_kernel(const qpb_params* __restrict__ P, const qpb_state_rec* __restrict__ states,
-                                  const qpb_out_rec* __restrict__ out, qpb_torque_cmd* __restrict__ cmd, int64_t n) {
+// One thread per robot; the 112-byte commands of a warp's 32 robots are assembled in shared memory (compaction of
+// the present legs is a dynamic shared-memory index, no local memory) and, for a full tile with 32-byte-aligned
+// arrays (V256), leave as one contiguous 3 584-byte run of 32-byte stores; the torques arrive as three 32-byte loads.
+template <bool V256>
+__global__ void __launch_bounds__(kXformThreads)
+torque_cmd_kernel(const qpb_params* __restrict__ P, const qpb_state_rec* __restrict__ states,
+                  const qpb_out_rec* __restrict__ out, qpb_torque_cmd* __restrict__ cmd, int64_t n) {
+  static_assert(sizeof(qpb_torque_cmd) == 112, "qpb_torque_cmd layout");
+  __shared__ __align__(16) double cmd_s[(kXformThreads / 32) * 32 * 14];
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const uint32_t contact = *reinterpret_cast<const uint32_t*>(states[i].contact);
-  const qpb_out_rec& o = out[i];
-  const bool qp_ok = o.status == QPB_OK;
-  qpb_torque_cmd c;
-  int cnt = 0;
+  const int lane = threadIdx.x & 31;
+  const int64_t tile0 = i - lane;
+  if (tile0 >= n) return;  // the whole warp leaves together
+  double* cs = cmd_s + (threadIdx.x >> 5) * (32 * 14);
+  if (i < n) {
+    const uint32_t contact = *reinterpret_cast<const uint32_t*>(states[i].contact);
+    const bool qp_ok = out[i].status == QPB_OK;
+    double tau[12];
+    if (V256) {
+      const double* tp = out[i].tau;  // byte 96 of a 256-byte record: 32-byte aligned
 #pragma unroll
-  for (int k = 0; k < 12; k++) {
-    c.torque[k] = 0.0;
-    c.leg[k] = 0;
-  }
-  const int order[4] = { 1, 3, 0, 2 };  // std::map<std::string, vec3> iterates FL, FR, RL, RR (commander_node.cpp:519)
+      for (int k = 0; k < 3; k++) {
+        const d4 v = ldg256(tp + 4 * k);
+        tau[4 * k] = v.a; tau[4 * k + 1] = v.b; tau[4 * k + 2] = v.c; tau[4 * k + 3] = v.d;
+      }
+    } else {
 #pragma unroll
-  for (int k = 0; k < 4; k++) {
-    const int leg = order[k];
-    const bool stance = (contact >> (8 * leg)) & 0xffu;
-    // torque_map = J^T f for the stance legs the QP returned (none when it failed) + the swing-leg torques (:510-515)
-    if (stance && !qp_ok) continue;
+      for (int k = 0; k < 12; k++) tau[k] = out[i].tau[k];
+    }
+    const double lo = P->tau_min, hi = P->tau_max;
+    double* mine = cs + 14 * lane;
+    int cnt = 0;
+    uint32_t sel = 0;  // leg of entry group s in byte s
+    const int order[4] = { 1, 3, 0, 2 };  // std::map<std::string, vec3> iterates FL, FR, RL, RR (commander_node.cpp:519)
 #pragma unroll
-    for (int j = 0; j < 3; j++) {
-      c.torque[cnt] = fmin(fmax(o.tau[3 * leg + j], P->tau_min), P->tau_max);  // arma::clamp, :526
-      c.leg[cnt] = (uint8_t)leg;
+    for (int k = 0; k < 4; k++) {
+      const int leg = order[k];
+      const bool stance = (contact >> (8 * leg)) & 0xffu;
+      // torque_map = J^T f for the stance legs the QP returned (none when it failed) + the swing-leg torques (:510-515)
+      if (stance && !qp_ok) continue;
+#pragma unroll
+      for (int j = 0; j < 3; j++) mine[3 * cnt + j] = fmin(fmax(tau[3 * leg + j], lo), hi);  // arma::clamp, :526
+      sel |= (uint32_t)leg << (8 * cnt);
       cnt++;
     }
+    for (int e = 3 * cnt; e < 12; e++) mine[e] = 0.0;
+    // leg[12] (entries 3s..3s+2 carry the leg of group s) and count, as the last two 8-byte words of the struct
+    const uint32_t g0 = sel & 0xffu, g1 = (sel >> 8) & 0xffu, g2 = (sel >> 16) & 0xffu, g3 = sel >> 24;
+    const unsigned long long w0 = (unsigned long long)(g0 * 0x010101u) | ((unsigned long long)(g1 * 0x010101u) << 24) |
+                                  ((unsigned long long)(g2 * 0x0101u) << 48);
+    const unsigned long long w1 = (unsigned long long)(g2 | ((g3 * 0x010101u) << 8)) | ((unsigned long long)(uint32_t)(3 * cnt) << 32);  // count = entries
+    mine[12] = __longlong_as_double((long long)w0);
+    mine[13] = __longlong_as_double((long long)w1);
   }
-  c.count = cnt;
-  cmd[i] = c;
+  __syncwarp();
+  if (V256 && tile0 + 32 <= n) {
+    char* dst = reinterpret_cast<char*>(cmd + tile0);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int c = lane + 32 * k;
+      if (c < 112) {
+        const double2 a = reinterpret_cast<const double2*>(cs)[2 * c], b = reinterpret_cast<const double2*>(cs)[2 * c + 1];
+        stg256(dst + 32 * c, a.x, a.y, b.x, b.y);
+      }
+    }
+  } else if (i < n) {
+    double2* dst = reinterpret_cast<double2*>(cmd + i);  // 112-byte stride: 16-byte aligned
+    const double* mine = cs + 14 * lane;
+#pragma unroll
+    for (int k = 0; k < 7; k++) dst[k] = make_double2(mine[2 * k], mine[2 * k + 1]);
+  }
 }
 
 }  // namespace qpb

@@ -259,6 +259,30 @@ def test_adapt_and_torque_cmd_gpu_match_oracle(solver06, params06):
         assert cmd["count"][i] == cnt and np.array_equal(cmd["torque"][i][:cnt], torque[:cnt])
         assert list(cmd["leg"][i][:cnt]) == list(legs[:cnt]) and not cmd["torque"][i][cnt:].any()
 
+    # Arrays that are only 16-byte aligned (the ABI minimum) take the double2 kernels instead of the 256-bit ones:
+    # same bytes out.  A short batch (n < 32) has no full tile: the per-thread tail path of the 256-bit kernels.
+    def shifted(a):
+        raw = torch.zeros(a.nbytes + 16, dtype=torch.uint8, device="cuda")
+        raw[16:].copy_(torch.from_numpy(a.view(np.uint8).reshape(-1)))
+        assert raw[16:].data_ptr() % 32 == 16
+        return raw[16:]
+
+    o_S, o_sw = shifted(S0), shifted(sw0)
+    solver06.adapt_inputs(shifted(com), shifted(js), o_S, o_sw, n, stream=st)
+    o_cmd = shifted(np.zeros(n, dtype=TORQUE_CMD_DTYPE))
+    solver06.torque_cmd(o_S, shifted(out), o_cmd, n, stream=st)
+    torch.cuda.synchronize()
+    assert _host(o_S, STATE_DTYPE).tobytes() == got_S.tobytes() and _host(o_sw, SWING_DTYPE).tobytes() == got_sw.tobytes()
+    assert _host(o_cmd, TORQUE_CMD_DTYPE).tobytes() == cmd.tobytes()
+    m = 19
+    t_S, t_sw = _dev(S0[:m]), _dev(sw0[:m])
+    solver06.adapt_inputs(_dev(com[:m]), _dev(js[:m]), t_S, t_sw, m, stream=st)
+    t_cmd = torch.zeros(m * TORQUE_CMD_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
+    solver06.torque_cmd(t_S, _dev(out[:m]), t_cmd, m, stream=st)
+    torch.cuda.synchronize()
+    assert _host(t_S, STATE_DTYPE).tobytes() == got_S[:m].tobytes() and _host(t_sw, SWING_DTYPE).tobytes() == got_sw[:m].tobytes()
+    assert _host(t_cmd, TORQUE_CMD_DTYPE).tobytes() == cmd[:m].tobytes()
+
 
 @pytest.mark.gpu
 def test_whole_tick_from_messages_gpu(solver06, params06):
