@@ -167,6 +167,9 @@ def run_reference(args):
         return
     kind, fn, desc = _cpu_arm()
     n, seed, masks, profile, wdesc = WORKLOADS[args.workload]
+    if args.profile:
+        profile = args.profile
+        wdesc += f" ({profile} disturbance profile)"
     params = default_params(MU)
     cores = os.cpu_count() or 1
     S_full = states.generate_states(n, seed, profile=profile, masks=masks)
@@ -217,6 +220,9 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
 
     n, seed, masks, profile, desc = WORKLOADS[args.workload]
+    if args.profile:
+        profile = args.profile
+        desc += f" ({profile} disturbance profile)"
     params = default_params(MU)
     solver = lib.BalanceSolver(params, device=local_rank)
 
@@ -293,7 +299,9 @@ def run_ours(args):
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": desc, "qps_per_step_per_gpu": n, "global_batch": world * n, "parallelism": f"batch-sharded x{world}",
                        "l2": f"{n_rot} distinct device batches rotate ({n_rot * n * 768 / 1e6:.0f} MB > 126 MB L2)" if n_rot * n * 768 > 126e6 else "inputs larger than L2",
-                       "iters_mean": float(last["iters"].mean()), "iters_max": int(last["iters"].max())},
+                       "iters_mean": float(last["iters"].mean()), "iters_max": int(last["iters"].max()),
+                       "profile": profile,
+                       "active_rows_hist": active_rows_histogram(host_batches[(args.steps - 1) % n_rot], last, params.mu, params.fzmin, params.fzmax)},
             "max_rel_grf_err_vs_oracle": err, "failed_qps": int(tot_failed),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic_per_launch(args.workload), "peak_source": peak_src,
@@ -315,6 +323,22 @@ def run_ours(args):
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def active_rows_histogram(S, out, mu, fzmin, fzmax):
+    """Active pyramid rows at the returned solution, per QP (SURVEY.md 8d asks for the histogram beside every
+    throughput number): world-frame forces f_w = -R f_b, rows |fx| <= mu fz, |fy| <= mu fz, fzmin <= fz <= fzmax."""
+    R = S["Rwb"].reshape(-1, 3, 3)
+    fb = out["grf_body"].reshape(-1, 4, 3)
+    fw = -np.einsum("nij,nlj->nli", R, fb)
+    stance = S["contact"].astype(bool)
+    fx, fy, fz = fw[..., 0], fw[..., 1], fw[..., 2]
+    tol = 1e-7
+    act = ((mu * fz - np.abs(fx) <= tol * (1 + mu * np.abs(fz))).astype(int) + (mu * fz - np.abs(fy) <= tol * (1 + mu * np.abs(fz))).astype(int)
+           + (fz - fzmin <= tol * (1 + abs(fzmin))).astype(int) + (fzmax - fz <= tol * (1 + abs(fzmax))).astype(int))
+    per_qp = (act * stance).sum(axis=1)[out["status"] == 0]
+    hist = np.bincount(per_qp, minlength=1)
+    return [int(v) for v in hist]
 
 
 def mpc_algorithmic_flops(contact, iters):
@@ -632,6 +656,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=("ours", "reference"), default="ours")
     ap.add_argument("--workload", choices=sorted(WORKLOADS) + ["cfg4", "tick"], default="cfg2")
+    ap.add_argument("--profile", choices=("default", "light", "stress"), default=None,
+                    help="disturbance profile of the synthetic states (SURVEY.md 8d); default: the workload's own")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.workload == "tick":
