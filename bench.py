@@ -52,6 +52,18 @@ def measured_peak_hbm():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def ncu_explanatory(workload):
+    """What actually bounds the kernel, from the committed `ncu --set full` capture (profiles/ncu_summary.json): issue-slot
+    and FP64-pipe utilisation.  Static evidence quoted beside the live HBM figure, not measured by this run."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_summary.json")) as f:
+            d = json.load(f).get(workload, {})
+        keys = ("issue_slots_busy_pct", "fp64_pipe_pct", "dram_pct_of_peak", "source")
+        return {k: d[k] for k in keys if k in d} or None
+    except Exception:
+        return None
+
+
 def ncu_traffic_per_launch(workload):
     """dram bytes per launch from the committed `ncu --set full` summary, if present."""
     try:
@@ -305,6 +317,7 @@ def run_ours(args):
             "max_rel_grf_err_vs_oracle": err, "failed_qps": int(tot_failed),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic_per_launch(args.workload), "peak_source": peak_src,
+                         "ncu": ncu_explanatory(args.workload),
                          "algorithmic_bytes_per_qp": ALGO_BYTES_PER_QP, "kernel": "balance_qp_kernel<PackedIO>" if os.environ.get("QPB_QPS_PER_WARP") == "1" else "balance_qp_kernel16<PackedIO>",
                          "kernel_ms": kernel_ms,
                          "note": "the path is FP64-issue/latency bound, not DRAM bound (DESIGN.md); per-GPU figure"},
