@@ -20,6 +20,8 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# stdout carries exactly one JSON line: whatever NCCL logs (the version banner when NCCL_DEBUG is set) goes to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 from quadruped_control_b200 import ALGO_BYTES_PER_QP, OUT_DTYPE, STATE_DTYPE, default_params, states  # noqa: E402
 from quadruped_control_b200.sharding import reduce_report  # noqa: E402
