@@ -6,6 +6,10 @@
  * rows, swing legs as zero-equality rows) by a textbook Goldfarb-Idnani dual active-set
  * method with QR-updated factors (Goldfarb & Idnani, Math. Programming 27 (1983)).
  * Citations: /root/reference/quadruped_controller/src/quadruped_controller/...
+ *
+ * Pinning (details in qpb_oracle.h and DESIGN.md section 5): every line the reference itself wrote on this path is pinned
+ * to 3e-11 against the reference's own sources compiled in oracle/_ref; the kinematics against the notebook vectors;
+ * the QP SOLVE IS PARITY UNPINNED (qpOASES is not installable here; uniqueness of the minimiser + a KKT certificate stand in).
  */
 #include "qpb_oracle.h"
 
