@@ -1,0 +1,52 @@
+"""CPU tests of the benchmark's host-side helpers (no GPU, no timing): the active-row histogram that every bench line
+carries, the ncu figures quoted beside the roofline, and the shape of the workload table."""
+import json
+import os
+
+import numpy as np
+
+import bench
+import oracle
+from quadruped_control_b200 import default_params, states
+
+NCPU = os.cpu_count() or 1
+
+
+def test_active_rows_histogram_matches_the_oracle_working_sets(built):
+    p = default_params(0.6)
+    S = states.generate_states(1024, 20260103, masks="mixed")
+    out = oracle.control_batch(p, S, NCPU)
+    hist = bench.active_rows_histogram(S, out, p.mu, p.fzmin, p.fzmax)
+    assert sum(hist) == int((out["status"] == 0).sum()) and len(hist) <= 13  # 12 variables: at most 12 independent rows
+    # a stance-pose robot at rest needs no row at all; two-foot stances can never have more than 6 active rows
+    S0 = states.stance_state(default_params(0.8))
+    assert bench.active_rows_histogram(S0, oracle.control_batch(default_params(0.8), S0), 0.8, 10.0, 120.0) == [1]
+    two = S[S["contact"].astype(bool).sum(axis=1) == 2]
+    h2 = bench.active_rows_histogram(two, oracle.control_batch(p, two, NCPU), p.mu, p.fzmin, p.fzmax)
+    assert len(h2) <= 7
+    # light profile: the bimodal histogram SURVEY App. E describes (a large share of unconstrained solutions)
+    L = states.generate_states(1024, 20260102, profile="light")
+    hl = bench.active_rows_histogram(L, oracle.control_batch(p, L, NCPU), p.mu, p.fzmin, p.fzmax)
+    assert hl[0] > 0.2 * sum(hl)
+
+
+def test_ncu_summary_feeds_the_roofline_fields():
+    with open(os.path.join(bench.ROOT, "profiles", "ncu_summary.json")) as f:
+        summary = json.load(f)
+    for wl in ("cfg2", "cfg3", "cfg4"):
+        assert bench.ncu_traffic_per_launch(wl) == summary[wl]["dram_bytes_per_launch"] > 0
+        ex = bench.ncu_explanatory(wl)
+        assert 0 < ex["fp64_pipe_pct"] < 100 and 0 < ex["issue_slots_busy_pct"] < 100
+        assert os.path.exists(os.path.join(bench.ROOT, ex["source"]))
+    assert bench.ncu_traffic_per_launch("no-such-workload") is None and bench.ncu_explanatory("no-such-workload") is None
+    # cfg2 reads exactly its 512-byte records: no re-reads (the first thing the roofline's `traffic` is there to show)
+    assert abs(summary["cfg2"]["dram_read_bytes"] / (65536 * 512) - 1.0) < 0.01
+
+
+def test_workload_table_is_the_baseline_configs():
+    assert bench.WORKLOADS["cfg2"][:3] == (65536, 20260102, "all4")
+    assert bench.WORKLOADS["cfg3"][:3] == (1048576, 20260103, "mixed")
+    assert bench.WORKLOADS["cfg5"][:3] == (1048576, 20260105, "mixed")  # per GPU; 8 388 608 over 8
+    assert bench.MPC_N == 65536 and bench.ALGO_BYTES_PER_QP == 680
+    peak, src = bench.measured_peak_hbm()
+    assert 3000 < peak < 9000 and ("measured" in src or "fallback" in src)
