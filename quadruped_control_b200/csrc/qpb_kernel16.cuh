@@ -95,7 +95,9 @@ balance_qp_kernel16(const qpb_params* __restrict__ gparams, IO io, int64_t n, un
   __syncthreads();
 
   const int lane = threadIdx.x & 31;
-  const int wib = threadIdx.x >> 5;
+  // warp index through a warp-wide reduction: the result lives in a uniform register, so the base address of this
+  // warp's shared-memory block is formed on the uniform datapath instead of being rebuilt from tid in every iteration
+  const int wib = (int)__reduce_max_sync(FULL, threadIdx.x >> 5);
   const int l = lane & 15;         // lane within the half
   const int hb = lane & 16;        // first lane of this half
   HalfSmem& hs = hsm[2 * wib + (lane >> 4)];
