@@ -4,7 +4,7 @@ import csv, subprocess, sys, collections, io
 rep = sys.argv[1]; nq = int(sys.argv[2]) if len(sys.argv) > 2 else 65536
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
-hdr, vals = rows[0], rows[2]
+hdr, units, vals = rows[0], rows[1], rows[2]
 want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "launch__registers_per_thread", "launch__grid_size",
         "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
@@ -16,9 +16,9 @@ want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio", "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio", "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio", "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio"]
-for h, v in zip(hdr, vals):
+for h, u, v in zip(hdr, units, vals):
     if h in want:
-        print(f"{h:95s} {v}")
+        print(f"{h:95s} {v} {u}")  # ncu scales units per metric (Mbyte / Kbyte, us / ms): print them
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
 h = rows[2]; iI = h.index("Instructions Executed"); iS = h.index("# Samples")
