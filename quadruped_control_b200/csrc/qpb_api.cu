@@ -122,8 +122,11 @@ int launch_balance(qpb_handle* h, const IO& io, int64_t n, int ctas_per_sm, cuda
   const uint32_t slot = h->ticket_slot.fetch_add(1, std::memory_order_relaxed) % kTicketSlots;
   unsigned long long* t0 = h->d_tickets + slot;
   unsigned long long* t1 = h->d_tickets + (slot + kTicketSlots / 2) % kTicketSlots;
-  if (per_warp == 2)
-    qpb::balance_qp_kernel16<IO><<<grid, qpb::WARPS_PER_CTA * 32, 0, stream>>>(h->d_params, io, n, t0, t1);
+  if (per_warp == 2) {
+    const qpb_params& p = h->params;
+    const qpb::LoopConsts kc{ p.mu, p.fzmin, p.fzmax, -1e-9 * (1.0 + std::fmax(std::fabs(p.fzmin), std::fabs(p.fzmax))), p.max_iter };
+    qpb::balance_qp_kernel16<IO><<<grid, qpb::WARPS_PER_CTA * 32, 0, stream>>>(h->d_params, io, n, t0, t1, kc);
+  }
   else
     qpb::balance_qp_kernel<IO><<<grid, qpb::WARPS_PER_CTA * 32, 0, stream>>>(h->d_params, io, n, t0, t1);
   h->launches.fetch_add(1, std::memory_order_relaxed);

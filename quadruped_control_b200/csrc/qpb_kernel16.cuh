@@ -12,6 +12,13 @@
 
 namespace qpb {
 
+// scalars of the solver loop, passed by value as a kernel argument (constant bank)
+struct LoopConsts {
+  double mu, fzmin, fzmax;
+  double ntol_z;  // violation tolerance of the fz rows: -1e-9 (1 + max(|fzmin|, |fzmax|))
+  int max_iter;
+};
+
 struct __align__(16) HalfSmem {
   double rec[64];        // staged input record
   double LJ[12 * LS];    // columns of L during factorisation, then rows of J0 = L^-T
@@ -81,7 +88,7 @@ __device__ __forceinline__ void load_rec16(const SplitIO& io, int64_t rec, int l
 template <class IO>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, QPB_MIN_CTAS_PER_SM)
 balance_qp_kernel16(const qpb_params* __restrict__ gparams, IO io, int64_t n, unsigned long long* __restrict__ ticket,
-                    unsigned long long* __restrict__ ticket_to_clear) {
+                    unsigned long long* __restrict__ ticket_to_clear, const LoopConsts kc) {
   __shared__ qpb_params P;
   __shared__ HalfSmem hsm[WARPS_PER_CTA * 2];
 
@@ -111,13 +118,14 @@ balance_qp_kernel16(const qpb_params* __restrict__ gparams, IO io, int64_t n, un
   const int leg = vi / 3, ax = vi - 3 * leg;
   const int zl = 3 * leg + 2;
   const int axp1 = (ax + 1) % 3, axp2 = (ax + 2) % 3;
-  const double mu = P.mu;
+  // kc: the scalars the solver loop uses, passed as kernel arguments: they sit in the constant bank and are used as
+  // instruction operands, costing neither registers nor shared-memory loads
+  const double mu = kc.mu;
   const double kz = ax < 2 ? mu : 0.0;
   const int sgnA = ax < 2 ? (int)0x80000000 : 0;  // sign applied to f in row A (row B uses the opposite)
-  const double bA = ax < 2 ? 0.0 : P.fzmin;
-  const double bB = ax < 2 ? 0.0 : -P.fzmax;
+  const bool lat = ax < 2;  // this lane watches the two pyramid rows of a lateral variable (else the two fz rows)
   // a row is violated when its slack is below -1e-9 (1 + |bound|); one value per lane (the larger bound of its two rows)
-  const double ntol = ax < 2 ? -1e-9 : -1e-9 * (1.0 + fmax(fabs(P.fzmin), fabs(P.fzmax)));
+
   uint32_t pair = gw;
   while (pair < npairs) {
     uint32_t next_ticket = 0;
@@ -306,8 +314,9 @@ balance_qp_kernel16(const qpb_params* __restrict__ gparams, IO io, int64_t n, un
       const double xz = shfl16(x, zl);
       const double base = kz * xz;
       const double xs = __hiloint2double(__double2hiint(x) ^ sgnA, __double2loint(x));  // -x (pyramid rows) or +x (fz rows)
-      const double sA = (base - bA) + xs;
-      const double sB = (base - bB) - xs;
+      const double sA = (base - (lat ? 0.0 : kc.fzmin)) + xs;
+      const double sB = (base + (lat ? 0.0 : kc.fzmax)) - xs;
+      const double ntol = lat ? -1e-9 : kc.ntol_z;
       const uint32_t act2 = (active | ignore) >> ((2 * l) & 31);
       const bool vA = stance && !(act2 & 1u) && (sA < ntol);
       const bool vB = stance && !(act2 & 2u) && (sB < ntol);
@@ -315,7 +324,7 @@ balance_qp_kernel16(const qpb_params* __restrict__ gparams, IO io, int64_t n, un
       const uint32_t keyB = vB ? (((uint32_t)__double2hiint(sB) & ~31u) | (uint32_t)(2 * l + 1)) : 0u;
       const uint32_t kmax = half_max_u32(max(keyA, keyB), hb != 0);
       const bool fresh = p < 0;
-      if (!done && ((fresh && kmax == 0u) || iters >= P.max_iter)) {
+      if (!done && ((fresh && kmax == 0u) || iters >= kc.max_iter)) {
         if (!(fresh && kmax == 0u)) status = QPB_MAX_ITER;
         done = true;
       }
@@ -367,7 +376,7 @@ balance_qp_kernel16(const qpb_params* __restrict__ gparams, IO io, int64_t n, un
       // violated (e.g. fzmin == fzmax).  The row is satisfied to rounding: set it aside instead of failing.
       const bool skip = !done && dep && !has1;
       if (skip) {
-        if (sp < -1e-6 * (1.0 + fmax(fabs(P.fzmin), fabs(P.fzmax)))) {  // not a rounding artefact: give up loudly
+        if (sp < 1e3 * kc.ntol_z) {  // not a rounding artefact: give up loudly
           status = QPB_BAD_INPUT;
           done = true;
         }
