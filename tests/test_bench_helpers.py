@@ -50,3 +50,29 @@ def test_workload_table_is_the_baseline_configs():
     assert bench.MPC_N == 65536 and bench.ALGO_BYTES_PER_QP == 680
     peak, src = bench.measured_peak_hbm()
     assert 3000 < peak < 9000 and ("measured" in src or "fallback" in src)
+
+
+def test_reference_arm_contract_under_torchrun(built):
+    """`bench.py --impl reference` launched as the driver launches it for N > 1: rank 0 alone runs the CPU path and prints
+    exactly one JSON line with the contract's keys; the other rank exits 0 without work.  Needs no GPU."""
+    import socket
+    import subprocess
+    import sys
+
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(bench.ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+           "--warmup", "3"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=bench.ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == bench.METRIC and d["unit"] == "QP/s" and d["higher_is_better"] is True
+    assert d["n_gpus"] == 2 and d["steps"] == 1 and d["warmup"] == 3 and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+    assert d["cpu_baseline"]["value"] == d["value"] == d["e2e"]["value"]
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["gpu_launches"] == 0
+    assert d["config"]["workload"].startswith("cfg2")
