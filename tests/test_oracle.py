@@ -258,3 +258,50 @@ def test_batch_threads_agree(params06):
     a = oracle.control_batch(params06, S, 1)
     b = oracle.control_batch(params06, S, 5)
     assert a.tobytes() == b.tobytes()
+
+
+def test_size_independent_properties_of_the_solution(params06):
+    """Properties the domain offers, used at full size by the GPU tests too: (1) scaling S and W by a common factor scales
+    the objective and leaves the minimiser alone; (2) mirroring the robot left <-> right (y -> -y) mirrors the forces;
+    (3) inactive rows do not matter: tightening fzmax to just above the largest returned fz changes nothing."""
+    S = states.generate_states(256, 515, masks="mixed")
+    ref = oracle.control_batch(params06, S)
+    assert (ref["status"] == 0).all()
+    # (1)
+    p2 = params06.copy()
+    for i in range(36):
+        p2.S[i] = 3.0 * params06.S[i]
+    for i in range(144):
+        p2.W[i] = 3.0 * params06.W[i]
+    out2 = oracle.control_batch(p2, S)
+    assert np.abs(out2["grf_body"] - ref["grf_body"]).max() <= 1e-7 * np.abs(ref["grf_body"]).max()
+    # (2) reflection M = diag(1, -1, 1): vectors v -> M v, rotations R -> M R M, pseudo-vectors (w) -> -M w; legs RL<->RR, FL<->FR
+    M = np.diag([1.0, -1.0, 1.0])
+    perm = [2, 3, 0, 1]
+    Sm = S.copy()
+    for f in ("Rwb", "Rwb_d"):
+        Sm[f] = (M @ S[f].reshape(-1, 3, 3) @ M).reshape(-1, 9)
+    for f in ("x", "xdot", "x_d", "xdot_d"):
+        Sm[f] = S[f] @ M
+    for f in ("w", "w_d"):
+        Sm[f] = -(S[f] @ M)
+    Sm["feet"] = (S["feet"].reshape(-1, 4, 3)[:, perm] @ M).reshape(-1, 12)
+    Sm["contact"] = S["contact"][:, perm]
+    qm = S["q"].reshape(-1, 4, 3)[:, perm].copy()
+    qm[..., 0] *= -1.0  # hip abduction changes sign under the mirror; thigh and calf angles do not
+    Sm["q"] = qm.reshape(-1, 12)
+    outm = oracle.control_batch(params06, Sm)
+    assert (outm["status"] == 0).all()
+    want = (ref["grf_body"].reshape(-1, 4, 3)[:, perm] @ M).reshape(-1, 12)
+    assert np.abs(outm["grf_body"] - want).max() <= 1e-6 * np.abs(want).max()
+    wt = ref["tau"].reshape(-1, 4, 3)[:, perm].copy()
+    wt[..., 0] *= -1.0
+    assert np.abs(outm["tau"] - wt.reshape(-1, 12)).max() <= 1e-6 * np.abs(wt).max()
+    # (3)
+    fz_world = -np.einsum("nij,nlj->nli", S["Rwb"].reshape(-1, 3, 3), ref["grf_body"].reshape(-1, 4, 3))[..., 2]
+    inner = fz_world.max(axis=1) < params06.fzmax - 1.0  # QPs whose fzmax rows are all inactive
+    assert inner.sum() > 20
+    p3 = params06.copy()
+    p3.fzmax = float(fz_world[inner].max()) + 1e-3
+    out3 = oracle.control_batch(p3, np.ascontiguousarray(S[inner]))
+    assert np.abs(out3["grf_body"] - ref["grf_body"][inner]).max() <= 1e-7 * np.abs(ref["grf_body"]).max()
