@@ -74,6 +74,29 @@ def test_mpc_oracle_passes_kkt_certificate(built, mpc_params):
         assert np.abs(out["U"][i][swing]).max(initial=0.0) <= 1e-9
 
 
+def test_mpc_oracle_is_equivariant_under_the_left_right_mirror(built, mpc_params):
+    """The model, the weights and the pyramids are symmetric under y -> -y (roll, yaw, omega_x, omega_z and every y
+    component change sign, legs RL <-> RR and FL <-> FR swap): the mirrored problem must return the mirrored forces.
+    A sign or index slip anywhere in the prediction matrices, the cross products or the leg order breaks this."""
+    import oracle
+
+    R = np.concatenate([generate_mpc(32, 20260104), generate_mpc(16, 11, scale=2.5)])
+    ref = oracle.mpc_batch(mpc_params, R, NCPU)
+    assert (ref["status"] == 0).all()
+    sgn = np.array([-1, 1, -1, 1, -1, 1, -1, 1, -1, 1, -1, 1, 1], dtype=np.float64)  # [roll pitch yaw | p | omega | v | g]
+    perm = [2, 3, 0, 1]
+    my = np.array([1.0, -1.0, 1.0])
+    Rm = R.copy()
+    Rm["x0"] = R["x0"] * sgn
+    Rm["xref"] = R["xref"] * sgn
+    Rm["r"] = R["r"][:, :, perm, :] * my
+    Rm["contact"] = R["contact"][:, :, perm]
+    out = oracle.mpc_batch(mpc_params, Rm, NCPU)
+    assert (out["status"] == 0).all()
+    want = (ref["U"].reshape(-1, 10, 4, 3)[:, :, perm, :] * my).reshape(-1, 120)
+    assert rel_err(out["U"], want) <= 1e-7
+
+
 def test_mpc_oracle_agrees_with_closed_form_restatement(built, mpc_params):
     """The closed-form condensed Hessian the CUDA kernel uses (numpy restatement in tests/tools/prototypes/proto_mpc.py)
     against the oracle's literal simulation of the prediction matrices, and the operator-form active-set loop against
