@@ -263,7 +263,8 @@ def test_batch_threads_agree(params06):
 def test_size_independent_properties_of_the_solution(params06):
     """Properties the domain offers, used at full size by the GPU tests too: (1) scaling S and W by a common factor scales
     the objective and leaves the minimiser alone; (2) mirroring the robot left <-> right (y -> -y) mirrors the forces;
-    (3) inactive rows do not matter: tightening fzmax to just above the largest returned fz changes nothing."""
+    (3) inactive rows do not matter: tightening fzmax to just above the largest returned fz changes nothing;
+    (4) body-frame results are invariant under a quarter turn of the world about z."""
     S = states.generate_states(256, 515, masks="mixed")
     ref = oracle.control_batch(params06, S)
     assert (ref["status"] == 0).all()
@@ -297,6 +298,18 @@ def test_size_independent_properties_of_the_solution(params06):
     wt = ref["tau"].reshape(-1, 4, 3)[:, perm].copy()
     wt[..., 0] *= -1.0
     assert np.abs(outm["tau"] - wt.reshape(-1, 12)).max() <= 1e-6 * np.abs(wt).max()
+    # (4) a quarter turn of the world about z maps the friction pyramids onto themselves and S, the gains and gravity are
+    #     symmetric in x and y: body-frame forces and torques must not change
+    G = np.array([[0.0, -1.0, 0.0], [1.0, 0.0, 0.0], [0.0, 0.0, 1.0]])
+    Sg = S.copy()
+    for f in ("Rwb", "Rwb_d"):
+        Sg[f] = (G @ S[f].reshape(-1, 3, 3)).reshape(-1, 9)
+    for f in ("x", "xdot", "w", "x_d", "xdot_d", "w_d"):
+        Sg[f] = S[f] @ G.T
+    outg = oracle.control_batch(params06, Sg)
+    assert (outg["status"] == 0).all()
+    assert np.abs(outg["grf_body"] - ref["grf_body"]).max() <= 1e-6 * np.abs(ref["grf_body"]).max()
+    assert np.abs(outg["tau"] - ref["tau"]).max() <= 1e-6 * np.abs(ref["tau"]).max()
     # (3)
     fz_world = -np.einsum("nij,nlj->nli", S["Rwb"].reshape(-1, 3, 3), ref["grf_body"].reshape(-1, 4, 3))[..., 2]
     inner = fz_world.max(axis=1) < params06.fzmax - 1.0  # QPs whose fzmax rows are all inactive
