@@ -320,7 +320,7 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic_per_launch(args.workload), "peak_source": peak_src,
                          "ncu": ncu_explanatory(args.workload),
-                         "algorithmic_bytes_per_qp": ALGO_BYTES_PER_QP, "kernel": "balance_qp_kernel<PackedIO>" if os.environ.get("QPB_QPS_PER_WARP") == "1" else "balance_qp_kernel16<PackedIO>",
+                         "algorithmic_bytes_per_qp": ALGO_BYTES_PER_QP, "kernel": {"1": "balance_qp_kernel<PackedIO>", "2": "balance_qp_kernel16<PackedIO>"}.get(os.environ.get("QPB_QPS_PER_WARP", ""), "balance_qp_tpq_kernel<PackedIO>"),
                          "kernel_ms": kernel_ms,
                          "note": "the path is FP64-issue/latency bound, not DRAM bound (DESIGN.md); per-GPU figure"},
             "cpu_baseline": cpu,

@@ -15,6 +15,7 @@
 #include "qpb_kernel16.cuh"
 #include "qpb_plan.cuh"
 #include "qpb_swing.cuh"
+#include "qpb_tpq.cuh"
 
 namespace {
 
@@ -58,7 +59,7 @@ bool is_sympd(const double* A, int n) {
 constexpr int kHostSlots = 6;          // streams / staging slots of the host-buffer pipeline
 constexpr int64_t kHostChunkMax = 16384;  // capacity of a pipeline stage (8 MiB in, 4 MiB out)
 constexpr int64_t kMaxRecordsPerLaunch = (int64_t)1 << 31;  // the kernels index work items with 32 bits
-constexpr uint32_t kTicketSlots = 4096;  // ring of work counters; a launch re-zeroes the slot half a ring ahead
+constexpr uint32_t kTicketSlots = 4096;  // ring of {work counter, CTAs finished} pairs; the kernels re-arm their own pair
 constexpr int64_t kSmallCall = 128;      // host calls up to this many robots go through one pinned, mapped staging block
 constexpr size_t kSmallBytes = (size_t)kSmallCall * 1536;  // states + results + swing records (or the kinematics arrays)
 
@@ -70,9 +71,13 @@ struct qpb_handle {
   int device = 0;
   int num_sms = 0;
   int ctas_per_sm_packed = 0, ctas_per_sm_split = 0, ctas_per_sm_16 = 0;
-  // kernel mapping: 2 = balance_qp_kernel16 (two QPs per warp, default: 1.2x the throughput), 1 = balance_qp_kernel
-  // (one warp per QP).  QPB_QPS_PER_WARP=1|2 in the environment at qpb_create time overrides it.
+  // kernel mapping: 32 = balance_qp_tpq_kernel (one thread per QP, range-space form; the default whenever W = w I and
+  // fzmin >= 0, i.e. for the reference's configuration), 2 = balance_qp_kernel16 (two QPs per warp; general W),
+  // 1 = balance_qp_kernel (one warp per QP, north_star's literal mapping).  QPB_QPS_PER_WARP=1|2|32 in the environment
+  // at qpb_create time overrides the choice (32 is refused when the parameters do not qualify).
   int qps_per_warp = 2;
+  int ctas_per_sm_tpq = 0;
+  qpb::tpq::FastParams fast;
   qpb_params params;
   qpb_params* d_params = nullptr;
   cudaStream_t streams[kHostSlots] = {};
@@ -112,23 +117,31 @@ template <class IO>
 int launch_balance(qpb_handle* h, const IO& io, int64_t n, int ctas_per_sm, cudaStream_t stream) {
   if (n == 0) return QPB_SUCCESS;
   if (n > kMaxRecordsPerLaunch) return fail(QPB_ERR_INVALID_ARG, "more than 2^31 records in one call: split the batch");
-  const int per_warp = h->qps_per_warp;  // 1: one warp per QP; 2: two QPs per warp (half-warp kernel)
+  const int per_warp = h->qps_per_warp;  // 1: one warp per QP; 2: two QPs per warp (half-warp kernel); 32: one thread per QP
+  // Launch i draws its work tickets from pair i % R of the ring; the last CTA of a launch re-arms the pair, so a launch
+  // is self-contained (safe under CUDA-graph replay) as long as fewer than R = 4096 launches of a handle are in flight.
+  const uint32_t slot = h->ticket_slot.fetch_add(1, std::memory_order_relaxed) % kTicketSlots;
+  unsigned long long* t0 = h->d_tickets + 2 * (size_t)slot;
+  if (per_warp == 32) {
+    const int64_t want = (n + 32 * QPB_TPQ_WARPS - 1) / (32 * QPB_TPQ_WARPS);
+    const int64_t cap = (int64_t)h->num_sms * h->ctas_per_sm_tpq;
+    const int grid = (int)(want < cap ? want : cap);
+    qpb::tpq::balance_qp_tpq_kernel<IO><<<grid, QPB_TPQ_WARPS * 32, 0, stream>>>(h->params, h->fast, io, n, t0);
+    h->launches.fetch_add(1, std::memory_order_relaxed);
+    QPB_CUDA(cudaGetLastError());
+    return QPB_SUCCESS;
+  }
   const int64_t units = (n + per_warp - 1) / per_warp;
   const int64_t want = (units + qpb::WARPS_PER_CTA - 1) / qpb::WARPS_PER_CTA;
   const int64_t cap = (int64_t)h->num_sms * (per_warp == 2 ? h->ctas_per_sm_16 : ctas_per_sm);
   const int grid = (int)(want < cap ? want : cap);
-  // Launch i draws tickets from slot i % R and zeroes slot (i + R/2) % R for a launch far in the future, so no
-  // memset sits on the critical path; this is safe while fewer than R/2 = 2048 launches of one handle are in flight.
-  const uint32_t slot = h->ticket_slot.fetch_add(1, std::memory_order_relaxed) % kTicketSlots;
-  unsigned long long* t0 = h->d_tickets + slot;
-  unsigned long long* t1 = h->d_tickets + (slot + kTicketSlots / 2) % kTicketSlots;
   if (per_warp == 2) {
     const qpb_params& p = h->params;
     const qpb::LoopConsts kc{ p.mu, p.fzmin, p.fzmax, -1e-9 * (1.0 + std::fmax(std::fabs(p.fzmin), std::fabs(p.fzmax))), p.max_iter };
-    qpb::balance_qp_kernel16<IO><<<grid, qpb::WARPS_PER_CTA * 32, 0, stream>>>(h->d_params, io, n, t0, t1, kc);
+    qpb::balance_qp_kernel16<IO><<<grid, qpb::WARPS_PER_CTA * 32, 0, stream>>>(h->d_params, io, n, t0, kc);
   }
   else
-    qpb::balance_qp_kernel<IO><<<grid, qpb::WARPS_PER_CTA * 32, 0, stream>>>(h->d_params, io, n, t0, t1);
+    qpb::balance_qp_kernel<IO><<<grid, qpb::WARPS_PER_CTA * 32, 0, stream>>>(h->d_params, io, n, t0);
   h->launches.fetch_add(1, std::memory_order_relaxed);
   QPB_CUDA(cudaGetLastError());
   return QPB_SUCCESS;
@@ -315,8 +328,8 @@ int qpb_create(const qpb_params* params, int device, qpb_handle** out) {
     qpb_default_plan_params(&pp);
     e = cudaMemcpy(h->d_plan, &pp, sizeof(pp), cudaMemcpyHostToDevice);
   }
-  if (e == cudaSuccess) e = cudaMalloc(&h->d_tickets, kTicketSlots * sizeof(unsigned long long));
-  if (e == cudaSuccess) e = cudaMemset(h->d_tickets, 0, kTicketSlots * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMalloc(&h->d_tickets, 2 * kTicketSlots * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMemset(h->d_tickets, 0, 2 * kTicketSlots * sizeof(unsigned long long));
   if (e == cudaSuccess)
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->ctas_per_sm_packed, qpb::balance_qp_kernel<qpb::PackedIO>,
                                                       qpb::WARPS_PER_CTA * 32, 0);
@@ -330,7 +343,15 @@ int qpb_create(const qpb_params* params, int device, qpb_handle** out) {
       e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, qpb::balance_qp_kernel16<qpb::SplitIO>, qpb::WARPS_PER_CTA * 32, 0);
     h->ctas_per_sm_16 = a < b ? a : b;
   }
-  if (e != cudaSuccess || h->ctas_per_sm_packed < 1 || h->ctas_per_sm_split < 1 || h->ctas_per_sm_16 < 1) {
+  if (e == cudaSuccess) {
+    int a = 0, b = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, qpb::tpq::balance_qp_tpq_kernel<qpb::PackedIO>, QPB_TPQ_WARPS * 32, 0);
+    if (e == cudaSuccess)
+      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, qpb::tpq::balance_qp_tpq_kernel<qpb::SplitIO>, QPB_TPQ_WARPS * 32, 0);
+    h->ctas_per_sm_tpq = a < b ? a : b;
+  }
+  if (e != cudaSuccess || h->ctas_per_sm_packed < 1 || h->ctas_per_sm_split < 1 || h->ctas_per_sm_16 < 1 ||
+      h->ctas_per_sm_tpq < 1) {
     const std::string msg = std::string("qpb_create: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "kernel does not fit");
     if (h->d_params) cudaFree(h->d_params);
     if (h->d_tickets) cudaFree(h->d_tickets);
@@ -340,9 +361,13 @@ int qpb_create(const qpb_params* params, int device, qpb_handle** out) {
     return fail(QPB_ERR_CUDA, msg);
   }
   h->num_sms = prop.multiProcessorCount;
+  // The thread-per-QP kernel needs W = w I (range-space form) and fzmin >= 0 (its working sets stay within the faces
+  // of the truncated pyramid, qpb_tpq_core.h); everything else takes the general half-warp kernel.
+  const bool fast_ok = qpb::tpq::make_fast_params(*params, h->fast) && params->fzmin >= 0.0;
+  h->qps_per_warp = fast_ok ? 32 : 2;
   if (const char* env = std::getenv("QPB_QPS_PER_WARP")) {
     const int v = std::atoi(env);
-    if (v == 1 || v == 2) h->qps_per_warp = v;
+    if (v == 1 || v == 2 || (v == 32 && fast_ok)) h->qps_per_warp = v;
   }
   if (const char* env = std::getenv("QPB_ZEROCOPY")) h->zero_copy = std::atoi(env);
   if (const char* env = std::getenv("QPB_HOST_CHUNK")) {

@@ -29,6 +29,7 @@
 #include <stdint.h>
 
 #include "../../include/qpb200.h"
+#include "qpb_stages.h"
 
 namespace qpb {
 
@@ -47,48 +48,6 @@ struct __align__(16) WarpSmem {
   double bz[32];         // broadcast buffer (one slot per lane)
   double bv[16];         // second broadcast buffer
 };
-
-// MUFU seeds carry >= 20 good bits (e <= 2^-20); one third-order step leaves e^3 <= 2^-60.
-__device__ __forceinline__ double rcp_fast(double x) {
-  double y;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-  const double e = fma(-x, y, 1.0);
-  return fma(y, fma(e, e, e), y);  // y (1 + e + e^2)
-}
-
-__device__ __forceinline__ double rsqrt_fast(double x) {
-  double y;
-  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-  const double e = fma(-(x * y), y, 1.0);               // 1 - x y^2
-  return fma(y * fma(0.375, e, 0.5), e, y);             // y (1 + e/2 + 3e^2/8)
-}
-__device__ __forceinline__ double sqrt_fast(double x) { return x > 0.0 ? x * rsqrt_fast(x) : 0.0; }
-
-// atan on [0, inf) x [0, inf): first-quadrant atan2(n, w) (n, w >= 0, not both 0).  Octant reduction
-// to |x| <= tan(pi/8), then x + x s P(s) with a degree-11 fit (max relative error 2.2e-16).
-__device__ __forceinline__ double atan2_q1(double n, double w) {
-  const bool swap = n > w;
-  const double num = swap ? w : n, den = swap ? n : w;
-  double r = num * rcp_fast(den);                        // in [0, 1]
-  const bool hi = r > 0.41421356237309503;
-  if (hi) r = (r - 1.0) * rcp_fast(r + 1.0);             // atan(r) = pi/4 + atan((r-1)/(r+1))
-  const double s = r * r;
-  double q = 1.08884100212413085e-02;
-  q = fma(q, s, -2.97502137203377037e-02);
-  q = fma(q, s, 4.36598234771156321e-02);
-  q = fma(q, s, -5.19008551015063060e-02);
-  q = fma(q, s, 5.87346776764138684e-02);
-  q = fma(q, s, -6.66594734155613600e-02);
-  q = fma(q, s, 7.69226916464344074e-02);
-  q = fma(q, s, -9.09090775828966802e-02);
-  q = fma(q, s, 1.11111110828050572e-01);
-  q = fma(q, s, -1.42857142853820868e-01);
-  q = fma(q, s, 1.99999999999983052e-01);
-  q = fma(q, s, -3.33333333333333370e-01);
-  double a = fma(r * s, q, r);
-  if (hi) a += 0.78539816339744831;
-  return swap ? 1.5707963267948966 - a : a;
-}
 
 __device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(FULL, v, src); }
 
@@ -117,53 +76,6 @@ __device__ __forceinline__ double dot12(const double (&a)[12], const double (&b)
     s1 = fma(a[j + 1], b[j + 1], s1);
   }
   return s0 + s1;
-}
-
-// SO(3) log map exactly as Eigen::AngleAxisd(Matrix3d) does it (reference rigid3d.cpp:198-203 ->
-// drake RotationMatrix::ToAngleAxis -> Eigen quaternion-from-matrix + angle-axis-from-quaternion).
-__device__ __forceinline__ void angle_axis_total(const double (&R)[9], double (&out)[3]) {
-  double qw, qv[3];
-  double t = R[0] + R[4] + R[8];
-  if (t > 0.0) {
-    t = sqrt_fast(t + 1.0);
-    qw = 0.5 * t;
-    t = 0.5 * rcp_fast(t);
-    qv[0] = (R[7] - R[5]) * t;
-    qv[1] = (R[2] - R[6]) * t;
-    qv[2] = (R[3] - R[1]) * t;
-  } else if (R[0] >= R[4] && R[0] >= R[8]) {  // i = 0 (Eigen picks the first largest diagonal)
-    t = sqrt_fast(R[0] - R[4] - R[8] + 1.0);
-    qv[0] = 0.5 * t;
-    t = 0.5 * rcp_fast(t);
-    qw = (R[7] - R[5]) * t;
-    qv[1] = (R[3] + R[1]) * t;
-    qv[2] = (R[6] + R[2]) * t;
-  } else if (R[4] > R[0] && R[4] >= R[8]) {  // i = 1
-    t = sqrt_fast(R[4] - R[8] - R[0] + 1.0);
-    qv[1] = 0.5 * t;
-    t = 0.5 * rcp_fast(t);
-    qw = (R[2] - R[6]) * t;
-    qv[2] = (R[7] + R[5]) * t;
-    qv[0] = (R[1] + R[3]) * t;
-  } else {  // i = 2
-    t = sqrt_fast(R[8] - R[0] - R[4] + 1.0);
-    qv[2] = 0.5 * t;
-    t = 0.5 * rcp_fast(t);
-    qw = (R[3] - R[1]) * t;
-    qv[0] = (R[2] + R[6]) * t;
-    qv[1] = (R[5] + R[7]) * t;
-  }
-  double n = sqrt_fast(qv[0] * qv[0] + qv[1] * qv[1] + qv[2] * qv[2]);
-  if (n > 1e-150) {
-    const double angle = 2.0 * atan2_q1(n, fabs(qw));
-    if (qw < 0.0) n = -n;
-    const double s = angle * rcp_fast(n);
-    out[0] = qv[0] * s;
-    out[1] = qv[1] * s;
-    out[2] = qv[2] * s;
-  } else {
-    out[0] = out[1] = out[2] = 0.0;
-  }
 }
 
 // Where a record's 64 double slots come from.
@@ -235,8 +147,7 @@ __device__ __forceinline__ void store_rec(const SplitIO& io, int64_t idx, int la
 // ------------------------------------------------------------------------------------------------
 template <class IO>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, QPB_MIN_CTAS_PER_SM)
-balance_qp_kernel(const qpb_params* __restrict__ gparams, IO io, int64_t n, unsigned long long* __restrict__ ticket,
-                  unsigned long long* __restrict__ ticket_to_clear) {
+balance_qp_kernel(const qpb_params* __restrict__ gparams, IO io, int64_t n, unsigned long long* __restrict__ ticket) {
   __shared__ qpb_params P;
   __shared__ WarpSmem wsm[WARPS_PER_CTA];
 
@@ -246,7 +157,6 @@ balance_qp_kernel(const qpb_params* __restrict__ gparams, IO io, int64_t n, unsi
     double* dst = reinterpret_cast<double*>(&P);
     for (int i = threadIdx.x; i < nw; i += blockDim.x) dst[i] = src[i];
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) *ticket_to_clear = 0ULL;  // for a launch half a ring from now
   __syncthreads();
 
   const int lane = threadIdx.x & 31;
@@ -305,53 +215,7 @@ balance_qp_kernel(const qpb_params* __restrict__ gparams, IO io, int64_t n, unsi
       const double* R = ws.rec;
       // ---- PD target, balance_controller.cpp:126-139 (uniform across lanes) ---------------------
       double b6[6];
-      {
-        double acc[3];
-#pragma unroll
-        for (int i = 0; i < 3; i++)
-          acc[i] = P.kp_p[i] * (ws.rec[27 + i] - ws.rec[18 + i]) + P.kd_p[i] * (ws.rec[30 + i] - ws.rec[21 + i]);
-        acc[0] += P.kff[0] * ws.rec[30];
-        acc[1] += P.kff[1] * ws.rec[31];
-        acc[2] += P.kff[2] * P.mass * 9.81;
-        const double g[3] = { 0.0, 0.0, -9.81 };
-#pragma unroll
-        for (int i = 0; i < 3; i++) b6[i] = P.mass * (acc[i] + g[i]);  // :265
-        double Re[9], aa[3], wd[3];
-#pragma unroll
-        for (int i = 0; i < 3; i++)
-#pragma unroll
-          for (int j = 0; j < 3; j++)  // R_d * R^T, :133
-            Re[3 * i + j] = ws.rec[9 + 3 * i] * R[3 * j] + ws.rec[9 + 3 * i + 1] * R[3 * j + 1] +
-                            ws.rec[9 + 3 * i + 2] * R[3 * j + 2];
-        angle_axis_total(Re, aa);
-#pragma unroll
-        for (int i = 0; i < 3; i++) wd[i] = P.kp_w[i] * aa[i] + P.kd_w[i] * (ws.rec[33 + i] - ws.rec[24 + i]);
-        wd[0] += P.kff[3] * ws.rec[33];
-        wd[1] += P.kff[4] * ws.rec[34];
-        wd[1] += P.kff[5] * ws.rec[35];  // index 1 twice: reference quirk, :139
-        // Iw = R Ib R^T, :251
-        double RI[9], Iw[9];
-#pragma unroll
-        for (int i = 0; i < 3; i++)
-#pragma unroll
-          for (int j = 0; j < 3; j++)
-            RI[3 * i + j] = R[3 * i] * P.Ib[j] + R[3 * i + 1] * P.Ib[3 + j] + R[3 * i + 2] * P.Ib[6 + j];
-#pragma unroll
-        for (int i = 0; i < 3; i++)
-#pragma unroll
-          for (int j = 0; j < 3; j++)
-            Iw[3 * i + j] = RI[3 * i] * R[3 * j] + RI[3 * i + 1] * R[3 * j + 1] + RI[3 * i + 2] * R[3 * j + 2];
-        const double w0 = ws.rec[33], w1 = ws.rec[34], w2 = ws.rec[35];  // desired omega, :269
-        double Iwd[3], Iww[3];
-#pragma unroll
-        for (int i = 0; i < 3; i++) {
-          Iwd[i] = Iw[3 * i] * wd[0] + Iw[3 * i + 1] * wd[1] + Iw[3 * i + 2] * wd[2];
-          Iww[i] = Iw[3 * i] * w0 + Iw[3 * i + 1] * w1 + Iw[3 * i + 2] * w2;
-        }
-        b6[3] = Iwd[0] + (w1 * Iww[2] - w2 * Iww[1]);
-        b6[4] = Iwd[1] + (w2 * Iww[0] - w0 * Iww[2]);
-        b6[5] = Iwd[2] + (w0 * Iww[1] - w1 * Iww[0]);
-      }
+      pd_rhs(P, ws.rec, b6);
 
       // ---- lever arms r_leg = R p_leg (:245-248); lane i holds component ax of leg ----------------
       const double ri = R[3 * ax] * ws.rec[36 + 3 * leg] + R[3 * ax + 1] * ws.rec[37 + 3 * leg] +
@@ -583,25 +447,23 @@ balance_qp_kernel(const qpb_params* __restrict__ gparams, IO io, int64_t n, unsi
     const double fbx = shfl_d(fb, 3 * leg), fby = shfl_d(fb, 3 * leg + 1), fbz = shfl_d(fb, 3 * leg + 2);
     const double l1 = P.link[3 * leg], l2 = P.link[3 * leg + 1], l3 = P.link[3 * leg + 2];
     double Jx, Jy, Jz;  // column ax of the leg Jacobian
-    if (ax == 0) {
-      Jx = 0.0;
-      Jy = -l1 * s1 - l2 * c1 * c2 - l3 * c1 * c23;
-      Jz = l1 * c1 - l2 * s1 * c2 - l3 * s1 * c23;
-    } else if (ax == 1) {
-      const double h = l2 * s2 + l3 * s23;
-      Jx = l2 * c2 + l3 * c23;
-      Jy = h * s1;
-      Jz = -h * c1;
-    } else {
-      Jx = l3 * c23;
-      Jy = l3 * s1 * s23;
-      Jz = -l3 * s23 * c1;
-    }
+    leg_jacobian_col(ax, l1, l2, l3, s1, c1, s2, c2, s23, c23, Jx, Jy, Jz);
     double tau = Jx * fbx + Jy * fby + Jz * fbz;
     if (P.clamp_tau) tau = fmin(fmax(tau, P.tau_min), P.tau_max);  // commander_node.cpp:526
     if (!(good && stance)) tau = 0.0;
     store_rec(io, idx, lane, fb, tau, status, iters);
     idx = nwarps + (int64_t)__shfl_sync(FULL, next_ticket, 0);
+  }
+  // The last CTA out re-arms the work counter: the launch is self-contained, so the same counter slot serves graph
+  // replays and later launches without a memset (ticket[0] = work counter, ticket[1] = CTAs finished).
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(ticket + 1, 1ULL) == (unsigned long long)gridDim.x - 1ULL) {
+      ticket[0] = 0ULL;
+      ticket[1] = 0ULL;
+      __threadfence();
+    }
   }
 }
 
@@ -622,10 +484,9 @@ __global__ void jt_kernel(const qpb_params* __restrict__ P, const double* __rest
   sincos(t2 + t3, &s23, &c23);
   const bool st = contact ? (contact[i] != 0) : true;
   const double fx = f[3 * i], fy = f[3 * i + 1], fz = f[3 * i + 2];
-  const double h = l2 * s2 + l3 * s23;
-  double o0 = (-l1 * s1 - l2 * c1 * c2 - l3 * c1 * c23) * fy + (l1 * c1 - l2 * s1 * c2 - l3 * s1 * c23) * fz;
-  double o1 = (l2 * c2 + l3 * c23) * fx + h * s1 * fy - h * c1 * fz;
-  double o2 = l3 * c23 * fx + l3 * s1 * s23 * fy - l3 * s23 * c1 * fz;
+  double o[3];
+  leg_jt(l1, l2, l3, s1, c1, s2, c2, s23, c23, fx, fy, fz, o);
+  double o0 = o[0], o1 = o[1], o2 = o[2];
   if (P->clamp_tau) {
     o0 = fmin(fmax(o0, P->tau_min), P->tau_max);
     o1 = fmin(fmax(o1, P->tau_min), P->tau_max);

@@ -88,7 +88,7 @@ __device__ __forceinline__ void load_rec16(const SplitIO& io, int64_t rec, int l
 template <class IO>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, QPB_MIN_CTAS_PER_SM)
 balance_qp_kernel16(const qpb_params* __restrict__ gparams, IO io, int64_t n, unsigned long long* __restrict__ ticket,
-                    unsigned long long* __restrict__ ticket_to_clear, const LoopConsts kc) {
+                    const LoopConsts kc) {
   __shared__ qpb_params P;
   __shared__ HalfSmem hsm[WARPS_PER_CTA * 2];
 
@@ -98,7 +98,6 @@ balance_qp_kernel16(const qpb_params* __restrict__ gparams, IO io, int64_t n, un
     double* dst = reinterpret_cast<double*>(&P);
     for (int i = threadIdx.x; i < nw; i += blockDim.x) dst[i] = src[i];
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) *ticket_to_clear = 0ULL;
   __syncthreads();
 
   const int lane = threadIdx.x & 31;
@@ -151,54 +150,9 @@ balance_qp_kernel16(const qpb_params* __restrict__ gparams, IO io, int64_t n, un
     double x = 0.0;
 
     const double* R = hs.rec;
-    // ---- PD target, balance_controller.cpp:126-139 (uniform across the half) ----------------------
+    // ---- PD target + dynamics right-hand side (qpb_stages.h; uniform across the half) ----------------
     double b6[6];
-    {
-      double acc[3];
-#pragma unroll
-      for (int i = 0; i < 3; i++)
-        acc[i] = P.kp_p[i] * (hs.rec[27 + i] - hs.rec[18 + i]) + P.kd_p[i] * (hs.rec[30 + i] - hs.rec[21 + i]);
-      acc[0] += P.kff[0] * hs.rec[30];
-      acc[1] += P.kff[1] * hs.rec[31];
-      acc[2] += P.kff[2] * P.mass * 9.81;
-      const double g[3] = { 0.0, 0.0, -9.81 };
-#pragma unroll
-      for (int i = 0; i < 3; i++) b6[i] = P.mass * (acc[i] + g[i]);  // :265
-      double Re[9], aa[3], wd[3];
-#pragma unroll
-      for (int i = 0; i < 3; i++)
-#pragma unroll
-        for (int j = 0; j < 3; j++)  // R_d * R^T, :133
-          Re[3 * i + j] = hs.rec[9 + 3 * i] * R[3 * j] + hs.rec[9 + 3 * i + 1] * R[3 * j + 1] +
-                          hs.rec[9 + 3 * i + 2] * R[3 * j + 2];
-      angle_axis_total(Re, aa);
-#pragma unroll
-      for (int i = 0; i < 3; i++) wd[i] = P.kp_w[i] * aa[i] + P.kd_w[i] * (hs.rec[33 + i] - hs.rec[24 + i]);
-      wd[0] += P.kff[3] * hs.rec[33];
-      wd[1] += P.kff[4] * hs.rec[34];
-      wd[1] += P.kff[5] * hs.rec[35];  // index 1 twice: reference quirk, :139
-      double RI[9], Iw[9];
-#pragma unroll
-      for (int i = 0; i < 3; i++)
-#pragma unroll
-        for (int j = 0; j < 3; j++)
-          RI[3 * i + j] = R[3 * i] * P.Ib[j] + R[3 * i + 1] * P.Ib[3 + j] + R[3 * i + 2] * P.Ib[6 + j];
-#pragma unroll
-      for (int i = 0; i < 3; i++)
-#pragma unroll
-        for (int j = 0; j < 3; j++)
-          Iw[3 * i + j] = RI[3 * i] * R[3 * j] + RI[3 * i + 1] * R[3 * j + 1] + RI[3 * i + 2] * R[3 * j + 2];
-      const double w0 = hs.rec[33], w1 = hs.rec[34], w2 = hs.rec[35];  // desired omega, :269
-      double Iwd[3], Iww[3];
-#pragma unroll
-      for (int i = 0; i < 3; i++) {
-        Iwd[i] = Iw[3 * i] * wd[0] + Iw[3 * i + 1] * wd[1] + Iw[3 * i + 2] * wd[2];
-        Iww[i] = Iw[3 * i] * w0 + Iw[3 * i + 1] * w1 + Iw[3 * i + 2] * w2;
-      }
-      b6[3] = Iwd[0] + (w1 * Iww[2] - w2 * Iww[1]);
-      b6[4] = Iwd[1] + (w2 * Iww[0] - w0 * Iww[2]);
-      b6[5] = Iwd[2] + (w0 * Iww[1] - w1 * Iww[0]);
-    }
+    pd_rhs(P, hs.rec, b6);
 
     // ---- lever arms r_leg = R p_leg (:245-248) ----------------------------------------------------
     const double ri = R[3 * ax] * hs.rec[36 + 3 * leg] + R[3 * ax + 1] * hs.rec[37 + 3 * leg] +
@@ -436,25 +390,23 @@ balance_qp_kernel16(const qpb_params* __restrict__ gparams, IO io, int64_t n, un
     const double fbx = shfl16(fb, 3 * leg), fby = shfl16(fb, 3 * leg + 1), fbz = shfl16(fb, 3 * leg + 2);
     const double l1 = P.link[3 * leg], l2 = P.link[3 * leg + 1], l3 = P.link[3 * leg + 2];
     double Jx, Jy, Jz;
-    if (ax == 0) {
-      Jx = 0.0;
-      Jy = -l1 * s1 - l2 * c1 * c2 - l3 * c1 * c23;
-      Jz = l1 * c1 - l2 * s1 * c2 - l3 * s1 * c23;
-    } else if (ax == 1) {
-      const double h = l2 * s2 + l3 * s23;
-      Jx = l2 * c2 + l3 * c23;
-      Jy = h * s1;
-      Jz = -h * c1;
-    } else {
-      Jx = l3 * c23;
-      Jy = l3 * s1 * s23;
-      Jz = -l3 * s23 * c1;
-    }
+    leg_jacobian_col(ax, l1, l2, l3, s1, c1, s2, c2, s23, c23, Jx, Jy, Jz);
     double tau = Jx * fbx + Jy * fby + Jz * fbz;
     if (P.clamp_tau) tau = fmin(fmax(tau, P.tau_min), P.tau_max);
     if (!(good && stance)) tau = 0.0;
     if (have) store_rec(io, rec, l, fb, tau, status, iters);
     pair = nwarps + __shfl_sync(FULL, next_ticket, 0);
+  }
+  // The last CTA out re-arms the work counter: the launch is self-contained, so the same counter slot serves graph
+  // replays and later launches without a memset (ticket[0] = work counter, ticket[1] = CTAs finished).
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(ticket + 1, 1ULL) == (unsigned long long)gridDim.x - 1ULL) {
+      ticket[0] = 0ULL;
+      ticket[1] = 0ULL;
+      __threadfence();
+    }
   }
 }
 

@@ -361,13 +361,12 @@ __device__ __forceinline__ double row_slack(int t, double fx, double fy, double 
 template <int NT>
 __global__ void __launch_bounds__(NT, 1)
 mpc_qp_kernel(const __grid_constant__ DevParams P, const qpb_mpc_rec* __restrict__ in, qpb_mpc_out_rec* __restrict__ out,
-              int64_t nrec, unsigned long long* __restrict__ ticket, unsigned long long* __restrict__ ticket_clear) {
+              int64_t nrec, unsigned long long* __restrict__ ticket) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem& S = *reinterpret_cast<Smem*>(smem_raw);
   constexpr int NW = NT / 32;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const double INF = __longlong_as_double(0x7ff0000000000000LL);
-  if (blockIdx.x == 0 && tid == 0) *ticket_clear = 0ull;  // counter of a launch far in the future
 
   int64_t rec = blockIdx.x;
   while (rec < nrec) {
@@ -934,6 +933,16 @@ mpc_qp_kernel(const __grid_constant__ DevParams P, const qpb_mpc_rec* __restrict
 #ifdef QPB_MPC_PROFILE
     if (tid == 0) atomicAdd(&g_mpc_prof[5], 1ull);
 #endif
+  }
+  // the last CTA out re-arms the work counter (ticket[0] = work counter, ticket[1] = CTAs finished): graph replays and
+  // later launches reuse the slot without a memset
+  if (tid == 0) {
+    __threadfence();
+    if (atomicAdd(ticket + 1, 1ull) == (unsigned long long)gridDim.x - 1ull) {
+      ticket[0] = 0ull;
+      ticket[1] = 0ull;
+      __threadfence();
+    }
   }
 }
 

@@ -66,9 +66,8 @@ int launch_mpc(qpb_mpc_handle* h, int64_t n, const qpb_mpc_rec* d_recs, qpb_mpc_
   if (n > ((int64_t)1 << 31) - 4096) return qpb_internal_fail(QPB_ERR_INVALID_ARG, "more than 2^31 records in one call: split the batch");
   const int grid = (int)(n < h->num_sms ? n : h->num_sms);  // one persistent CTA per SM (215 KB of shared memory each)
   const uint32_t slot = h->ticket_slot.fetch_add(1, std::memory_order_relaxed) % kTicketSlots;
-  unsigned long long* t0 = h->d_tickets + slot;
-  unsigned long long* t1 = h->d_tickets + (slot + kTicketSlots / 2) % kTicketSlots;
-  qpbmpc::mpc_qp_kernel<256><<<grid, 256, sizeof(qpbmpc::Smem), stream>>>(h->dp, d_recs, d_out, n, t0, t1);
+  unsigned long long* t0 = h->d_tickets + 2 * (size_t)slot;  // {work counter, CTAs finished}; the kernel re-arms both
+  qpbmpc::mpc_qp_kernel<256><<<grid, 256, sizeof(qpbmpc::Smem), stream>>>(h->dp, d_recs, d_out, n, t0);
   h->launches.fetch_add(1, std::memory_order_relaxed);
   MPC_CUDA(cudaGetLastError());
   return QPB_SUCCESS;
@@ -136,8 +135,8 @@ int qpb_mpc_create(const qpb_mpc_params* params, int device, qpb_mpc_handle** ou
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(qpbmpc::mpc_qp_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(qpbmpc::Smem));
 
-  if (e == cudaSuccess) e = cudaMalloc(&h->d_tickets, kTicketSlots * sizeof(unsigned long long));
-  if (e == cudaSuccess) e = cudaMemset(h->d_tickets, 0, kTicketSlots * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMalloc(&h->d_tickets, 2 * kTicketSlots * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMemset(h->d_tickets, 0, 2 * kTicketSlots * sizeof(unsigned long long));
   if (e != cudaSuccess) {
     const std::string msg = std::string("qpb_mpc_create: ") + cudaGetErrorString(e);
     if (h->d_tickets) cudaFree(h->d_tickets);

@@ -314,10 +314,11 @@ def test_cpp_shim_reproduces_reference_call_sequence(built, params08):
         assert np.allclose(data["torque_3stance"][name], ref3["tau"][0][3 * leg:3 * leg + 3], rtol=1e-7, atol=1e-7)
 
 
-@pytest.mark.parametrize("qps_per_warp", ["1", "2"])
+@pytest.mark.parametrize("qps_per_warp", ["1", "2", "32"])
 def test_both_kernel_mappings(built, params06, qps_per_warp, monkeypatch):
-    """balance_qp_kernel (one warp per QP) and balance_qp_kernel16 (two QPs per warp, lock-step halves) run the
-    same arithmetic; both must meet the parity bar on every contact mask, odd batch sizes and failure paths."""
+    """balance_qp_kernel (one warp per QP), balance_qp_kernel16 (two QPs per warp, lock-step halves) and
+    balance_qp_tpq_kernel (one thread per QP, range-space form; the default for W = w I) must all meet the parity bar
+    on every contact mask, odd batch sizes and failure paths."""
     monkeypatch.setenv("QPB_QPS_PER_WARP", qps_per_warp)
     solver = lib.BalanceSolver(params06)
     S = states.generate_states(8191, 606, profile="stress", masks="mixed")  # odd count: last pair is half empty
@@ -414,3 +415,35 @@ def test_single_process_multi_device_sharding(solver06, params06):
     assert all_dev.control_host(Sm).tobytes() == solver06.control_host(Sm).tobytes()
     all_dev.close()
     multi.close()
+
+
+def test_warm_start_across_ticks(built, params06):
+    """The reference hot-starts qpOASES from the previous tick's working set (balance_controller.cpp:177-202).  Here the
+    working set travels as a word in the records' padding: out.pad[0:4] of tick k is copied into state.pad[0:4] of tick
+    k+1.  Results must equal the cold solve (unique optimum) while the working-set changes per tick collapse."""
+    rng = np.random.default_rng(11)
+    S = states.generate_states(8192, 20260103, masks="mixed")
+    solver = lib.BalanceSolver(params06)
+    word = np.zeros((len(S), 4), dtype=np.uint8)
+    warm_iters, cold_iters = [], []
+    for tick in range(6):
+        cold = solver.control_host(S)
+        W = S.copy()
+        W["pad"][:, :4] = word
+        warm = solver.control_host(W)
+        assert np.array_equal(warm["status"], cold["status"])
+        assert rel_err(warm["grf_body"], cold["grf_body"]) <= 1e-7 and rel_err(warm["tau"], cold["tau"]) <= 1e-7
+        if tick:
+            warm_iters.append(warm["iters"].mean())
+            cold_iters.append(cold["iters"].mean())
+        word = warm["pad"][:, :4].copy()
+        assert (word[:, 3] & 0x80).all()  # every result carries its working set
+        # the robots move a little between ticks (1 ms of a 1 kHz loop)
+        S["x"] += rng.normal(0, 2e-4, S["x"].shape)
+        S["xdot"] += rng.normal(0, 2e-3, S["xdot"].shape)
+        S["w"] += rng.normal(0, 2e-3, S["w"].shape)
+    assert np.mean(warm_iters) <= 2.0 < np.mean(cold_iters), (warm_iters, cold_iters)
+    ref = oracle.control_batch(params06, S, NCPU)  # and the last tick against the oracle
+    S["pad"][:, :4] = word
+    _compare(solver.control_host(S), ref)
+    solver.close()

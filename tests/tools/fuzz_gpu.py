@@ -1,4 +1,4 @@
-"""Randomised parameter fuzz: CUDA path (both kernel mappings) vs the CPU oracle."""
+"""Randomised parameter fuzz: CUDA path (default kernel choice and both warp mappings) vs the CPU oracle."""
 import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, oracle
@@ -30,8 +30,11 @@ for t in range(trials):
     if rng.random() < 0.3:
         Sin["x_d"][:, 2] -= rng.uniform(0, 0.5, nper)
     ref = oracle.control_batch(p, Sin, ncpu)
-    for mode in ("2", "1"):
-        os.environ["QPB_QPS_PER_WARP"] = mode
+    for mode in ("auto", "2", "1"):  # auto: thread-per-QP kernel when W = w I and fzmin >= 0, else the half-warp kernel
+        if mode == "auto":
+            os.environ.pop("QPB_QPS_PER_WARP", None)
+        else:
+            os.environ["QPB_QPS_PER_WARP"] = mode
         sol = lib.BalanceSolver(p); out = sol.control_host(Sin); sol.close()
         mism = int((out["status"] != ref["status"]).sum())
         ok = (out["status"] == 0) & (ref["status"] == 0)
@@ -42,4 +45,4 @@ for t in range(trials):
             fails += 1
             print(f"FAIL trial {t} mode {mode}: mu={p.mu:.3g} mass={p.mass:.3g} fz=[{p.fzmin:.3g},{p.fzmax:.3g}] w={w:.2e} sS={sS} sW={sW} {prof}/{masks} "
                   f"status mism {mism} (gpu {np.bincount(out['status'], minlength=3)}, ref {np.bincount(ref['status'], minlength=3)}) err {err:.2e} {errt:.2e} iters max {out['iters'].max()}")
-print(f"fuzz: {trials} parameter sets x {nper} states x 2 mappings, failures {fails}, worst rel err {worst:.2e}")
+print(f"fuzz: {trials} parameter sets x {nper} states x 3 kernel choices, failures {fails}, worst rel err {worst:.2e}")
