@@ -76,7 +76,8 @@ struct qpb_handle {
   // 1 = balance_qp_kernel (one warp per QP, north_star's literal mapping).  QPB_QPS_PER_WARP=1|2|32 in the environment
   // at qpb_create time overrides the choice (32 is refused when the parameters do not qualify).
   int qps_per_warp = 2;
-  int ctas_per_sm_tpq = 0;
+  int ctas_per_sm_tpq[5] = {};  // indexed by lanes per QP (1, 2, 4)
+  int tpq_lpq = 2;              // lanes per QP of the thread-per-QP kernel family (QPB_TPQ_LPQ=1|2|4 overrides)
   qpb::tpq::FastParams fast;
   qpb_params params;
   qpb_params* d_params = nullptr;
@@ -123,10 +124,17 @@ int launch_balance(qpb_handle* h, const IO& io, int64_t n, int ctas_per_sm, cuda
   const uint32_t slot = h->ticket_slot.fetch_add(1, std::memory_order_relaxed) % kTicketSlots;
   unsigned long long* t0 = h->d_tickets + 2 * (size_t)slot;
   if (per_warp == 32) {
-    const int64_t want = (n + 32 * QPB_TPQ_WARPS - 1) / (32 * QPB_TPQ_WARPS);
-    const int64_t cap = (int64_t)h->num_sms * h->ctas_per_sm_tpq;
+    const int lpq = h->tpq_lpq;
+    const int warps = lpq == 1 ? qpb::tpq::Shape<1>::W : (lpq == 2 ? qpb::tpq::Shape<2>::W : qpb::tpq::Shape<4>::W);
+    const int64_t want = (n + 32 * warps - 1) / (32 * warps);  // a CTA with fewer than 32 records per warp would idle
+    const int64_t cap = (int64_t)h->num_sms * h->ctas_per_sm_tpq[lpq];
     const int grid = (int)(want < cap ? want : cap);
-    qpb::tpq::balance_qp_tpq_kernel<IO><<<grid, QPB_TPQ_WARPS * 32, 0, stream>>>(h->params, h->fast, io, n, t0);
+    if (lpq == 1)
+      qpb::tpq::balance_qp_tpq_kernel<IO, 1><<<grid, warps * 32, 0, stream>>>(h->params, h->fast, io, n, t0);
+    else if (lpq == 4)
+      qpb::tpq::balance_qp_tpq_kernel<IO, 4><<<grid, warps * 32, 0, stream>>>(h->params, h->fast, io, n, t0);
+    else
+      qpb::tpq::balance_qp_tpq_kernel<IO, 2><<<grid, warps * 32, 0, stream>>>(h->params, h->fast, io, n, t0);
     h->launches.fetch_add(1, std::memory_order_relaxed);
     QPB_CUDA(cudaGetLastError());
     return QPB_SUCCESS;
@@ -343,15 +351,17 @@ int qpb_create(const qpb_params* params, int device, qpb_handle** out) {
       e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, qpb::balance_qp_kernel16<qpb::SplitIO>, qpb::WARPS_PER_CTA * 32, 0);
     h->ctas_per_sm_16 = a < b ? a : b;
   }
-  if (e == cudaSuccess) {
+  auto tpq_occ = [&](auto kp, auto ks, int lpq, int warps) {
     int a = 0, b = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, qpb::tpq::balance_qp_tpq_kernel<qpb::PackedIO>, QPB_TPQ_WARPS * 32, 0);
-    if (e == cudaSuccess)
-      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, qpb::tpq::balance_qp_tpq_kernel<qpb::SplitIO>, QPB_TPQ_WARPS * 32, 0);
-    h->ctas_per_sm_tpq = a < b ? a : b;
-  }
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, kp, warps * 32, 0);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, ks, warps * 32, 0);
+    h->ctas_per_sm_tpq[lpq] = a < b ? a : b;
+  };
+  tpq_occ(qpb::tpq::balance_qp_tpq_kernel<qpb::PackedIO, 1>, qpb::tpq::balance_qp_tpq_kernel<qpb::SplitIO, 1>, 1, qpb::tpq::Shape<1>::W);
+  tpq_occ(qpb::tpq::balance_qp_tpq_kernel<qpb::PackedIO, 2>, qpb::tpq::balance_qp_tpq_kernel<qpb::SplitIO, 2>, 2, qpb::tpq::Shape<2>::W);
+  tpq_occ(qpb::tpq::balance_qp_tpq_kernel<qpb::PackedIO, 4>, qpb::tpq::balance_qp_tpq_kernel<qpb::SplitIO, 4>, 4, qpb::tpq::Shape<4>::W);
   if (e != cudaSuccess || h->ctas_per_sm_packed < 1 || h->ctas_per_sm_split < 1 || h->ctas_per_sm_16 < 1 ||
-      h->ctas_per_sm_tpq < 1) {
+      h->ctas_per_sm_tpq[1] < 1 || h->ctas_per_sm_tpq[2] < 1 || h->ctas_per_sm_tpq[4] < 1) {
     const std::string msg = std::string("qpb_create: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "kernel does not fit");
     if (h->d_params) cudaFree(h->d_params);
     if (h->d_tickets) cudaFree(h->d_tickets);
@@ -368,6 +378,10 @@ int qpb_create(const qpb_params* params, int device, qpb_handle** out) {
   if (const char* env = std::getenv("QPB_QPS_PER_WARP")) {
     const int v = std::atoi(env);
     if (v == 1 || v == 2 || (v == 32 && fast_ok)) h->qps_per_warp = v;
+  }
+  if (const char* env = std::getenv("QPB_TPQ_LPQ")) {
+    const int v = std::atoi(env);
+    if (v == 1 || v == 2 || v == 4) h->tpq_lpq = v;
   }
   if (const char* env = std::getenv("QPB_ZEROCOPY")) h->zero_copy = std::atoi(env);
   if (const char* env = std::getenv("QPB_HOST_CHUNK")) {

@@ -12,8 +12,9 @@
 // system whatever the working set.  The solver is Goldfarb-Idnani's dual active-set method (the same method, selection
 // rule and tolerances as the half-warp kernel, so the iteration path is the same), but each step direction
 //   z = (1/2w) (Pi n_p - 2 Pi A' yh),   G yh = (1/2) A_l Pi_l n_p,      N r = n_p - Q z  (leg by leg, closed form)
-// is solved afresh from a 6x6 Cholesky factor: no operator is updated from step to step, so no error accumulates
-// beyond the iterate itself.  State per QP: f (12), multipliers (12), lever arms (12), one sign per row group.
+// comes from a fresh 6x6 Cholesky factorisation of G = w S^-1 + sum_i A_i Pi_i A_i'; G itself follows the working
+// set by one rank-one update per change (G -+= v v' / (n' t), v = A_l t, t = the row's normal projected on the face
+// without that row).  State per QP: f (12), multipliers (12), lever arms (12), G (21), a 24-bit working-set word.
 //
 // Working sets are restricted to at most one row per group (x, y, z) and leg -- the faces of the truncated pyramid.
 // Goldfarb-Idnani may add any violated row, so the selection rule simply never picks the second row of a group that is
@@ -29,6 +30,8 @@
 // Everything here compiles for the host as well: tests/ build it with g++ to check the algorithm against the oracle
 // on the CPU.  The product path is the CUDA kernel in qpb_tpq.cuh only.
 #pragma once
+
+#include <string.h>
 
 #include "qpb_stages.h"
 
@@ -48,37 +51,105 @@ struct FastParams {
 
 #define ix(i, j) ((i) * ((i) + 1) / 2 + (j))  // packed lower triangle
 
-// Face of one leg: Pi = diag(ax, ay, 0) + kap d d', d = (dx, dy, 1).
-struct Face {
-  double ax, ay, dx, dy, kap;
-};
-
-// sx, sy, sz: coefficient of the active row of the group on its own axis (0 = none):
-//   x rows (sx, 0, mu), y rows (0, sy, mu), z rows (0, 0, sz)   [A rows: sx = sy = -1, sz = +1; B rows the opposite]
-QPB_HD Face face_of(double sx, double sy, double sz, bool stance, const FastParams& K) {
-  const bool X = sx != 0.0, Y = sy != 0.0, Z = sz != 0.0;
-  Face F;
-  F.ax = (X || !stance) ? 0.0 : 1.0;
-  F.ay = (Y || !stance) ? 0.0 : 1.0;
-  F.dx = -sx * K.mu;
-  F.dy = -sy * K.mu;
-  F.kap = (Z || !stance) ? 0.0 : ((X && Y) ? K.k2 : ((X || Y) ? K.k1 : 1.0));
-  return F;
+// bit patterns of doubles (ordering tricks below): host and device
+QPB_HD int hi32(double x) {
+#if defined(__CUDA_ARCH__)
+  return __double2hiint(x);
+#else
+  uint64_t b;
+  memcpy(&b, &x, 8);
+  return (int)(b >> 32);
+#endif
+}
+QPB_HD double flip_sign(double x, bool flip) {  // flip ? -x : x, on the integer datapath
+#if defined(__CUDA_ARCH__)
+  return __hiloint2double(__double2hiint(x) ^ (flip ? (int)0x80000000 : 0), __double2loint(x));
+#else
+  return flip ? -x : x;
+#endif
 }
 
-QPB_HD void face_proj(const Face& F, const double (&g)[3], double (&o)[3]) {
-  const double dg = F.kap * fma(F.dx, g[0], fma(F.dy, g[1], g[2]));
-  o[0] = fma(F.ax, g[0], dg * F.dx);
-  o[1] = fma(F.ay, g[1], dg * F.dy);
+// Working set: one 24-bit word, 2 bits per (leg, group): 0 none, 1 row A, 2 row B, at bit 6 leg + 2 group.
+//   x rows (s, 0, mu), y rows (0, s, mu): A has s = -1 (-f + mu fz >= 0), B has s = +1 (f + mu fz >= 0)
+//   z rows (0, 0, s): A has s = +1 (fz >= fzmin), B has s = -1 (-fz >= -fzmax)
+// Face of one leg: tangent-space projector Pi = diag(!X, !Y, 0) + kap d d', d = (dx, dy, 1)  (X: an x row is active, ...).
+// A swing leg is pinned at zero: Pi = 0 and no rows.
+struct Leg {
+  bool X, Y;          // x / y component fixed by the face (or swing leg)
+  uint32_t cx, cy, cz;  // row codes
+  double dx, dy, kap;
+};
+
+// code 1 -> +mu, code 2 -> -mu, 0 -> 0  (= -s mu for the row's own coefficient s), on the integer datapath
+QPB_HD double signed_mu(const FastParams& K, uint32_t c) {
+#if defined(__CUDA_ARCH__)
+  const int m = c ? -1 : 0;
+  return __hiloint2double((__double2hiint(K.mu) & m) ^ (int)((c & 2u) << 30), __double2loint(K.mu) & m);
+#else
+  return c == 1u ? K.mu : (c == 2u ? -K.mu : 0.0);
+#endif
+}
+
+QPB_HD Leg leg_of(uint32_t codes /* word >> 6 leg */, bool stance, const FastParams& K) {
+  Leg L;
+  const uint32_t c = stance ? codes : 0u;
+  L.cx = c & 3u;
+  L.cy = (c >> 2) & 3u;
+  L.cz = (c >> 4) & 3u;
+  const bool ax = L.cx != 0u, ay = L.cy != 0u;
+  L.X = ax || !stance;
+  L.Y = ay || !stance;
+  L.dx = signed_mu(K, L.cx);
+  L.dy = signed_mu(K, L.cy);
+  const double k12 = (ax && ay) ? K.k2 : K.k1;
+  const double k01 = (ax || ay) ? k12 : 1.0;
+  L.kap = (L.cz != 0u || !stance) ? 0.0 : k01;
+  return L;
+}
+
+QPB_HD void leg_proj(const Leg& L, const double (&g)[3], double (&o)[3]) {
+  const double dg = L.kap * fma(L.dx, g[0], fma(L.dy, g[1], g[2]));
+  o[0] = L.X ? dg * L.dx : g[0];  // x free => dx = 0 => (Pi g)_x = g_x
+  o[1] = L.Y ? dg * L.dy : g[1];
   o[2] = dg;
 }
 
-// G += A_i Pi_i A_i' as three rank-one terms: ax a_x a_x' + ay a_y a_y' + kap (A_i d)(A_i d)',
+// normal of row (group g, code c) restricted to its leg, and its bound: n' f >= dp
+QPB_HD void row_normal(const FastParams& K, int g, uint32_t c, double (&n)[3], double& dp) {
+  const double s = (g < 2) == (c == 1u) ? -1.0 : 1.0;
+  n[0] = g == 0 ? s : 0.0;
+  n[1] = g == 1 ? s : 0.0;
+  n[2] = g == 2 ? s : K.mu;
+  dp = g == 2 ? (c == 1u ? K.fzmin : -K.fzmax) : 0.0;
+}
+
+// Multipliers of the active rows of one leg from h = N u:  (sx ux, sy uy, mu (ux + uy) + sz uz) = h
+QPB_HD void leg_multipliers(const FastParams& K, const Leg& L, const double (&h)[3], double (&o)[3]) {
+  o[0] = L.cx == 0u ? 0.0 : flip_sign(h[0], L.cx == 1u);
+  o[1] = L.cy == 0u ? 0.0 : flip_sign(h[1], L.cy == 1u);
+  const double t = h[2] - K.mu * (o[0] + o[1]);
+  o[2] = L.cz == 0u ? 0.0 : flip_sign(t, L.cz == 2u);
+}
+
+// G += c v v'  (packed lower triangle)
+QPB_HD void rank1(double (&G)[21], const double (&v)[6], double c) {
+  double cv[6];
+#pragma unroll
+  for (int i = 0; i < 6; i++) cv[i] = c * v[i];
+#pragma unroll
+  for (int i = 0; i < 6; i++)
+#pragma unroll
+    for (int j = 0; j < 6; j++)
+      if (j <= i) G[ix(i, j)] = fma(cv[i], v[j], G[ix(i, j)]);
+}
+
+// G += A_i Pi_i A_i' as three rank-one terms: !X a_x a_x' + !Y a_y a_y' + kap (A_i d)(A_i d)',
 // a_x = (1,0,0, 0, rz, -ry), a_y = (0,1,0, -rz, 0, rx), A_i d = (d, r x d).
-QPB_HD void add_leg(double (&G)[21], const Face& F, double rx, double ry, double rz) {
+QPB_HD void add_leg(double (&G)[21], const Leg& L, double rx, double ry, double rz) {
+  const double fx = L.X ? 0.0 : 1.0, fy = L.Y ? 0.0 : 1.0;
   {
-    const double a4 = F.ax * rz, a5 = -F.ax * ry;
-    G[ix(0, 0)] += F.ax;
+    const double a4 = fx * rz, a5 = -fx * ry;
+    G[ix(0, 0)] += fx;
     G[ix(4, 0)] += a4;
     G[ix(5, 0)] += a5;
     G[ix(4, 4)] = fma(a4, rz, G[ix(4, 4)]);
@@ -86,33 +157,20 @@ QPB_HD void add_leg(double (&G)[21], const Face& F, double rx, double ry, double
     G[ix(5, 5)] = fma(-a5, ry, G[ix(5, 5)]);
   }
   {
-    const double a3 = -F.ay * rz, a5 = F.ay * rx;
-    G[ix(1, 1)] += F.ay;
+    const double a3 = -fy * rz, a5 = fy * rx;
+    G[ix(1, 1)] += fy;
     G[ix(3, 1)] += a3;
     G[ix(5, 1)] += a5;
     G[ix(3, 3)] = fma(-a3, rz, G[ix(3, 3)]);
     G[ix(5, 3)] = fma(a3, rx, G[ix(5, 3)]);
     G[ix(5, 5)] = fma(a5, rx, G[ix(5, 5)]);
   }
-  {
-    double v[6], kv[6];
-    v[0] = F.dx;
-    v[1] = F.dy;
-    v[2] = 1.0;
-    v[3] = fma(-rz, F.dy, ry);
-    v[4] = fma(rz, F.dx, -rx);
-    v[5] = fma(rx, F.dy, -ry * F.dx);
-#pragma unroll
-    for (int i = 0; i < 6; i++) kv[i] = F.kap * v[i];
-#pragma unroll
-    for (int i = 0; i < 6; i++)
-#pragma unroll
-      for (int j = 0; j < 6; j++)
-        if (j <= i) G[ix(i, j)] = fma(kv[i], v[j], G[ix(i, j)]);
-  }
+  const double v[6] = { L.dx, L.dy, 1.0, fma(-rz, L.dy, ry), fma(rz, L.dx, -rx), fma(rx, L.dy, -ry * L.dx) };
+  rank1(G, v, L.kap);
 }
 
 // In-place Cholesky of the packed 6x6 matrix: G <- L (the diagonal holds 1 / L_jj).  False if not positive definite.
+// (Loops have constant trip counts with guards: the front end then keeps G in registers.)
 QPB_HD bool chol6(double (&G)[21]) {
   bool ok = true;
 #pragma unroll
@@ -164,34 +222,37 @@ QPB_HD void At_y(const double (&y)[6], double rx, double ry, double rz, double (
   g[1] = y[1] - (rz * y[3] - rx * y[5]);
   g[2] = y[2] - (rx * y[4] - ry * y[3]);
 }
+// v = A_i t = (t, r x t)
+QPB_HD void A_t(const double (&t)[3], double rx, double ry, double rz, double (&v)[6]) {
+  v[0] = t[0];
+  v[1] = t[1];
+  v[2] = t[2];
+  v[3] = ry * t[2] - rz * t[1];
+  v[4] = rz * t[0] - rx * t[2];
+  v[5] = rx * t[1] - ry * t[0];
+}
 
-// Solver state of one QP (registers on the device).
+// Solver state of one QP (registers on the device).  The 6x6 matrix G = w S^-1 + sum_i A_i Pi_i A_i' of the current
+// working set lives outside (per-lane shared memory on the device): it is loaded, factorised and rank-one updated
+// once per working-set change.
 struct State {
   double f[12];   // world-frame forces
   double u[12];   // multiplier of the active row of group g of leg i at 3 i + g
-  double sg[12];  // its sign (0 = group inactive)
   double r[12];   // lever arms R p_i
+  uint32_t word;  // working set (24 bits)
   uint32_t stance;  // bit i = leg i in contact
-  int p;          // row being added (3 leg + group), -1 = none pending
-  double ps;      // its sign
+  int p;          // row being added: 3 leg + group, -1 = none pending
+  uint32_t pc;    // its code (1 = A, 2 = B)
   double up;      // its multiplier so far
   int iters, status;
   bool done;
 };
 
-// Multipliers of the active rows of one leg from h = N u:  (sx ux, sy uy, mu (ux + uy) + sz uz) = h
-QPB_HD void leg_multipliers(const FastParams& K, const double* sg, const double (&h)[3], double (&o)[3]) {
-  o[0] = sg[0] * h[0];
-  o[1] = sg[1] * h[1];
-  o[2] = sg[2] * (h[2] - K.mu * (o[0] + o[1]));
-}
-
-// Minimiser on the faces st.sg: fills st.f and st.u.  False when the 6x6 system is not positive definite.
-QPB_HD bool face_solve(const FastParams& K, State& st, const double (&b6)[6]) {
-  double G[21];
+// Minimiser on the faces st.word: fills st.f, st.u and G (unfactorised).  False when G is not positive definite.
+QPB_HD bool face_solve(const FastParams& K, State& st, const double (&b6)[6], double (&G)[21]) {
 #pragma unroll
   for (int i = 0; i < 21; i++) G[i] = K.wSinv[i];
-  Face F[4];
+  Leg L[4];
   double pt[12];
   double rhs[6];
 #pragma unroll
@@ -199,99 +260,79 @@ QPB_HD bool face_solve(const FastParams& K, State& st, const double (&b6)[6]) {
 #pragma unroll
   for (int i = 0; i < 4; i++) {
     const bool stance = (st.stance >> i) & 1u;
-    F[i] = face_of(st.sg[3 * i], st.sg[3 * i + 1], st.sg[3 * i + 2], stance, K);
-    add_leg(G, F[i], st.r[3 * i], st.r[3 * i + 1], st.r[3 * i + 2]);
-    // a point of the face, then its component normal to the face
-    const double sz = st.sg[3 * i + 2];
-    const double cz = (sz == 0.0 || !stance) ? 0.0 : (sz > 0.0 ? K.fzmin : K.fzmax);
-    const double c[3] = { -st.sg[3 * i] * K.mu * cz, -st.sg[3 * i + 1] * K.mu * cz, cz };
-    double pc[3];
-    face_proj(F[i], c, pc);
-#pragma unroll
-    for (int k = 0; k < 3; k++) pt[3 * i + k] = stance ? c[k] - pc[k] : 0.0;
+    L[i] = leg_of(st.word >> (6 * i), stance, K);
     const double rx = st.r[3 * i], ry = st.r[3 * i + 1], rz = st.r[3 * i + 2];
-    rhs[0] += pt[3 * i];
-    rhs[1] += pt[3 * i + 1];
-    rhs[2] += pt[3 * i + 2];
-    rhs[3] += ry * pt[3 * i + 2] - rz * pt[3 * i + 1];
-    rhs[4] += rz * pt[3 * i] - rx * pt[3 * i + 2];
-    rhs[5] += rx * pt[3 * i + 1] - ry * pt[3 * i];
+    add_leg(G, L[i], rx, ry, rz);
+    // a point of the face (fz on its bound if a z row is active, x / y on the pyramid sides), then its component
+    // normal to the face
+    const double cz = L[i].cz == 0u ? 0.0 : (L[i].cz == 1u ? K.fzmin : K.fzmax);
+    const double c[3] = { L[i].dx * cz, L[i].dy * cz, cz };
+    double pc[3], v[6];
+    leg_proj(L[i], c, pc);
+#pragma unroll
+    for (int k = 0; k < 3; k++) pc[k] = c[k] - pc[k];
+    A_t(pc, rx, ry, rz, v);
+#pragma unroll
+    for (int k = 0; k < 3; k++) pt[3 * i + k] = pc[k];
+#pragma unroll
+    for (int k = 0; k < 6; k++) rhs[k] += v[k];
   }
-  const bool ok = chol6(G);
+  double Lc[21];
+#pragma unroll
+  for (int i = 0; i < 21; i++) Lc[i] = G[i];
+  const bool ok = chol6(Lc);
   double y[6];
 #pragma unroll
   for (int i = 0; i < 6; i++) y[i] = K.w * rhs[i];
-  chol6_solve(G, y);
+  chol6_solve(Lc, y);
 #pragma unroll
   for (int i = 0; i < 4; i++) {
     double g[3], pg[3], h[3], m[3];
     At_y(y, st.r[3 * i], st.r[3 * i + 1], st.r[3 * i + 2], g);
-    face_proj(F[i], g, pg);
+    leg_proj(L[i], g, pg);
 #pragma unroll
     for (int k = 0; k < 3; k++) {
       st.f[3 * i + k] = fma(-K.inv_w, pg[k], pt[3 * i + k]);
-      h[k] = 2.0 * fma(K.w, st.f[3 * i + k], g[k]);
+      h[k] = 2.0 * fma(K.w, pt[3 * i + k], g[k] - pg[k]);  // = 2 (g + w f): the component normal to the face
     }
-    leg_multipliers(K, st.sg + 3 * i, h, m);
+    leg_multipliers(K, L[i], h, m);
 #pragma unroll
     for (int k = 0; k < 3; k++) st.u[3 * i + k] = m[k];
   }
   return ok;
 }
 
-// Decode a 24-bit working-set word (2 bits per group: 0 none, 1 row A, 2 row B) into signs.
-QPB_HD void wset_decode(uint32_t word, uint32_t stance, double (&sg)[12]) {
+// keep only well-formed codes of stance legs (a hint is untrusted input)
+QPB_HD uint32_t wset_sanitize(uint32_t word, uint32_t stance) {
+  uint32_t out = 0;
 #pragma unroll
   for (int i = 0; i < 4; i++)
 #pragma unroll
     for (int g = 0; g < 3; g++) {
       const uint32_t c = (word >> (6 * i + 2 * g)) & 3u;
-      const bool st = (stance >> i) & 1u;
-      // A rows: -1 on x, y and +1 on z; B rows the opposite
-      const double sA = g < 2 ? -1.0 : 1.0;
-      sg[3 * i + g] = (!st || c == 0u || c == 3u) ? 0.0 : (c == 1u ? sA : -sA);
+      if (((stance >> i) & 1u) && c != 3u) out |= c << (6 * i + 2 * g);
     }
-}
-QPB_HD uint32_t wset_encode(const double (&sg)[12]) {
-  uint32_t word = 0;
-#pragma unroll
-  for (int i = 0; i < 4; i++)
-#pragma unroll
-    for (int g = 0; g < 3; g++) {
-      const double s = sg[3 * i + g];
-      const bool isA = g < 2 ? (s < 0.0) : (s > 0.0);
-      const uint32_t c = s == 0.0 ? 0u : (isA ? 1u : 2u);
-      word |= c << (6 * i + 2 * g);
-    }
-  return word;
+  return out;
 }
 
 // Start: minimiser on the hinted faces if that is a dual-feasible pair, else the unconstrained minimiser.
-QPB_HD void start(const FastParams& K, State& st, const double (&b6)[6], uint32_t hint, bool have_hint) {
+QPB_HD void start(const FastParams& K, State& st, const double (&b6)[6], uint32_t hint, bool have_hint, double (&G)[21]) {
   st.p = -1;
-  st.ps = 0.0;
+  st.pc = 0u;
   st.up = 0.0;
   st.iters = 0;
   st.status = QPB_OK;
   st.done = false;
-  bool warm = have_hint && (hint & 0xffffffu) != 0u;
-  if (warm) {
-    wset_decode(hint, st.stance, st.sg);
-  } else {
-#pragma unroll
-    for (int i = 0; i < 12; i++) st.sg[i] = 0.0;
-  }
+  st.word = have_hint ? wset_sanitize(hint, st.stance) : 0u;
   bool ok = true;
 #pragma unroll 1
   for (int attempt = 0; attempt < 2; attempt++) {  // a loop so that face_solve is emitted once
-    ok = face_solve(K, st, b6);
+    ok = face_solve(K, st, b6, G);
     bool feas = true;
 #pragma unroll
-    for (int i = 0; i < 12; i++) feas = feas && !(st.sg[i] != 0.0 && !(st.u[i] >= 0.0));
-    if (!warm || feas) break;
-    warm = false;  // the hinted faces are not a dual-feasible pair: cold start
-#pragma unroll
-    for (int i = 0; i < 12; i++) st.sg[i] = 0.0;
+    for (int i = 0; i < 12; i++) feas = feas && (st.u[i] >= 0.0);  // inactive groups carry u = 0
+    if (st.word == 0u || feas) break;
+    st.word = 0u;  // the hinted faces are not a dual-feasible pair: cold start
   }
   if (!ok) {
     st.status = QPB_BAD_INPUT;
@@ -305,7 +346,8 @@ QPB_HD void start(const FastParams& K, State& st, const double (&b6)[6], uint32_
 // that means the working set is not optimal and the QP is reported unsolved.
 QPB_HD void polish(const FastParams& K, State& st, const double (&b6)[6]) {
   if (st.status != QPB_OK) return;
-  const bool ok = face_solve(K, st, b6);
+  double G[21];
+  const bool ok = face_solve(K, st, b6, G);
   bool good = ok;
   const double zscale = 1.0 + fmax(fabs(K.fzmin), fabs(K.fzmax));
   double umax = 0.0;
@@ -319,144 +361,265 @@ QPB_HD void polish(const FastParams& K, State& st, const double (&b6)[6]) {
       const double loose = -1e-6 * (zscale + fabs(base));
       good = good && (base - fabs(fx) >= loose) && (base - fabs(fy) >= loose) && (fz - K.fzmin >= loose) && (K.fzmax - fz >= loose);
 #pragma unroll
-      for (int k = 0; k < 3; k++) good = good && (st.sg[3 * i + k] == 0.0 || st.u[3 * i + k] >= -1e-6 * umax);
+      for (int k = 0; k < 3; k++) good = good && (st.u[3 * i + k] >= -1e-6 * umax);
     }
   }
   if (!good) st.status = QPB_MAX_ITER;
 }
 
-// One working-set change of Goldfarb-Idnani (or the optimality test that ends the solve).
-QPB_HD void iterate(const FastParams& K, State& st) {
-  if (st.done) return;
-  // (1) most violated row, if no row is pending
-  if (st.p < 0) {
-    double best = 0.0;
-    int bidx = -1;
-    double bsgn = 0.0;
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-      const bool stance = (st.stance >> i) & 1u;
-      const double fx = st.f[3 * i], fy = st.f[3 * i + 1], fz = st.f[3 * i + 2];
-      const double base = K.mu * fz;
-      const double slx = base - fabs(fx), sly = base - fabs(fy);
-      const double sA = fz - K.fzmin, sB = K.fzmax - fz;
-      const double slz = fmin(sA, sB);
-      if (stance) {
-        if (st.sg[3 * i] == 0.0) {
-          if (slx < -1e-9 && slx < best) { best = slx; bidx = 3 * i; bsgn = fx > 0.0 ? -1.0 : 1.0; }
-        }  // (the other row of an active group can only be violated while fz < 0: the fz row of this leg goes first)
-        if (st.sg[3 * i + 1] == 0.0) {
-          if (sly < -1e-9 && sly < best) { best = sly; bidx = 3 * i + 1; bsgn = fy > 0.0 ? -1.0 : 1.0; }
-        }
-        if (st.sg[3 * i + 2] == 0.0) {
-          if (slz < K.ntol_z && slz < best) { best = slz; bidx = 3 * i + 2; bsgn = sA < sB ? 1.0 : -1.0; }
-        }
-      }
-    }
-    if (bidx < 0) {  // no inactive group is violated: the loop ends here (polish() re-checks every row)
-      st.done = true;
-      return;
-    }
-    st.p = bidx;
-    st.ps = bsgn;
-    st.up = 0.0;
-  }
-  if (st.iters >= K.max_iter) {
-    st.status = QPB_MAX_ITER;
-    st.done = true;
-    return;
-  }
-  st.iters++;
-  const int p = st.p;
-  const int pl = (p * 11) >> 5, pg = p - 3 * pl;  // leg and group of row p
-  const double n[3] = { pg == 0 ? st.ps : 0.0, pg == 1 ? st.ps : 0.0, pg == 2 ? st.ps : K.mu };
-  const double dp = pg == 2 ? (st.ps > 0.0 ? K.fzmin : -K.fzmax) : 0.0;  // row p: n' f >= dp
+// ---- the iteration loop, LPQ lanes per QP ---------------------------------------------------------------------------
+// A QP is iterated on by LPQ = 1, 2 or 4 lanes; each owns LPL = 4 / LPQ legs (their f and u).  Everything a lane needs of
+// the other legs is either replicated (lever arms, working-set word, pending row, G in shared memory) or crosses the
+// group at three exchange points per working-set change: the most violated row (one integer max), its slack (one sum),
+// the blocking row (one fraction min).  The 6x6 factorisation is redundant across the lanes of a QP; the per-leg work
+// is not.  With LPQ = 1 this is one thread per QP and the exchanges are the identity.
 
-  // (2) faces, G = w S^-1 + sum A_i Pi_i A_i', right-hand side (1/2) A_l Pi_l n
+template <int LPL>
+struct Lane {
+  double f[3 * LPL], u[3 * LPL];  // own legs: forces and multipliers (row of group g of own leg li at 3 li + g)
+  double r[3 * LPL];              // own legs: lever arms (all twelve also sit in the QP's side block, for the row's leg)
+  uint32_t word, stance;          // working set, contact mask (replicated, as is everything below)
+  int p;                          // row being added: 3 leg + group, -1 = none pending
+  uint32_t pc;                    // its code (1 = A, 2 = B)
+  double up, sp;                  // its multiplier so far, its slack n' f - bound (< 0 while pending)
+  int iters, status;
+  bool done;
+};
+
+// One lane's share of a solver state.  j = index of the lane within its QP.
+template <int LPL>
+QPB_HD void lane_init(Lane<LPL>& ln, int j, const double* f12, const double* r12, const double* u12, uint32_t word, uint32_t stance,
+                      int status) {
+#pragma unroll
+  for (int i = 0; i < 3 * LPL; i++) {
+    ln.f[i] = f12[3 * LPL * j + i];
+    ln.u[i] = u12[3 * LPL * j + i];
+    ln.r[i] = r12[3 * LPL * j + i];
+  }
+  ln.word = word;
+  ln.stance = stance;
+  ln.p = -1;
+  ln.pc = 0u;
+  ln.up = 0.0;
+  ln.sp = 0.0;
+  ln.iters = 0;
+  ln.status = status;
+  ln.done = status != QPB_OK;
+}
+
+// side block of a QP while it is iterated on (shared memory on the device): b (6), G (21), lever arms (12)
+enum : int { kSideB = 0, kSideG = 6, kSideR = 27, kSideSize = 39 };
+
+// Exchange 1 (integer max over the group): the most violated row among the groups that are not active.  Key: the high
+// word of (slack - tolerance) orders negative doubles by magnitude as an unsigned integer; low 5 bits = 3 leg + group,
+// + 16 for row B.  (The other row of an ACTIVE group can only be violated while fz < 0; the fz row of that leg then
+// goes first.)  0 from lanes that are not selecting.
+template <int LPL>
+QPB_HD uint32_t select_local(const FastParams& K, const Lane<LPL>& ln, int j) {
+  uint32_t best = 0u;
+#pragma unroll
+  for (int li = 0; li < LPL; li++) {
+    const int i = LPL * j + li;  // leg
+    const bool stance = (ln.stance >> i) & 1u;
+    const uint32_t c = ln.word >> (6 * i);
+    const double fx = ln.f[3 * li], fy = ln.f[3 * li + 1], fz = ln.f[3 * li + 2];
+    const double base = fma(K.mu, fz, 1e-9);
+    const double slx = base - fabs(fx), sly = base - fabs(fy);
+    const double sA = (fz - K.fzmin) - K.ntol_z, sB = (K.fzmax - fz) - K.ntol_z;
+    const uint32_t id = (uint32_t)(3 * i);
+    const uint32_t kx = ((uint32_t)hi32(slx) & ~31u) | id | (hi32(fx) < 0 ? 16u : 0u);  // fx > 0: row A binds
+    const uint32_t ky = ((uint32_t)hi32(sly) & ~31u) | (id + 1u) | (hi32(fy) < 0 ? 16u : 0u);
+    const uint32_t ka = ((uint32_t)hi32(sA) & ~31u) | (id + 2u);
+    const uint32_t kb = ((uint32_t)hi32(sB) & ~31u) | (id + 2u) | 16u;
+    const uint32_t mx = (stance && (c & 3u) == 0u) ? kx : 0u;
+    const uint32_t my = (stance && (c & 12u) == 0u) ? ky : 0u;
+    const uint32_t mz = (stance && (c & 48u) == 0u) ? (ka > kb ? ka : kb) : 0u;
+    const uint32_t m1 = mx > my ? mx : my;
+    const uint32_t m2 = m1 > mz ? m1 : mz;
+    best = best > m2 ? best : m2;
+  }
+  return (ln.done || ln.p >= 0) ? 0u : best;
+}
+
+// After exchange 1: take the row (or finish: nothing is violated).  Returns this lane's contribution to exchange 2
+// (a sum over the group): the exact slack of the new row, from the lane that owns its leg.
+template <int LPL>
+QPB_HD double select_commit(const FastParams& K, Lane<LPL>& ln, int j, uint32_t best, bool& fresh) {
+  fresh = false;
+  double contrib = 0.0;
+  if (!ln.done && ln.p < 0) {
+    if ((best >> 31) == 0u) {
+      ln.done = true;  // no inactive group is violated: the loop ends here (polish() re-checks every row)
+    } else {
+      fresh = true;
+      ln.p = (int)(best & 15u);
+      ln.pc = (best & 16u) ? 2u : 1u;
+      ln.up = 0.0;
+      const int pl = (ln.p * 11) >> 5, pg = ln.p - 3 * pl;
+      double n[3], dp;
+      row_normal(K, pg, ln.pc, n, dp);
+#pragma unroll
+      for (int li = 0; li < LPL; li++)
+        if (LPL * j + li == pl) contrib = (n[0] * ln.f[3 * li] + n[1] * ln.f[3 * li + 1] + n[2] * ln.f[3 * li + 2]) - dp;
+    }
+  }
+  return contrib;
+}
+
+template <int LPL>
+struct StepTmp {
+  double z[3 * LPL], rr[3 * LPL];
+  double a[6];
+  double zeta0, zeta;
+  bool act;
+};
+
+// Between exchanges 2 and 3: step direction on the own legs, multiplier directions, and the own candidate for the
+// blocking row as a fraction ub / rb (rb = 0: none), kb = 3 leg + group.
+template <int LPL>
+QPB_HD void direction(const FastParams& K, Lane<LPL>& ln, int j, const double* side, StepTmp<LPL>& T, double& ub, double& rb, int& kb) {
+  const double* Gs = side + kSideG;
+  if (!ln.done && ln.iters >= K.max_iter) {
+    ln.status = QPB_MAX_ITER;
+    ln.done = true;
+  }
+  T.act = !ln.done;
+  if (T.act) ln.iters++;
+  const int p = T.act ? ln.p : 0;
+  const int pl = (p * 11) >> 5, pg = p - 3 * pl;  // leg and group of row p
+  double n[3], dp;
+  row_normal(K, pg, T.act ? ln.pc : 1u, n, dp);
+  // tangential part tn of n on the face of leg pl; a = A_pl tn
+  double tn[3];
+  {
+    const double rx = side[kSideR + 3 * pl], ry = side[kSideR + 3 * pl + 1], rz = side[kSideR + 3 * pl + 2];
+    const Leg Lp = leg_of(ln.word >> (6 * pl), (ln.stance >> pl) & 1u, K);
+    leg_proj(Lp, n, tn);
+    A_t(tn, rx, ry, rz, T.a);
+  }
+  T.zeta0 = n[0] * tn[0] + n[1] * tn[1] + n[2] * tn[2];  // > 0: one row per group is always independent
+  // G yh = a / 2
   double G[21];
 #pragma unroll
-  for (int i = 0; i < 21; i++) G[i] = K.wSinv[i];
-  Face F[4];
-  double tn[3] = { 0.0, 0.0, 0.0 };
-  double yh[6] = { 0.0, 0.0, 0.0, 0.0, 0.0, 0.0 };
-  double sp = -dp;
-#pragma unroll
-  for (int i = 0; i < 4; i++) {
-    const bool stance = (st.stance >> i) & 1u;
-    F[i] = face_of(st.sg[3 * i], st.sg[3 * i + 1], st.sg[3 * i + 2], stance, K);
-    const double rx = st.r[3 * i], ry = st.r[3 * i + 1], rz = st.r[3 * i + 2];
-    add_leg(G, F[i], rx, ry, rz);
-    if (i == pl) {
-      face_proj(F[i], n, tn);
-      yh[0] = 0.5 * tn[0];
-      yh[1] = 0.5 * tn[1];
-      yh[2] = 0.5 * tn[2];
-      yh[3] = 0.5 * (ry * tn[2] - rz * tn[1]);
-      yh[4] = 0.5 * (rz * tn[0] - rx * tn[2]);
-      yh[5] = 0.5 * (rx * tn[1] - ry * tn[0]);
-      sp += n[0] * st.f[3 * i] + n[1] * st.f[3 * i + 1] + n[2] * st.f[3 * i + 2];
-    }
-  }
+  for (int i = 0; i < 21; i++) G[i] = Gs[i];
   const bool pd = chol6(G);
+  double yh[6];
+#pragma unroll
+  for (int i = 0; i < 6; i++) yh[i] = 0.5 * T.a[i];
   chol6_solve(G, yh);
-
-  // (3) step direction z, its curvature zeta = n' z, multiplier directions r, blocking row
-  double z[12], rr[12];
-  double zeta = 0.0;
-  double ub = 1.0, rb = 0.0;  // best ratio so far as a fraction ub / rb (rb = 0: none)
-  int kb = -1;
+  // curvature along the step: zeta = n' z = (zeta0 - 2 a' yh) / (2 w)
+  double ayh = 0.0;
 #pragma unroll
-  for (int i = 0; i < 4; i++) {
+  for (int i = 0; i < 6; i++) ayh = fma(T.a[i], yh[i], ayh);
+  const double hw = 0.5 * K.inv_w;
+  T.zeta = hw * fma(-2.0, ayh, T.zeta0);
+  if (T.act && (!pd || !(T.zeta > 0.0) || !(T.zeta0 > 0.0))) {  // cannot happen within the face family
+    ln.status = QPB_MAX_ITER;
+    ln.done = true;
+    T.act = false;
+  }
+  // own legs: z_i = (1/w) (tn / 2 [i = pl] - Pi_i A_i' yh), N r = n [i = pl] - Q z; blocking candidate
+  ub = 1.0;
+  rb = 0.0;
+  kb = -1;
+#pragma unroll
+  for (int li = 0; li < LPL; li++) {
+    const int i = LPL * j + li;
+    const Leg L = leg_of(ln.word >> (6 * i), (ln.stance >> i) & 1u, K);
     double g[3], pgv[3], h[3], m[3];
-    At_y(yh, st.r[3 * i], st.r[3 * i + 1], st.r[3 * i + 2], g);
-    face_proj(F[i], g, pgv);
-    const double ci = (i == pl) ? 1.0 : 0.0;
+    At_y(yh, ln.r[3 * li], ln.r[3 * li + 1], ln.r[3 * li + 2], g);
+    leg_proj(L, g, pgv);
+    const bool me = i == pl;
 #pragma unroll
     for (int k = 0; k < 3; k++) {
-      z[3 * i + k] = K.inv_w * fma(0.5 * ci, tn[k], -pgv[k]);
-      h[k] = fma(ci, n[k], -2.0 * fma(K.w, z[3 * i + k], g[k]));
+      const double zk = -K.inv_w * pgv[k];
+      T.z[3 * li + k] = me ? fma(hw, tn[k], zk) : zk;
+      const double hk = -2.0 * (g[k] - pgv[k]);  // the component of -2 A' yh normal to the face
+      h[k] = me ? hk + (n[k] - tn[k]) : hk;
     }
-    zeta += ci * (n[0] * z[3 * i] + n[1] * z[3 * i + 1] + n[2] * z[3 * i + 2]);
-    leg_multipliers(K, st.sg + 3 * i, h, m);
+    leg_multipliers(K, L, h, m);
 #pragma unroll
     for (int k = 0; k < 3; k++) {
-      rr[3 * i + k] = m[k];
-      const double uu = st.u[3 * i + k] > 0.0 ? st.u[3 * i + k] : 0.0;  // rounding can leave -1e-17
-      const bool cand = st.sg[3 * i + k] != 0.0 && m[k] > 0.0;
-      if (cand && uu * rb < ub * m[k]) {  // uu / m[k] < ub / rb
-        ub = uu;
+      T.rr[3 * li + k] = m[k];
+      const bool cand = hi32(m[k]) > 0 && ln.u[3 * li + k] * rb < ub * m[k];  // m > 0 and u / m < ub / rb
+      if (cand) {
+        ub = ln.u[3 * li + k];
         rb = m[k];
         kb = 3 * i + k;
       }
     }
   }
-  if (!pd || !(zeta > 0.0)) {  // cannot happen within the face family (G is positive definite, n is independent)
-    st.status = QPB_MAX_ITER;
-    st.done = true;
-    return;
+  if (!T.act) {
+    rb = 0.0;
+    kb = -1;
   }
+}
+
+// combine two blocking candidates (exchange 3 is a reduction with this operator)
+QPB_HD void better_ratio(double& ub, double& rb, int& kb, double ub2, double rb2, int kb2) {
+  if (hi32(rb2) > 0 && ub2 * rb < ub * rb2) {
+    ub = ub2;
+    rb = rb2;
+    kb = kb2;
+  }
+}
+
+// After exchange 3: step, working-set change, rank-one update of G.  store_G: this lane writes G back (one per QP).
+template <int LPL>
+QPB_HD void advance(const FastParams& K, Lane<LPL>& ln, int j, double* side, const StepTmp<LPL>& T, double ub, double rb, int kb,
+                    bool store_G) {
+  double* Gs = side + kSideG;
   const bool has1 = kb >= 0;
   const double t1 = has1 ? ub * rcp_fast(rb) : 0.0;
-  const double t2 = -sp * rcp_fast(zeta);
+  const double t2 = -ln.sp * rcp_fast(T.zeta);
   const bool full = !has1 || t2 <= t1;
-  const double t = full ? t2 : t1;
-  // (4) step
+  const double t = T.act ? (full ? t2 : t1) : 0.0;
 #pragma unroll
-  for (int i = 0; i < 12; i++) {
-    st.f[i] = fma(t, z[i], st.f[i]);
-    st.u[i] = fma(-t, rr[i], st.u[i]);
+  for (int i = 0; i < 3 * LPL; i++) {
+    ln.f[i] = fma(t, T.z[i], ln.f[i]);
+    ln.u[i] = fma(-t, T.rr[i], ln.u[i]);
   }
-  st.up += t;
-  // (5) working-set change: row p enters (full step) or the blocking row leaves (partial step)
-  const int idx = full ? p : kb;
-  const double sv = full ? st.ps : 0.0, uv = full ? st.up : 0.0;
+  ln.up += t;
+  ln.sp = fma(t, T.zeta, ln.sp);  // the slack of row p grows by t zeta
+  // working-set change: row p enters (full step) or the blocking row leaves (partial step); G follows by a rank-one
+  // update with v = A t, t = the row's normal projected on the face WITHOUT that row:  G -+= v v' / (n' t)
+  const int p = ln.p < 0 ? 0 : ln.p;
+  const int idx = full ? p : (has1 ? kb : 0);
+  double v[6], cc;
 #pragma unroll
-  for (int i = 0; i < 12; i++)
-    if (i == idx) {
-      st.sg[i] = sv;
-      st.u[i] = uv;
+  for (int i = 0; i < 6; i++) v[i] = T.a[i];
+  cc = -rcp_fast(T.zeta0);
+  uint32_t word = ln.word;
+  if (full) {
+    word |= ln.pc << (2 * p);
+  } else {
+    const int kl = (idx * 11) >> 5, kg = idx - 3 * kl;
+    const uint32_t kc = (word >> (2 * idx)) & 3u;
+    word &= ~(3u << (2 * idx));
+    double nk[3], dk, tk[3];
+    row_normal(K, kg, kc, nk, dk);
+    const double rx = side[kSideR + 3 * kl], ry = side[kSideR + 3 * kl + 1], rz = side[kSideR + 3 * kl + 2];
+    const Leg Lk = leg_of(word >> (6 * kl), true, K);
+    leg_proj(Lk, nk, tk);
+    A_t(tk, rx, ry, rz, v);
+    cc = rcp_fast(nk[0] * tk[0] + nk[1] * tk[1] + nk[2] * tk[2]);
+  }
+  if (T.act) {
+    ln.word = word;
+    const double uv = full ? ln.up : 0.0;
+#pragma unroll
+    for (int i = 0; i < 3 * LPL; i++)
+      if (3 * LPL * j + i == idx) ln.u[i] = uv;
+    if (full) ln.p = -1;
+    double G[21];
+#pragma unroll
+    for (int i = 0; i < 21; i++) G[i] = Gs[i];
+    rank1(G, v, cc);
+    if (store_G) {
+#pragma unroll
+      for (int i = 0; i < 21; i++) Gs[i] = G[i];
     }
-  if (full) st.p = -1;
+  }
 }
 
 // ---- whole-record wrappers: what one thread does before and after the iteration loop ----------------------------
@@ -469,7 +632,7 @@ QPB_HD uint32_t stance_mask(uint32_t cbytes) {
 // rec: slots 0..47 of the state record (attitudes, twists, feet).  hint: bit 31 set = bits 0..23 hold a working set.
 template <class Params>
 QPB_HD void setup(const Params& P, const FastParams& K, const double* rec, uint32_t cbytes, uint32_t hint, State& st,
-                  double (&b6)[6]) {
+                  double (&b6)[6], double (&G)[21]) {
   st.stance = stance_mask(cbytes);
   bool fin = true;
 #pragma unroll
@@ -489,7 +652,7 @@ QPB_HD void setup(const Params& P, const FastParams& K, const double* rec, uint3
 #pragma unroll
     for (int i = 0; i < 6; i++) b6[i] = 0.0;
   }
-  start(K, st, b6, hint, (hint >> 31) != 0u);
+  start(K, st, b6, hint, (hint >> 31) != 0u, G);
   if (!fin) {
     st.status = QPB_BAD_INPUT;
     st.done = true;
@@ -501,7 +664,8 @@ QPB_HD void setup(const Params& P, const FastParams& K, const double* rec, uint3
 template <class Params>
 QPB_HD void finish(const Params& P, const double* R, const double* q, const State& st, double (&grf)[12], double (&tau)[12]) {
   const bool good = st.status == QPB_OK;
-#pragma unroll
+  const bool qok = st.status != QPB_BAD_INPUT;
+#pragma unroll 1  // one copy of the three sincos expansions instead of four: this runs once per QP, code size matters more
   for (int i = 0; i < 4; i++) {
     const bool on = good && ((st.stance >> i) & 1u);
     const double f0 = st.f[3 * i], f1 = st.f[3 * i + 1], f2 = st.f[3 * i + 2];
@@ -509,7 +673,6 @@ QPB_HD void finish(const Params& P, const double* R, const double* q, const Stat
 #pragma unroll
     for (int k = 0; k < 3; k++) fb[k] = on ? -1.0 * (R[k] * f0 + R[3 + k] * f1 + R[6 + k] * f2) : 0.0;
     double s1, c1, s2, c2, s23, c23;
-    const bool qok = st.status != QPB_BAD_INPUT;
     sincos(qok ? q[3 * i] : 0.0, &s1, &c1);
     sincos(qok ? q[3 * i + 1] : 0.0, &s2, &c2);
     sincos(qok ? q[3 * i + 1] + q[3 * i + 2] : 0.0, &s23, &c23);

@@ -1,16 +1,62 @@
 // Host build of the thread-per-QP solver core (quadruped_control_b200/csrc/qpb_tpq_core.h) for the CPU tests:
 // the same source the CUDA kernel compiles, run one QP at a time, so the algorithm can be checked against the oracle
-// without a GPU.  TEST INFRASTRUCTURE ONLY: nothing in the product library links or loads this.
+// without a GPU.  The LPQ lanes that share a QP on the device are stepped here in lock step, and the three warp
+// exchanges of the kernel (integer max, sum, fraction min over the lanes of a QP) are plain loops.
+// TEST INFRASTRUCTURE ONLY: nothing in the product library links or loads this.
 #include <cstdint>
 #include <cstring>
 
 #include "../../quadruped_control_b200/csrc/qpb_tpq_core.h"
 
+using namespace qpb::tpq;
 
+template <int LPQ>
+static void solve_loop(const FastParams& K, State& st, const double* G0) {
+  double side[kSideSize] = {};
+  std::memcpy(side + kSideG, G0, 21 * sizeof(double));
+  std::memcpy(side + kSideR, st.r, 12 * sizeof(double));
+  double* G = side + kSideG;
+  constexpr int LPL = 4 / LPQ;
+  Lane<LPL> ln[LPQ];
+  for (int j = 0; j < LPQ; j++) lane_init(ln[j], j, st.f, st.r, st.u, st.word, st.stance, st.status);
+  while (!ln[0].done) {
+    uint32_t best = 0;
+    for (int j = 0; j < LPQ; j++) {
+      const uint32_t k = select_local(K, ln[j], j);
+      best = k > best ? k : best;
+    }
+    double slack = 0.0;
+    bool fresh[LPQ];
+    for (int j = 0; j < LPQ; j++) slack += select_commit(K, ln[j], j, best, fresh[j]);
+    for (int j = 0; j < LPQ; j++)
+      if (fresh[j]) ln[j].sp = slack;
+    StepTmp<LPL> T[LPQ];
+    double ub = 1.0, rb = 0.0;
+    int kb = -1;
+    for (int j = 0; j < LPQ; j++) {
+      double u1, r1;
+      int k1;
+      direction(K, ln[j], j, side, T[j], u1, r1, k1);
+      if (j == 0) { ub = u1; rb = r1; kb = k1; }
+      else better_ratio(ub, rb, kb, u1, r1, k1);
+    }
+    double Gnew[21];
+    std::memcpy(Gnew, G, sizeof(Gnew));
+    for (int j = 0; j < LPQ; j++) {  // every lane reads the old G; one writes the new one
+      double sj[kSideSize];
+      std::memcpy(sj, side, sizeof(sj));
+      advance(K, ln[j], j, sj, T[j], ub, rb, kb, true);
+      if (j == 0) std::memcpy(Gnew, sj + kSideG, sizeof(Gnew));
+    }
+    std::memcpy(G, Gnew, sizeof(Gnew));
+  }
+  st.word = ln[0].word;
+  st.status = ln[0].status;
+  st.iters = ln[0].iters;
+}
 
 extern "C" int tpq_host_control_batch(const qpb_params* P, const qpb_state_rec* in, int64_t n, qpb_out_rec* out,
-                                      double* fw /* n x 12 world-frame or null */, int do_polish) {
-  using namespace qpb::tpq;
+                                      int lpq /* lanes per QP: 1, 2 or 4 */, int do_polish) {
   FastParams K;
   if (!make_fast_params(*P, K)) return -1;
   for (int64_t i = 0; i < n; i++) {
@@ -19,9 +65,11 @@ extern "C" int tpq_host_control_batch(const qpb_params* P, const qpb_state_rec* 
     std::memcpy(&cbytes, in[i].contact, 4);
     std::memcpy(&hint, in[i].pad, 4);
     State st;
-    double b6[6];
-    setup(*P, K, rec, cbytes, hint, st, b6);
-    while (!st.done) iterate(K, st);
+    double b6[6], G[21];
+    setup(*P, K, rec, cbytes, hint, st, b6, G);
+    if (lpq == 4) solve_loop<4>(K, st, G);
+    else if (lpq == 2) solve_loop<2>(K, st, G);
+    else solve_loop<1>(K, st, G);
     if (do_polish) polish(K, st, b6);
     double grf[12], tau[12];
     finish(*P, rec, rec + qpb::kQ, st, grf, tau);
@@ -30,9 +78,8 @@ extern "C" int tpq_host_control_batch(const qpb_params* P, const qpb_state_rec* 
     std::memcpy(out[i].tau, tau, sizeof(tau));
     out[i].status = st.status;
     out[i].iters = st.iters;
-    const uint32_t word = wset_encode(st.sg) | 0x80000000u;
+    const uint32_t word = st.word | 0x80000000u;
     std::memcpy(out[i].pad, &word, 4);
-    if (fw) std::memcpy(fw + 12 * i, st.f, sizeof(st.f));
   }
   return 0;
 }

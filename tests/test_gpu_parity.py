@@ -96,7 +96,7 @@ def test_three_entry_points_agree(solver06, params06):
     torch.cuda.synchronize()
     packed = d_out.cpu().numpy().view(OUT_DTYPE)
     assert packed.tobytes() == host.tobytes()
-    assert not packed["pad"].any()
+    assert not packed["pad"][:, 4:].any()  # pad[0:4] carries the final working set (the warm-start word)
     dev = {k: torch.from_numpy(np.ascontiguousarray(S[k])).cuda() for k in
            ("Rwb", "Rwb_d", "x", "xdot", "w", "x_d", "xdot_d", "w_d", "feet", "contact", "q")}
     grf = torch.zeros(n, 12, dtype=torch.float64, device="cuda")

@@ -27,19 +27,19 @@ def host():
     if not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(d) for d in deps):
         subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", LIB, SRC], check=True)
     L = ctypes.CDLL(LIB)
-    L.tpq_host_control_batch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+    L.tpq_host_control_batch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
 
-    def run(params, S, polish=1):
+    def run(params, S, lpq=2, polish=1):
         S = np.ascontiguousarray(S)
         out = np.zeros(len(S), dtype=OUT_DTYPE)
-        rc = L.tpq_host_control_batch(ctypes.byref(params), S.ctypes.data, len(S), out.ctypes.data, None, polish)
+        rc = L.tpq_host_control_batch(ctypes.byref(params), S.ctypes.data, len(S), out.ctypes.data, lpq, polish)
         return rc, out
 
     return run
 
 
-def _check(run, params, S, tol):
-    rc, out = run(params, S)
+def _check(run, params, S, tol, lpq=2):
+    rc, out = run(params, S, lpq)
     assert rc == 0
     ref = oracle.control_batch(params, S, NCPU)
     assert np.array_equal(out["status"], ref["status"])
@@ -54,6 +54,17 @@ def test_core_matches_oracle(host, params06, profile, masks):
     S = states.generate_states(6000, 20260102 if masks == "all4" else 20260103, profile=profile, masks=masks)
     out, ref = _check(host, params06, S, 1e-7)
     assert out["iters"].max() < 64
+
+
+def test_lanes_per_qp_are_the_same_algorithm(host, params06):
+    """One, two or four lanes per QP (the kernel's template parameter) only distribute the legs: working sets,
+    iteration counts and results must be identical."""
+    S = states.generate_states(3000, 20260103, profile="stress", masks="mixed")
+    outs = [host(params06, S, lpq)[1] for lpq in (1, 2, 4)]
+    for o in outs[1:]:
+        assert o.tobytes() == outs[0].tobytes()
+    _check(host, params06, S, 1e-7, lpq=4)
+    _check(host, params06, S, 1e-7, lpq=1)
 
 
 def test_core_config1_and_every_contact_mask(host, params06, params08):
