@@ -61,6 +61,7 @@ constexpr int64_t kHostChunkMax = 16384;  // capacity of a pipeline stage (8 MiB
 constexpr int64_t kMaxRecordsPerLaunch = (int64_t)1 << 31;  // the kernels index work items with 32 bits
 constexpr uint32_t kTicketSlots = 4096;  // ring of {work counter, CTAs finished} pairs; the kernels re-arm their own pair
 constexpr int64_t kSmallCall = 128;      // host calls up to this many robots go through one pinned, mapped staging block
+constexpr int64_t kTpqChunk = (int64_t)1 << 20;  // records per set-up / loop / finish triple (512 MiB of scratch)
 constexpr size_t kSmallBytes = (size_t)kSmallCall * 1536;  // states + results + swing records (or the kinematics arrays)
 
 }  // namespace
@@ -77,7 +78,8 @@ struct qpb_handle {
   // at qpb_create time overrides the choice (32 is refused when the parameters do not qualify).
   int qps_per_warp = 2;
   int ctas_per_sm_tpq[5] = {};  // indexed by lanes per QP (1, 2, 4)
-  int tpq_lpq = 2;              // lanes per QP of the thread-per-QP kernel family (QPB_TPQ_LPQ=1|2|4 overrides)
+  int tpq_lpq = 2;              // lanes per QP of the range-space loop kernel (QPB_TPQ_LPQ=1|2|4 overrides)
+  int64_t tpq_min_n = 4096;     // smaller batches take the half-warp kernel: one launch, lower latency (QPB_TPQ_MIN_N)
   qpb::tpq::FastParams fast;
   qpb_params params;
   qpb_params* d_params = nullptr;
@@ -114,31 +116,54 @@ struct DeviceGuard {
   }
 };
 
+inline qpb::PackedIO offset_io(const qpb::PackedIO& io, int64_t lo) { return qpb::PackedIO{ io.in + lo, io.out + lo }; }
+inline qpb::SplitIO offset_io(const qpb::SplitIO& io, int64_t lo) {
+  return qpb::SplitIO{ io.Rwb + 9 * lo, io.Rwb_d + 9 * lo, io.x + 3 * lo, io.xdot + 3 * lo, io.w + 3 * lo, io.x_d + 3 * lo,
+                       io.xdot_d + 3 * lo, io.w_d + 3 * lo, io.feet + 12 * lo, io.q + 12 * lo, io.contact + 4 * lo,
+                       io.grf + 12 * lo, io.tau ? io.tau + 12 * lo : nullptr, io.status ? io.status + lo : nullptr };
+}
+
 template <class IO>
 int launch_balance(qpb_handle* h, const IO& io, int64_t n, int ctas_per_sm, cudaStream_t stream) {
   if (n == 0) return QPB_SUCCESS;
   if (n > kMaxRecordsPerLaunch) return fail(QPB_ERR_INVALID_ARG, "more than 2^31 records in one call: split the batch");
-  const int per_warp = h->qps_per_warp;  // 1: one warp per QP; 2: two QPs per warp (half-warp kernel); 32: one thread per QP
+  int per_warp = h->qps_per_warp;  // 1: one warp per QP; 2: two QPs per warp (half-warp kernel); 32: range-space path
   // Launch i draws its work tickets from pair i % R of the ring; the last CTA of a launch re-arms the pair, so a launch
   // is self-contained (safe under CUDA-graph replay) as long as fewer than R = 4096 launches of a handle are in flight.
   const uint32_t slot = h->ticket_slot.fetch_add(1, std::memory_order_relaxed) % kTicketSlots;
-  unsigned long long* t0 = h->d_tickets + 2 * (size_t)slot;
-  if (per_warp == 32) {
+  unsigned long long* t0 = h->d_tickets + 4 * (size_t)slot;  // {work ticket, CTAs finished, worklist entries, -}
+  if (per_warp == 32 && n >= h->tpq_min_n) {
+    // Three passes over scratch memory (qpb_tpq.cuh): set-up -> prepared records, the active-set loop, polish + epilogue.
+    // The scratch comes from the stream-ordered allocator, so concurrent calls on different streams never share it.
     const int lpq = h->tpq_lpq;
-    const int warps = lpq == 1 ? qpb::tpq::Shape<1>::W : (lpq == 2 ? qpb::tpq::Shape<2>::W : qpb::tpq::Shape<4>::W);
-    const int64_t want = (n + 32 * warps - 1) / (32 * warps);  // a CTA with fewer than 32 records per warp would idle
-    const int64_t cap = (int64_t)h->num_sms * h->ctas_per_sm_tpq[lpq];
-    const int grid = (int)(want < cap ? want : cap);
-    if (lpq == 1)
-      qpb::tpq::balance_qp_tpq_kernel<IO, 1><<<grid, warps * 32, 0, stream>>>(h->params, h->fast, io, n, t0);
-    else if (lpq == 4)
-      qpb::tpq::balance_qp_tpq_kernel<IO, 4><<<grid, warps * 32, 0, stream>>>(h->params, h->fast, io, n, t0);
-    else
-      qpb::tpq::balance_qp_tpq_kernel<IO, 2><<<grid, warps * 32, 0, stream>>>(h->params, h->fast, io, n, t0);
-    h->launches.fetch_add(1, std::memory_order_relaxed);
-    QPB_CUDA(cudaGetLastError());
+    for (int64_t lo = 0; lo < n; lo += kTpqChunk) {
+      const int64_t m = n - lo < kTpqChunk ? n - lo : kTpqChunk;
+      const IO part = offset_io(io, lo);
+      double* prep = nullptr;  // m prepared records, then the worklist of the loop pass (m record indices)
+      const size_t prep_bytes = (size_t)m * qpb::tpq::kPrepSize * sizeof(double);
+      QPB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&prep), prep_bytes + (size_t)m * sizeof(uint32_t), stream));
+      uint32_t* work = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(prep) + prep_bytes);
+      const uint32_t slot2 = lo == 0 ? slot : h->ticket_slot.fetch_add(1, std::memory_order_relaxed) % kTicketSlots;
+      unsigned long long* tk = h->d_tickets + 4 * (size_t)slot2;
+      const unsigned edge = (unsigned)((m + qpb::tpq::kEdgeThreads - 1) / qpb::tpq::kEdgeThreads);
+      qpb::tpq::tpq_setup_kernel<IO><<<edge, qpb::tpq::kEdgeThreads, 0, stream>>>(h->params, h->fast, part, m, prep, work, tk);
+      const int64_t want = (m * lpq + qpb::tpq::kLoopThreads - 1) / qpb::tpq::kLoopThreads;
+      const int64_t cap = (int64_t)h->num_sms * h->ctas_per_sm_tpq[lpq];
+      const int grid = (int)(want < cap ? want : cap);
+      if (lpq == 1)
+        qpb::tpq::tpq_loop_kernel<1><<<grid, qpb::tpq::kLoopThreads, 0, stream>>>(h->fast, prep, work, tk);
+      else if (lpq == 2)
+        qpb::tpq::tpq_loop_kernel<2><<<grid, qpb::tpq::kLoopThreads, 0, stream>>>(h->fast, prep, work, tk);
+      else
+        qpb::tpq::tpq_loop_kernel<4><<<grid, qpb::tpq::kLoopThreads, 0, stream>>>(h->fast, prep, work, tk);
+      qpb::tpq::tpq_finish_kernel<IO><<<edge, qpb::tpq::kEdgeThreads, 0, stream>>>(h->params, h->fast, part, m, prep);
+      h->launches.fetch_add(3, std::memory_order_relaxed);
+      QPB_CUDA(cudaGetLastError());
+      QPB_CUDA(cudaFreeAsync(prep, stream));
+    }
     return QPB_SUCCESS;
   }
+  if (per_warp == 32) per_warp = 2;  // small batches: the half-warp kernel has the lower latency (one launch, 16 lanes per QP)
   const int64_t units = (n + per_warp - 1) / per_warp;
   const int64_t want = (units + qpb::WARPS_PER_CTA - 1) / qpb::WARPS_PER_CTA;
   const int64_t cap = (int64_t)h->num_sms * (per_warp == 2 ? h->ctas_per_sm_16 : ctas_per_sm);
@@ -336,8 +361,8 @@ int qpb_create(const qpb_params* params, int device, qpb_handle** out) {
     qpb_default_plan_params(&pp);
     e = cudaMemcpy(h->d_plan, &pp, sizeof(pp), cudaMemcpyHostToDevice);
   }
-  if (e == cudaSuccess) e = cudaMalloc(&h->d_tickets, 2 * kTicketSlots * sizeof(unsigned long long));
-  if (e == cudaSuccess) e = cudaMemset(h->d_tickets, 0, 2 * kTicketSlots * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMalloc(&h->d_tickets, 4 * kTicketSlots * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMemset(h->d_tickets, 0, 4 * kTicketSlots * sizeof(unsigned long long));
   if (e == cudaSuccess)
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->ctas_per_sm_packed, qpb::balance_qp_kernel<qpb::PackedIO>,
                                                       qpb::WARPS_PER_CTA * 32, 0);
@@ -351,15 +376,17 @@ int qpb_create(const qpb_params* params, int device, qpb_handle** out) {
       e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, qpb::balance_qp_kernel16<qpb::SplitIO>, qpb::WARPS_PER_CTA * 32, 0);
     h->ctas_per_sm_16 = a < b ? a : b;
   }
-  auto tpq_occ = [&](auto kp, auto ks, int lpq, int warps) {
-    int a = 0, b = 0;
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, kp, warps * 32, 0);
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, ks, warps * 32, 0);
-    h->ctas_per_sm_tpq[lpq] = a < b ? a : b;
-  };
-  tpq_occ(qpb::tpq::balance_qp_tpq_kernel<qpb::PackedIO, 1>, qpb::tpq::balance_qp_tpq_kernel<qpb::SplitIO, 1>, 1, qpb::tpq::Shape<1>::W);
-  tpq_occ(qpb::tpq::balance_qp_tpq_kernel<qpb::PackedIO, 2>, qpb::tpq::balance_qp_tpq_kernel<qpb::SplitIO, 2>, 2, qpb::tpq::Shape<2>::W);
-  tpq_occ(qpb::tpq::balance_qp_tpq_kernel<qpb::PackedIO, 4>, qpb::tpq::balance_qp_tpq_kernel<qpb::SplitIO, 4>, 4, qpb::tpq::Shape<4>::W);
+  if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->ctas_per_sm_tpq[1], qpb::tpq::tpq_loop_kernel<1>, qpb::tpq::kLoopThreads, 0);
+  if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->ctas_per_sm_tpq[2], qpb::tpq::tpq_loop_kernel<2>, qpb::tpq::kLoopThreads, 0);
+  if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->ctas_per_sm_tpq[4], qpb::tpq::tpq_loop_kernel<4>, qpb::tpq::kLoopThreads, 0);
+  if (e == cudaSuccess) {  // keep freed scratch in the stream-ordered pool instead of returning it to the OS after every call
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      unsigned long long keep = ~0ULL;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    (void)cudaGetLastError();
+  }
   if (e != cudaSuccess || h->ctas_per_sm_packed < 1 || h->ctas_per_sm_split < 1 || h->ctas_per_sm_16 < 1 ||
       h->ctas_per_sm_tpq[1] < 1 || h->ctas_per_sm_tpq[2] < 1 || h->ctas_per_sm_tpq[4] < 1) {
     const std::string msg = std::string("qpb_create: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "kernel does not fit");
@@ -382,6 +409,10 @@ int qpb_create(const qpb_params* params, int device, qpb_handle** out) {
   if (const char* env = std::getenv("QPB_TPQ_LPQ")) {
     const int v = std::atoi(env);
     if (v == 1 || v == 2 || v == 4) h->tpq_lpq = v;
+  }
+  if (const char* env = std::getenv("QPB_TPQ_MIN_N")) {
+    const long long v = std::atoll(env);
+    if (v >= 0) h->tpq_min_n = v;
   }
   if (const char* env = std::getenv("QPB_ZEROCOPY")) h->zero_copy = std::atoi(env);
   if (const char* env = std::getenv("QPB_HOST_CHUNK")) {

@@ -1,18 +1,19 @@
-// qpb_tpq.cuh -- balance_qp_tpq_kernel: the default balance kernel when W = w I (the reference's configuration) and
-// fzmin >= 0.  The arithmetic is qpb_tpq_core.h (range-space Goldfarb-Idnani, a 6x6 Cholesky per working-set change).
-// A QP is iterated on by LPQ lanes (template parameter: 1 = one thread per QP, 2 = two legs per lane, 4 = one leg per
-// lane); this file is the warp-level plumbing that keeps the lanes busy although iteration counts differ from QP to QP
-// (0..40):
+// qpb_tpq.cuh -- the default balance path when W = w I (the reference's configuration) and fzmin >= 0: three kernels
+// around the arithmetic of qpb_tpq_core.h (range-space Goldfarb-Idnani, one 6x6 Cholesky per working-set change).
 //
-//   * set-up (load, PD target, lever arms, unconstrained / hinted minimiser) always runs one record per THREAD on a full
-//     warp, 32 new records at a time, and parks the 64-double solver states in a per-warp shared-memory stack ("prep");
-//   * the iteration loop runs on the 32 / LPQ QPs the warp holds; as soon as QPB_TPQ_REFILL lanes are idle, finished QPs
-//     push their final working sets (8 doubles) onto a second per-warp stack ("ret") and idle lanes pop fresh states;
-//   * the epilogue (polish = one more 6x6 solve on the final faces, world->body, 12 sincos, J^T f, 256-B store) runs
-//     one result per thread on a full warp whenever 32 results are parked.
+//   tpq_setup_kernel   one THREAD per record: load, PD target, lever arms, the unconstrained (or hinted) minimiser;
+//                      writes a 512-B prepared record (f, r, u, b, G, working set) to scratch memory
+//   tpq_loop_kernel    the active-set loop.  A QP is iterated on by LPQ lanes (template: 1 = one thread per QP, 2 = two
+//                      legs per lane, 4 = one leg per lane).  Persistent warps: whenever QPB_TPQ_REFILL lanes are idle,
+//                      finished QPs write their final working set (8 bytes) back and idle lanes claim the next prepared
+//                      records from a global ticket -- iteration counts differ from QP to QP (0..40), lanes never wait
+//                      for each other beyond that threshold, warps never synchronise with each other
+//   tpq_finish_kernel  one THREAD per record: polish (the minimiser on the final faces from one fresh 6x6 solve),
+//                      world->body, 12 sincos, J^T f, the 256-B result record
 //
-// Warps never synchronise with each other: the stacks are private to a warp (__syncwarp only), work is claimed in
-// chunks of 32 records from a global ticket.
+// Splitting the path in three lets each part run at its own register budget and keeps the loop's code small enough for
+// the instruction cache: fused in one kernel (an earlier build, profiles/r02_ncu_tpq_v3_*) every variant sat at the
+// same 4.3e8 QP/s on config 3, latency-bound at 8-16 warps per SM with the set-up's and epilogue's registers.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -21,37 +22,32 @@
 #include "qpb_tpq_core.h"
 
 #ifndef QPB_TPQ_REFILL
-#define QPB_TPQ_REFILL 2  // idle lanes that trigger a retire + refill
+#define QPB_TPQ_REFILL 2  // idle lanes that trigger a retire + refill in the loop kernel
 #endif
 
 namespace qpb {
 namespace tpq {
 
-constexpr int PREP_STRIDE = 65;  // doubles per parked solver state (odd: lane-strided access is conflict-free)
-constexpr int RET_STRIDE = 9;    // doubles per parked result
-constexpr int SIDE_STRIDE = kSideSize;  // per-QP storage while it is iterated on: b (6), G (21), lever arms (12)
-constexpr int PREP_CAP = 32, RET_CAP = 32;
+constexpr int kLoopThreads = 128;   // loop kernel: 4 warps per CTA
+constexpr int kEdgeThreads = 128;   // set-up / finishing kernels
 
-// Shared memory of a CTA of W warps: ONE stack of prepared states for all its warps (popped and restocked under a
-// try-lock: a warp that finds it taken just keeps iterating and tries again a round later), and per warp the stack of
-// results awaiting the epilogue and the b / G blocks of the QPs it is iterating on.
-template <int LPQ, int W>
-struct __align__(16) CtaShared {
-  double prep[PREP_CAP * PREP_STRIDE];
-  struct PerWarp {
-    double ret[RET_CAP * RET_STRIDE];
-    double side[(32 / LPQ) * SIDE_STRIDE];
-  } w[W];
-  int lock;       // 0 free, 1 held
-  int prep_n;     // height of prep (read and written under the lock)
-  int exhausted;  // the work ticket has run past the last chunk (set under the lock, never cleared)
-};
-
-// kernel shape per lanes-per-QP: warps per CTA and the minimum CTAs per SM (= the register cap)
-template <int LPQ> struct Shape;
-template <> struct Shape<1> { static constexpr int W = 2, MIN_CTAS = 4; };   // 255 registers,  8 warps / SM
-template <> struct Shape<2> { static constexpr int W = 4, MIN_CTAS = 3; };   // 168 registers, 12 warps / SM
-template <> struct Shape<4> { static constexpr int W = 4, MIN_CTAS = 4; };   // 128 registers, 16 warps / SM
+// minimum CTAs per SM = the register cap (65536 / (128 threads * MIN_CTAS)); overridable for experiments
+#ifndef QPB_TPQ_MINCTAS_1
+#define QPB_TPQ_MINCTAS_1 2  // 255 registers
+#endif
+#ifndef QPB_TPQ_MINCTAS_2
+#define QPB_TPQ_MINCTAS_2 3  // 168
+#endif
+#ifndef QPB_TPQ_MINCTAS_4
+#define QPB_TPQ_MINCTAS_4 4  // 128
+#endif
+#ifndef QPB_TPQ_EDGE_MINCTAS
+#define QPB_TPQ_EDGE_MINCTAS 2
+#endif
+template <int LPQ> struct LoopShape;
+template <> struct LoopShape<1> { static constexpr int MIN_CTAS = QPB_TPQ_MINCTAS_1; };
+template <> struct LoopShape<2> { static constexpr int MIN_CTAS = QPB_TPQ_MINCTAS_2; };
+template <> struct LoopShape<4> { static constexpr int MIN_CTAS = QPB_TPQ_MINCTAS_4; };
 
 // ---- exchanges between the LPQ lanes of a QP (xor butterflies inside aligned groups of LPQ lanes) -----------------------
 template <int LPQ>
@@ -82,20 +78,29 @@ __device__ __forceinline__ void group_min_ratio(double& ub, double& rb, int& kb)
   }
 }
 
-// One working-set change for every QP the warp holds (or the optimality test that ends a solve).
+// One working-set change for every QP the warp holds, then the choice of the next row (or the end of the solve: nothing
+// is violated any more).  Every QP enters with its row already chosen -- the first one by the set-up pass.
 template <int LPQ>
 __device__ __forceinline__ void iterate_group(const FastParams& K, Lane<4 / LPQ>& ln, int j, double* side) {
   constexpr int LPL = 4 / LPQ;
-  const uint32_t best = group_umax<LPQ>(select_local<LPL>(K, ln, j));
-  bool fresh;
-  const double slack = group_sum<LPQ>(select_commit<LPL>(K, ln, j, best, fresh));
-  if (fresh) ln.sp = slack;
   StepTmp<LPL> T;
   double ub, rb;
   int kb;
   direction<LPL>(K, ln, j, side, T, ub, rb, kb);
   group_min_ratio<LPQ>(ub, rb, kb);
   advance<LPL>(K, ln, j, side, T, ub, rb, kb, j == 0);
+  const uint32_t best = group_umax<LPQ>(select_local<LPL>(K, ln, j));
+  bool fresh;
+  const double slack = group_sum<LPQ>(select_commit<LPL>(K, ln, j, best, fresh));
+  if (fresh) ln.sp = slack;
+}
+
+// meta word of a prepared record.  low: working set (24) | stance (4) | status (2).  high: working-set changes so far
+// (16) | first row of the loop (5 bits: 3 leg + group, + 16 for row B) << 16 | "there is one" << 21.
+__device__ __forceinline__ double pack_meta(uint32_t word, uint32_t stance, int status, int iters, uint32_t key) {
+  const uint32_t lo = word | (stance << 24) | ((uint32_t)status << 28);
+  const uint32_t hi = ((uint32_t)iters & 0xffffu) | ((key & 31u) << 16) | ((key >> 31) << 21);
+  return __hiloint2double((int)hi, (int)lo);
 }
 
 // ---- record access: 48 doubles + contact bytes + warm-start word in, 256-B record out --------------------------
@@ -118,29 +123,24 @@ __device__ __forceinline__ void tpq_load(const SplitIO& io, int64_t rec, double 
            ((uint32_t)io.contact[rec * 4 + 3] << 24);
   hint = 0u;
 }
-// what the epilogue needs of a record: R (9), feet (12), q (12)
-__device__ __forceinline__ void tpq_load_Rq(const PackedIO& io, int64_t rec, double (&R)[9], double (&feet)[12], double (&q)[12]) {
+// what the finishing pass needs of a record: R (9), q (12)
+__device__ __forceinline__ void tpq_load_Rq(const PackedIO& io, int64_t rec, double (&R)[9], double (&q)[12]) {
   const double* p = reinterpret_cast<const double*>(io.in + rec);
 #pragma unroll
   for (int j = 0; j < 9; j++) R[j] = __ldg(p + j);
-  const double2* pq = reinterpret_cast<const double2*>(p + kFeet);  // feet, q: slots 36..59
+  const double2* pq = reinterpret_cast<const double2*>(p + kQ);
 #pragma unroll
   for (int j = 0; j < 6; j++) {
-    const double2 t = __ldg(pq + j), t2 = __ldg(pq + 6 + j);
-    feet[2 * j] = t.x;
-    feet[2 * j + 1] = t.y;
-    q[2 * j] = t2.x;
-    q[2 * j + 1] = t2.y;
+    const double2 t = __ldg(pq + j);
+    q[2 * j] = t.x;
+    q[2 * j + 1] = t.y;
   }
 }
-__device__ __forceinline__ void tpq_load_Rq(const SplitIO& io, int64_t rec, double (&R)[9], double (&feet)[12], double (&q)[12]) {
+__device__ __forceinline__ void tpq_load_Rq(const SplitIO& io, int64_t rec, double (&R)[9], double (&q)[12]) {
 #pragma unroll
   for (int j = 0; j < 9; j++) R[j] = __ldg(io.Rwb + rec * 9 + j);
 #pragma unroll
-  for (int j = 0; j < 12; j++) {
-    feet[j] = __ldg(io.feet + rec * 12 + j);
-    q[j] = __ldg(io.q + rec * 12 + j);
-  }
+  for (int j = 0; j < 12; j++) q[j] = __ldg(io.q + rec * 12 + j);
 }
 __device__ __forceinline__ void tpq_store(const PackedIO& io, int64_t rec, const double (&grf)[12], const double (&tau)[12],
                                           int status, int iters, uint32_t wword) {
@@ -166,207 +166,132 @@ __device__ __forceinline__ void tpq_store(const SplitIO& io, int64_t rec, const 
   if (io.status) io.status[rec] = status;
 }
 
-// ---- parked solver state: f, r, u, b, G, then (lo: working set | stance << 24 | status << 28, hi: record index) --
-__device__ __forceinline__ void park_state(double* e, const State& st, const double (&b6)[6], const double (&G)[21], uint32_t rec) {
+// ---- pass 1: set-up, one thread per record ----------------------------------------------------------------------------
+// Writes a dual-feasible starting pair into the prepared record: f, u, G and the meta word (working set, contact mask,
+// status, block rounds spent).  Called for every pair the block rounds of start() accept; the last call wins.
+struct PrepCommit {
+  double* e;
+  uint32_t key;  // first row of the loop at the last pair committed (0: that pair is optimal, no loop needed)
+  __device__ __forceinline__ void operator()(const State& st, const double (&G)[21], uint32_t k) {
+    key = k;
+    double2* o = reinterpret_cast<double2*>(e);
 #pragma unroll
-  for (int i = 0; i < 12; i++) {
-    e[i] = st.f[i];
-    e[12 + i] = st.r[i];
-    e[24 + i] = st.u[i];
+    for (int i = 0; i < 6; i++) {
+      o[kPrepF / 2 + i] = make_double2(st.f[2 * i], st.f[2 * i + 1]);
+      o[kPrepU / 2 + i] = make_double2(st.u[2 * i], st.u[2 * i + 1]);
+    }
+#pragma unroll
+    for (int i = 0; i < 10; i++) o[kPrepG / 2 + i] = make_double2(G[2 * i], G[2 * i + 1]);
+    o[kPrepG / 2 + 10] = make_double2(G[20], pack_meta(st.word, st.stance, st.status, st.iters, k));
   }
-#pragma unroll
-  for (int i = 0; i < 6; i++) e[36 + i] = b6[i];
-#pragma unroll
-  for (int i = 0; i < 21; i++) e[42 + i] = G[i];
-  const uint32_t lo = st.word | (st.stance << 24) | ((uint32_t)st.status << 28);
-  e[63] = __hiloint2double((int)rec, (int)lo);
-}
-// a group of LPQ lanes takes a parked state: every lane its share of f and u, all of r; b and G go to the QP's side block
-template <int LPQ>
-__device__ __forceinline__ void unpark_state(const double* e, Lane<4 / LPQ>& ln, int j, double* side, uint32_t& rec) {
-  const double w = e[63];
-  const uint32_t lo = (uint32_t)__double2loint(w);
-  rec = (uint32_t)__double2hiint(w);
-  lane_init<4 / LPQ>(ln, j, e, e + 12, e + 24, lo & 0xffffffu, (lo >> 24) & 15u, (int)(lo >> 28));
-#pragma unroll
-  for (int i = 0; i < (27 + LPQ - 1) / LPQ; i++) {
-    const int k = j + LPQ * i;
-    if (k < 27) side[k] = e[36 + k];  // b, G
-  }
-#pragma unroll
-  for (int i = 0; i < 12 / LPQ; i++) side[kSideR + j + LPQ * i] = e[12 + j + LPQ * i];  // all lever arms
-}
-// ---- parked result: b, (lo: working set | stance << 24 | status << 28, hi: record index), iterations ------------------
-template <int LPL>
-__device__ __forceinline__ void park_result(double* e, const Lane<LPL>& ln, const double* side, uint32_t rec) {
-#pragma unroll
-  for (int i = 0; i < 6; i++) e[i] = side[i];
-  const uint32_t lo = ln.word | (ln.stance << 24) | ((uint32_t)ln.status << 28);
-  e[6] = __hiloint2double((int)rec, (int)lo);
-  e[7] = __hiloint2double(0, ln.iters);
-}
+};
 
-// Full-warp epilogue over the first cnt parked results: polish (the minimiser on the final faces, from scratch),
-// world->body, J^T f, store.
 template <class IO>
-__device__ __noinline__ void flush_results(const qpb_params& P, const FastParams& K, const IO& io, const double* ret, int cnt,
-                                           int lane) {
-  if (lane < cnt) {
-    const double* e = ret + lane * RET_STRIDE;
+__global__ void __launch_bounds__(kEdgeThreads, QPB_TPQ_EDGE_MINCTAS)
+tpq_setup_kernel(const __grid_constant__ qpb_params P, const __grid_constant__ FastParams K, IO io, int64_t n, double* __restrict__ prep,
+                 uint32_t* __restrict__ work, unsigned long long* __restrict__ ticket) {
+  const int64_t rec = (int64_t)blockIdx.x * kEdgeThreads + threadIdx.x;
+  bool need = false;  // this record goes through the active-set loop (its starting pair is not optimal yet)
+  if (rec < n) {
+    double v[48];
+    uint32_t cbytes, hint;
+    tpq_load(io, rec, v, cbytes, hint);
     State st;
-    double b6[6];
+    double b6[6], G[21];
+    PrepCommit commit{ prep + rec * kPrepSize, 0u };
+    setup(P, K, v, cbytes, hint, st, b6, G, commit);
+    // what does not depend on the working set: lever arms and the right-hand side (after a non-finite input they are zero)
+    double2* o = reinterpret_cast<double2*>(commit.e);
 #pragma unroll
-    for (int i = 0; i < 6; i++) b6[i] = e[i];
-    const double w = e[6];
-    const uint32_t rec = (uint32_t)__double2hiint(w);
-    const uint32_t lo = (uint32_t)__double2loint(w);
-    st.word = lo & 0xffffffu;
-    st.stance = (lo >> 24) & 15u;
-    st.status = (int)(lo >> 28);
-    st.iters = __double2loint(e[7]);
-    double R[9], feet[12], q[12], grf[12], tau[12];
-    tpq_load_Rq(io, (int64_t)rec, R, feet, q);
-    bool qfin = true;  // the set-up checked slots 0..47; the joint angles are first touched here
+    for (int i = 0; i < 6; i++) o[kPrepR / 2 + i] = make_double2(st.r[2 * i], st.r[2 * i + 1]);
 #pragma unroll
-    for (int i = 0; i < 12; i++) qfin = qfin && (fabs(q[i]) <= 1.79769313486231570e308);
-    if (!qfin && st.status == QPB_OK) st.status = QPB_BAD_INPUT;
-    const bool sane = st.status != QPB_BAD_INPUT;
-#pragma unroll
-    for (int i = 0; i < 4; i++)
-#pragma unroll
-      for (int k = 0; k < 3; k++)  // lever arms r_i = R p_i again (cheaper than parking them)
-        st.r[3 * i + k] = sane ? R[3 * k] * feet[3 * i] + R[3 * k + 1] * feet[3 * i + 1] + R[3 * k + 2] * feet[3 * i + 2] : 0.0;
-#pragma unroll
-    for (int i = 0; i < 12; i++) st.f[i] = st.u[i] = 0.0;
-    polish(K, st, b6);
-    finish(P, R, q, st, grf, tau);
-    tpq_store(io, (int64_t)rec, grf, tau, st.status, st.iters, st.word | 0x80000000u);
+    for (int i = 0; i < 3; i++) o[kPrepB / 2 + i] = make_double2(b6[2 * i], b6[2 * i + 1]);
+    need = commit.key != 0u;
+  }
+  // worklist of the loop pass: one atomic per warp (ticket[2] counts the entries; the loop's last CTA re-arms it)
+  const uint32_t m = __ballot_sync(FULL, need);
+  if (m) {
+    const int lane = threadIdx.x & 31;
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(ticket + 2, (unsigned long long)__popc(m));
+    base = __shfl_sync(FULL, base, 0);
+    if (need) work[base + __popc(m & ((1u << lane) - 1u))] = (uint32_t)rec;
   }
 }
 
-template <class IO, int LPQ>
-__global__ void __launch_bounds__(Shape<LPQ>::W * 32, Shape<LPQ>::MIN_CTAS)
-balance_qp_tpq_kernel(const __grid_constant__ qpb_params P, const __grid_constant__ FastParams K, IO io, int64_t n,
-                      unsigned long long* __restrict__ ticket) {
-  constexpr int LPL = 4 / LPQ, W = Shape<LPQ>::W;
-  __shared__ CtaShared<LPQ, W> sh;
+// ---- pass 2: the active-set loop ----------------------------------------------------------------------------------------
+template <int LPQ>
+__global__ void __launch_bounds__(kLoopThreads, LoopShape<LPQ>::MIN_CTAS)
+tpq_loop_kernel(const __grid_constant__ FastParams K, double* __restrict__ prep, const uint32_t* __restrict__ work,
+                unsigned long long* __restrict__ ticket) {
+  constexpr int LPL = 4 / LPQ, NS = 32 / LPQ;  // legs per lane, QP slots per warp
+  __shared__ double side_all[(kLoopThreads / LPQ) * kSideSize];
   const int lane = threadIdx.x & 31;
-  const int wib = threadIdx.x >> 5;
-  if (threadIdx.x == 0) {
-    sh.lock = 0;
-    sh.prep_n = 0;
-    sh.exhausted = 0;
-  }
-  __syncthreads();
-  typename CtaShared<LPQ, W>::PerWarp& ws = sh.w[wib];
   const int j = lane & (LPQ - 1);                             // lane within its QP
   const uint32_t leaders = 0xffffffffu / ((1u << LPQ) - 1u);  // bit of the first lane of every group
-  const uint32_t lt = (1u << lane) - 1u;
-  const uint32_t glt = (1u << (lane & ~(LPQ - 1))) - 1u;  // lanes below this lane's group
-  double* side = ws.side + (lane / LPQ) * SIDE_STRIDE;
-  const uint32_t nchunks = (uint32_t)((n + 31) >> 5);
+  const uint32_t glt = (1u << (lane & ~(LPQ - 1))) - 1u;      // lanes below this lane's group
+  double* side = side_all + (threadIdx.x / LPQ) * kSideSize;
   constexpr int kRefill = (QPB_TPQ_REFILL + LPQ - 1) / LPQ;  // idle QP slots that trigger a retire + refill
 
-  int ret_n = 0;      // warp-uniform height of the result stack
-  bool have = false;  // this lane's group holds a QP
-  uint32_t rec = 0;
+  const int64_t n = (int64_t)*reinterpret_cast<volatile unsigned long long*>(ticket + 2);  // entries of the worklist
+  bool have = false;   // this lane's group holds a QP
+  bool more = true;    // the ticket has not run past the end of the worklist yet (warp-uniform)
+  int64_t rec = 0;
   Lane<LPL> ln;
   {
     const double zero[12] = { 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0 };
-    lane_init<LPL>(ln, j, zero, zero, zero, 0u, 0u, QPB_OK);
+    lane_init<LPL>(ln, j, zero, zero, zero, 0u, 0u, QPB_OK, 0, 0u);
     ln.done = true;
   }
 
   for (;;) {
     const uint32_t busy = __ballot_sync(FULL, have && !ln.done) & leaders;
-    if (32 / LPQ - __popc(busy) >= kRefill || busy == 0u) {
-      // ---- retire: finished QPs park their results; a full stack -> full-warp epilogue ---------------------------
-      const bool fin = have && ln.done;
-      const uint32_t fm = __ballot_sync(FULL, fin) & leaders;
-      if (fm) {
-        if (ret_n + __popc(fm) > RET_CAP) {  // no room for all of them: run the epilogue on what is parked (>= 31/32 full)
-          flush_results(P, K, io, ws.ret, ret_n, lane);
-          ret_n = 0;
-          __syncwarp();
-        }
-        if (fin) {
-          if (j == 0) park_result<LPL>(ws.ret + (ret_n + __popc(fm & lt)) * RET_STRIDE, ln, side, rec);
-          have = false;
-        }
-        ret_n += __popc(fm);
-        __syncwarp();
-        if (ret_n == RET_CAP) {
-          flush_results(P, K, io, ws.ret, ret_n, lane);
-          ret_n = 0;
-          __syncwarp();
-        }
+    if (NS - __popc(busy) >= kRefill || busy == 0u) {
+      // retire: a finished QP hands its final working set and iteration count to the finishing pass
+      if (have && ln.done) {
+        if (j == 0) prep[rec * kPrepSize + kPrepMeta] = pack_meta(ln.word, ln.stance, ln.status, ln.iters, 0u);
+        have = false;
       }
-      // ---- refill under the CTA's try-lock: idle groups pop prepared states; an empty stack is restocked by a set-up
-      //      of the next 32 records, one record per thread ----------------------------------------------------------------
-      int got = 0;
-      if (lane == 0) got = atomicCAS(&sh.lock, 0, 1) == 0;
-      got = __shfl_sync(FULL, got, 0);
-      if (got) {
-        __threadfence_block();
-        int prep_n = *(volatile int*)&sh.prep_n;
-        int exhausted = *(volatile int*)&sh.exhausted;
-        bool stocked = false;
-#pragma unroll 1
-        for (int pass = 0; pass < 2; pass++) {
-          const uint32_t idle = ~__ballot_sync(FULL, have) & leaders;
-          const int want = __popc(idle);
-          if (want == 0) break;
-          if (prep_n == 0) {
-            if (stocked || exhausted) break;
-            stocked = true;
-            uint32_t chunk = 0;
-            if (lane == 0) chunk = (uint32_t)atomicAdd(ticket, 1ULL);
-            chunk = __shfl_sync(FULL, chunk, 0);
-            if (chunk >= nchunks) {
-              exhausted = 1;
-              break;
-            }
-            const int64_t r0 = (int64_t)chunk * 32 + lane;
-            const bool valid = r0 < n;
-            if (valid) {
-              double v[48];
-              uint32_t cbytes, hint;
-              tpq_load(io, r0, v, cbytes, hint);
-              State s0;
-              double b6[6], G[21];
-              setup(P, K, v, cbytes, hint, s0, b6, G);
-              park_state(sh.prep + lane * PREP_STRIDE, s0, b6, G, (uint32_t)r0);
-            }
-            prep_n = __popc(__ballot_sync(FULL, valid));  // valid lanes are the low ones: the stack is dense
-            __syncwarp();
+      // refill: idle groups claim the next entries of the worklist (one atomic per warp) and load their share
+      const uint32_t idle = ~__ballot_sync(FULL, have) & leaders;
+      const int want = __popc(idle);
+      if (want > 0 && more) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(ticket, (unsigned long long)want);
+        base = __shfl_sync(FULL, base, 0);
+        const int64_t mine = (int64_t)base + __popc(idle & glt);
+        more = (int64_t)base + want < n;
+        const bool take = !have && mine < n;
+        if (take) {
+          rec = (int64_t)__ldg(work + mine);
+          const double* e = prep + rec * kPrepSize;
+          const double meta = __ldg(e + kPrepMeta);
+          const uint32_t lo = (uint32_t)__double2loint(meta), hi = (uint32_t)__double2hiint(meta);
+          double f[3 * LPL], u[3 * LPL], r[3 * LPL];
+#pragma unroll
+          for (int i = 0; i < 3 * LPL; i++) {
+            f[i] = __ldg(e + kPrepF + 3 * LPL * j + i);
+            u[i] = __ldg(e + kPrepU + 3 * LPL * j + i);
+            r[i] = __ldg(e + kPrepR + 3 * LPL * j + i);
           }
-          const int rank = __popc(idle & glt);
-          if (!have && rank < prep_n) {
-            unpark_state<LPQ>(sh.prep + (prep_n - 1 - rank) * PREP_STRIDE, ln, j, side, rec);
-            have = true;
+          // lane_init indexes all twelve with the lane's position; it gets arrays that hold just this lane's share
+          lane_init<LPL>(ln, 0, f, r, u, lo & 0xffffffu, (lo >> 24) & 15u, (int)((lo >> 28) & 3u), (int)(hi & 0xffffu),
+                         ((hi >> 16) & 31u) | ((hi >> 21) << 31));
+#pragma unroll
+          for (int i = 0; i < (21 + LPQ - 1) / LPQ; i++) {
+            const int k = j + LPQ * i;
+            if (k < 21) side[kSideG + k] = __ldg(e + kPrepG + k);
           }
-          prep_n -= min(want, prep_n);
-          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 12 / LPQ; i++) side[kSideR + j + LPQ * i] = __ldg(e + kPrepR + j + LPQ * i);
+          have = true;
         }
-        if (lane == 0) {
-          *(volatile int*)&sh.prep_n = prep_n;
-          *(volatile int*)&sh.exhausted = exhausted;
-          __threadfence_block();
-          atomicExch(&sh.lock, 0);
-        }
+        // the slack of the first row: the lane that owns its leg has it, the others get it here
+        const double slack = group_sum<LPQ>(take ? row_slack_share<LPL>(K, ln, j) : 0.0);
+        if (take) ln.sp = slack;
         __syncwarp();
       }
-      if (__ballot_sync(FULL, have) == 0u) {
-        // This warp holds nothing.  It is finished once the input is exhausted and the shared stack is empty (exhausted
-        // is read first: after it is set no set-up runs, so prep_n can only go down).
-        const int ex = *(volatile int*)&sh.exhausted;
-        const int pn = *(volatile int*)&sh.prep_n;
-        if (ex && pn == 0) {
-          if (ret_n > 0) flush_results(P, K, io, ws.ret, ret_n, lane);
-          break;
-        }
-        continue;  // the lock was busy or another warp is restocking: look again
-      }
+      if (__ballot_sync(FULL, have) == 0u) break;  // nothing held, nothing left to claim
     }
     iterate_group<LPQ>(K, ln, j, side);
     __syncwarp();  // G written by the first lane of a QP is read by its other lanes in the next round
@@ -379,9 +304,51 @@ balance_qp_tpq_kernel(const __grid_constant__ qpb_params P, const __grid_constan
     if (atomicAdd(ticket + 1, 1ULL) == (unsigned long long)gridDim.x - 1ULL) {
       ticket[0] = 0ULL;
       ticket[1] = 0ULL;
+      ticket[2] = 0ULL;  // the worklist counter the set-up pass filled
       __threadfence();
     }
   }
+}
+
+// ---- pass 3: polish + epilogue, one thread per record -------------------------------------------------------------------
+template <class IO>
+__global__ void __launch_bounds__(kEdgeThreads, QPB_TPQ_EDGE_MINCTAS)
+tpq_finish_kernel(const __grid_constant__ qpb_params P, const __grid_constant__ FastParams K, IO io, int64_t n,
+                  const double* __restrict__ prep) {
+  const int64_t rec = (int64_t)blockIdx.x * kEdgeThreads + threadIdx.x;
+  if (rec >= n) return;
+  const double* e = prep + rec * kPrepSize;
+  State st;
+  double b6[6];
+  const double w = __ldg(e + kPrepMeta);
+  const uint32_t lo = (uint32_t)__double2loint(w);
+  st.word = lo & 0xffffffu;
+  st.stance = (lo >> 24) & 15u;
+  st.status = (int)((lo >> 28) & 3u);
+  st.iters = __double2hiint(w) & 0xffff;
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+    const double2 t = __ldg(reinterpret_cast<const double2*>(e + kPrepR) + i);
+    st.r[2 * i] = t.x;
+    st.r[2 * i + 1] = t.y;
+  }
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    const double2 t = __ldg(reinterpret_cast<const double2*>(e + kPrepB) + i);
+    b6[2 * i] = t.x;
+    b6[2 * i + 1] = t.y;
+  }
+#pragma unroll
+  for (int i = 0; i < 12; i++) st.f[i] = st.u[i] = 0.0;
+  double R[9], q[12], grf[12], tau[12];
+  tpq_load_Rq(io, rec, R, q);
+  bool qfin = true;  // the set-up checked slots 0..47; the joint angles are first touched here
+#pragma unroll
+  for (int i = 0; i < 12; i++) qfin = qfin && (fabs(q[i]) <= 1.79769313486231570e308);
+  if (!qfin && st.status == QPB_OK) st.status = QPB_BAD_INPUT;
+  polish(K, st, b6);  // the minimiser on the final faces, from scratch
+  finish(P, R, q, st, grf, tau);
+  tpq_store(io, rec, grf, tau, st.status, st.iters, st.word | 0x80000000u);
 }
 
 }  // namespace tpq

@@ -315,28 +315,120 @@ QPB_HD uint32_t wset_sanitize(uint32_t word, uint32_t stance) {
   return out;
 }
 
-// Start: minimiser on the hinted faces if that is a dual-feasible pair, else the unconstrained minimiser.
-QPB_HD void start(const FastParams& K, State& st, const double (&b6)[6], uint32_t hint, bool have_hint, double (&G)[21]) {
+// Selection key of one leg: the most violated row among its groups that are not active, 0 if none.  The high word of
+// (slack - tolerance) orders negative doubles by magnitude as an unsigned integer; low 5 bits = 3 leg + group, + 16 for
+// row B.  (The other row of an ACTIVE group can only be violated while fz < 0; the fz row of that leg then goes first.)
+QPB_HD uint32_t leg_key(const FastParams& K, double fx, double fy, double fz, uint32_t codes, bool stance, int i) {
+  const double base = fma(K.mu, fz, 1e-9);
+  const double slx = base - fabs(fx), sly = base - fabs(fy);
+  const double sA = (fz - K.fzmin) - K.ntol_z, sB = (K.fzmax - fz) - K.ntol_z;
+  const uint32_t id = (uint32_t)(3 * i);
+  const uint32_t kx = ((uint32_t)hi32(slx) & ~31u) | id | (hi32(fx) < 0 ? 16u : 0u);  // fx > 0: row A binds
+  const uint32_t ky = ((uint32_t)hi32(sly) & ~31u) | (id + 1u) | (hi32(fy) < 0 ? 16u : 0u);
+  const uint32_t ka = ((uint32_t)hi32(sA) & ~31u) | (id + 2u);
+  const uint32_t kb = ((uint32_t)hi32(sB) & ~31u) | (id + 2u) | 16u;
+  const uint32_t mx = (stance && (codes & 3u) == 0u) ? kx : 0u;
+  const uint32_t my = (stance && (codes & 12u) == 0u) ? ky : 0u;
+  const uint32_t mz = (stance && (codes & 48u) == 0u) ? (ka > kb ? ka : kb) : 0u;
+  const uint32_t m1 = mx > my ? mx : my;
+  const uint32_t m2 = m1 > mz ? m1 : mz;
+  return (m2 >> 31) ? m2 : 0u;  // only violated rows (negative slack) count
+}
+
+// Rows violated at st.f among the groups that are not active, at most one per group (the binding side), as a
+// working-set word.  Same tolerances as the loop's selection.
+QPB_HD uint32_t violated_rows(const FastParams& K, const State& st) {
+  uint32_t w = 0u;
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const uint32_t c = st.word >> (6 * i);
+    const double fx = st.f[3 * i], fy = st.f[3 * i + 1], fz = st.f[3 * i + 2];
+    const double base = fma(K.mu, fz, 1e-9);
+    uint32_t add = 0u;
+    if ((c & 3u) == 0u && base - fabs(fx) < 0.0) add |= hi32(fx) < 0 ? 2u : 1u;  // fx > 0: row A binds
+    if ((c & 12u) == 0u && base - fabs(fy) < 0.0) add |= hi32(fy) < 0 ? 8u : 4u;
+    if ((c & 48u) == 0u) {
+      if ((fz - K.fzmin) - K.ntol_z < 0.0) add |= 16u;
+      else if ((K.fzmax - fz) - K.ntol_z < 0.0) add |= 32u;
+    }
+    if ((st.stance >> i) & 1u) w |= add << (6 * i);
+  }
+  return w;
+}
+
+#ifndef QPB_START_ADDS
+#define QPB_START_ADDS 1
+#endif
+#ifndef QPB_START_DROPS
+#define QPB_START_DROPS 2
+#endif
+constexpr int kStartAdds = QPB_START_ADDS;    // block rounds that add every violated row at once
+constexpr int kStartDrops = QPB_START_DROPS;  // rounds that drop every row with a negative multiplier, per add round
+constexpr int kStartSolves = 1 + kStartAdds * (1 + kStartDrops) + 1 + kStartDrops;  // bound on the 6x6 solves of start()
+
+// Start of the active-set method.  Goldfarb-Idnani may start from ANY working set whose face minimiser has non-negative
+// multipliers (a dual-feasible pair); the closer that set is to the optimal one, the fewer one-row-at-a-time changes
+// the loop needs.  So, before the loop: solve on the hinted faces (warm start = the reference's hotstart) or on none
+// (the unconstrained minimiser); then up to kStartAdds block rounds: add EVERY violated row at once, re-solve, drop
+// every row whose multiplier came out negative (up to kStartDrops times), and keep the result only if it is a
+// dual-feasible pair.  Every pair that qualifies is handed to commit(st, G, key) -- key = the first row the loop would
+// add there, 0 if the pair is already optimal; the last one committed is where the loop
+// starts (often it is already optimal: with one block round the loop's working-set changes fall from 12.5 to 5.7 per
+// QP on BASELINE config 2 and from 7.0 to 2.7 on config 3).  A solve from scratch costs about as much as one loop
+// iteration, so only the first block round -- which stands in for ~6 iterations -- pays; measured on the B200, one
+// round beats none, two and three (profiles/r02_start_budget.txt).
+template <class Commit>
+QPB_HD void start(const FastParams& K, State& st, const double (&b6)[6], uint32_t hint, bool have_hint, double (&G)[21],
+                  Commit& commit) {
   st.p = -1;
   st.pc = 0u;
   st.up = 0.0;
   st.iters = 0;
   st.status = QPB_OK;
   st.done = false;
-  st.word = have_hint ? wset_sanitize(hint, st.stance) : 0u;
-  bool ok = true;
+  uint32_t word = have_hint ? wset_sanitize(hint, st.stance) : 0u;
+  bool committed = false, ok = true;
+  int adds = 0, drops = 0, rounds = 0;
 #pragma unroll 1
-  for (int attempt = 0; attempt < 2; attempt++) {  // a loop so that face_solve is emitted once
+  for (int pass = 0; pass < kStartSolves; pass++) {  // a loop so that face_solve is emitted once
+    st.word = word;
+    st.iters = rounds;
     ok = face_solve(K, st, b6, G);
-    bool feas = true;
+    if (!ok) break;
+    uint32_t neg = 0u;
 #pragma unroll
-    for (int i = 0; i < 12; i++) feas = feas && (st.u[i] >= 0.0);  // inactive groups carry u = 0
-    if (st.word == 0u || feas) break;
-    st.word = 0u;  // the hinted faces are not a dual-feasible pair: cold start
+    for (int i = 0; i < 12; i++)
+      if (st.u[i] < 0.0) neg |= 3u << (2 * i);  // inactive groups carry u = 0
+    if (neg == 0u) {
+      uint32_t key = 0u;  // the row the loop would add first at this pair; 0: nothing is violated, the pair is optimal
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const uint32_t k = leg_key(K, st.f[3 * i], st.f[3 * i + 1], st.f[3 * i + 2], word >> (6 * i), (st.stance >> i) & 1u, i);
+        key = k > key ? k : key;
+      }
+      commit(st, G, key);
+      committed = true;
+      const uint32_t viol = violated_rows(K, st);
+      if (viol == 0u || adds >= kStartAdds || rounds >= K.max_iter) break;  // optimal already / budget spent
+      word |= viol;
+      adds++;
+      drops = 0;
+    } else if (drops < kStartDrops && rounds < K.max_iter) {
+      word &= ~neg;
+      drops++;
+    } else if (!committed) {
+      word = 0u;  // a hint that does not lead to a dual-feasible pair: cold start (the empty set always qualifies)
+      drops = 0;
+      rounds = -1;
+    } else {
+      break;
+    }
+    rounds++;
   }
-  if (!ok) {
+  if (!ok || !committed) {
     st.status = QPB_BAD_INPUT;
     st.done = true;
+    commit(st, G, 0u);
   }
 }
 
@@ -389,7 +481,7 @@ struct Lane {
 // One lane's share of a solver state.  j = index of the lane within its QP.
 template <int LPL>
 QPB_HD void lane_init(Lane<LPL>& ln, int j, const double* f12, const double* r12, const double* u12, uint32_t word, uint32_t stance,
-                      int status) {
+                      int status, int iters, uint32_t key) {
 #pragma unroll
   for (int i = 0; i < 3 * LPL; i++) {
     ln.f[i] = f12[3 * LPL * j + i];
@@ -398,45 +490,47 @@ QPB_HD void lane_init(Lane<LPL>& ln, int j, const double* f12, const double* r12
   }
   ln.word = word;
   ln.stance = stance;
-  ln.p = -1;
-  ln.pc = 0u;
+  // the loop enters with its first row chosen (by the set-up pass); its slack follows from row_slack_share()
+  ln.p = (key >> 31) ? (int)(key & 15u) : -1;
+  ln.pc = (key & 16u) ? 2u : 1u;
   ln.up = 0.0;
   ln.sp = 0.0;
-  ln.iters = 0;
+  ln.iters = iters;  // working-set changes already spent by the set-up's block rounds
   ln.status = status;
-  ln.done = status != QPB_OK;
+  ln.done = status != QPB_OK || ln.p < 0;
 }
 
-// side block of a QP while it is iterated on (shared memory on the device): b (6), G (21), lever arms (12)
-enum : int { kSideB = 0, kSideG = 6, kSideR = 27, kSideSize = 39 };
+// This lane's share of the slack n' f - bound of the pending row (the lane that owns its leg has all of it).
+template <int LPL>
+QPB_HD double row_slack_share(const FastParams& K, const Lane<LPL>& ln, int j) {
+  const int p = ln.p < 0 ? 0 : ln.p;
+  const int pl = (p * 11) >> 5, pg = p - 3 * pl;
+  double n[3], dp, share = 0.0;
+  row_normal(K, pg, ln.pc, n, dp);
+#pragma unroll
+  for (int li = 0; li < LPL; li++)
+    if (LPL * j + li == pl) share = (n[0] * ln.f[3 * li] + n[1] * ln.f[3 * li + 1] + n[2] * ln.f[3 * li + 2]) - dp;
+  return ln.p < 0 ? 0.0 : share;
+}
 
-// Exchange 1 (integer max over the group): the most violated row among the groups that are not active.  Key: the high
-// word of (slack - tolerance) orders negative doubles by magnitude as an unsigned integer; low 5 bits = 3 leg + group,
-// + 16 for row B.  (The other row of an ACTIVE group can only be violated while fz < 0; the fz row of that leg then
-// goes first.)  0 from lanes that are not selecting.
+// side block of a QP while it is iterated on (shared memory on the device): G (21), lever arms of all legs (12)
+enum : int { kSideG = 0, kSideR = 21, kSideSize = 33 };
+
+// Prepared record: what the set-up pass hands to the loop and the loop hands to the finishing pass (64 doubles):
+// f (12), r (12), u (12), b (6), G (21), meta.  meta: low word = working set | stance << 24 | status << 28, high word =
+// working-set changes used (written by the loop).
+enum : int { kPrepF = 0, kPrepR = 12, kPrepU = 24, kPrepB = 36, kPrepG = 42, kPrepMeta = 63, kPrepSize = 64 };
+
+// Exchange 1 (integer max over the group): the most violated row among the groups that are not active (leg_key).
+// 0 from lanes that are not selecting.
 template <int LPL>
 QPB_HD uint32_t select_local(const FastParams& K, const Lane<LPL>& ln, int j) {
   uint32_t best = 0u;
 #pragma unroll
   for (int li = 0; li < LPL; li++) {
     const int i = LPL * j + li;  // leg
-    const bool stance = (ln.stance >> i) & 1u;
-    const uint32_t c = ln.word >> (6 * i);
-    const double fx = ln.f[3 * li], fy = ln.f[3 * li + 1], fz = ln.f[3 * li + 2];
-    const double base = fma(K.mu, fz, 1e-9);
-    const double slx = base - fabs(fx), sly = base - fabs(fy);
-    const double sA = (fz - K.fzmin) - K.ntol_z, sB = (K.fzmax - fz) - K.ntol_z;
-    const uint32_t id = (uint32_t)(3 * i);
-    const uint32_t kx = ((uint32_t)hi32(slx) & ~31u) | id | (hi32(fx) < 0 ? 16u : 0u);  // fx > 0: row A binds
-    const uint32_t ky = ((uint32_t)hi32(sly) & ~31u) | (id + 1u) | (hi32(fy) < 0 ? 16u : 0u);
-    const uint32_t ka = ((uint32_t)hi32(sA) & ~31u) | (id + 2u);
-    const uint32_t kb = ((uint32_t)hi32(sB) & ~31u) | (id + 2u) | 16u;
-    const uint32_t mx = (stance && (c & 3u) == 0u) ? kx : 0u;
-    const uint32_t my = (stance && (c & 12u) == 0u) ? ky : 0u;
-    const uint32_t mz = (stance && (c & 48u) == 0u) ? (ka > kb ? ka : kb) : 0u;
-    const uint32_t m1 = mx > my ? mx : my;
-    const uint32_t m2 = m1 > mz ? m1 : mz;
-    best = best > m2 ? best : m2;
+    const uint32_t k = leg_key(K, ln.f[3 * li], ln.f[3 * li + 1], ln.f[3 * li + 2], ln.word >> (6 * i), (ln.stance >> i) & 1u, i);
+    best = best > k ? best : k;
   }
   return (ln.done || ln.p >= 0) ? 0u : best;
 }
@@ -446,7 +540,6 @@ QPB_HD uint32_t select_local(const FastParams& K, const Lane<LPL>& ln, int j) {
 template <int LPL>
 QPB_HD double select_commit(const FastParams& K, Lane<LPL>& ln, int j, uint32_t best, bool& fresh) {
   fresh = false;
-  double contrib = 0.0;
   if (!ln.done && ln.p < 0) {
     if ((best >> 31) == 0u) {
       ln.done = true;  // no inactive group is violated: the loop ends here (polish() re-checks every row)
@@ -455,15 +548,9 @@ QPB_HD double select_commit(const FastParams& K, Lane<LPL>& ln, int j, uint32_t 
       ln.p = (int)(best & 15u);
       ln.pc = (best & 16u) ? 2u : 1u;
       ln.up = 0.0;
-      const int pl = (ln.p * 11) >> 5, pg = ln.p - 3 * pl;
-      double n[3], dp;
-      row_normal(K, pg, ln.pc, n, dp);
-#pragma unroll
-      for (int li = 0; li < LPL; li++)
-        if (LPL * j + li == pl) contrib = (n[0] * ln.f[3 * li] + n[1] * ln.f[3 * li + 1] + n[2] * ln.f[3 * li + 2]) - dp;
     }
   }
-  return contrib;
+  return fresh ? row_slack_share<LPL>(K, ln, j) : 0.0;
 }
 
 template <int LPL>
@@ -630,9 +717,10 @@ QPB_HD uint32_t stance_mask(uint32_t cbytes) {
 }
 
 // rec: slots 0..47 of the state record (attitudes, twists, feet).  hint: bit 31 set = bits 0..23 hold a working set.
-template <class Params>
+// commit(st, G, key) receives every dual-feasible starting pair found (the last call wins) -- or the bad-input record.
+template <class Params, class Commit>
 QPB_HD void setup(const Params& P, const FastParams& K, const double* rec, uint32_t cbytes, uint32_t hint, State& st,
-                  double (&b6)[6], double (&G)[21]) {
+                  double (&b6)[6], double (&G)[21], Commit& commit) {
   st.stance = stance_mask(cbytes);
   bool fin = true;
 #pragma unroll
@@ -652,10 +740,18 @@ QPB_HD void setup(const Params& P, const FastParams& K, const double* rec, uint3
 #pragma unroll
     for (int i = 0; i < 6; i++) b6[i] = 0.0;
   }
-  start(K, st, b6, hint, (hint >> 31) != 0u, G);
-  if (!fin) {
+  if (fin) {
+    start(K, st, b6, hint, (hint >> 31) != 0u, G, commit);
+  } else {
+    st.word = 0u;
+    st.iters = 0;
     st.status = QPB_BAD_INPUT;
     st.done = true;
+#pragma unroll
+    for (int i = 0; i < 12; i++) st.f[i] = st.u[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < 21; i++) G[i] = 0.0;
+    commit(st, G, 0u);
   }
 }
 

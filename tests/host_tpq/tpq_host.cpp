@@ -11,25 +11,22 @@
 using namespace qpb::tpq;
 
 template <int LPQ>
-static void solve_loop(const FastParams& K, State& st, const double* G0) {
+static void solve_loop(const FastParams& K, State& st, const double* G0, uint32_t key) {
+  constexpr int LPL = 4 / LPQ;
   double side[kSideSize] = {};
   std::memcpy(side + kSideG, G0, 21 * sizeof(double));
   std::memcpy(side + kSideR, st.r, 12 * sizeof(double));
   double* G = side + kSideG;
-  constexpr int LPL = 4 / LPQ;
   Lane<LPL> ln[LPQ];
-  for (int j = 0; j < LPQ; j++) lane_init(ln[j], j, st.f, st.r, st.u, st.word, st.stance, st.status);
+  double slack = 0.0;
+  for (int j = 0; j < LPQ; j++) {
+    lane_init(ln[j], j, st.f, st.r, st.u, st.word, st.stance, st.status, st.iters, key);
+    slack += row_slack_share(K, ln[j], j);
+  }
+  for (int j = 0; j < LPQ; j++) ln[j].sp = slack;
+  // a trip: direction -> (exchange: blocking row) -> step + working-set change -> selection of the next row
+  // (exchanges: most violated row, its slack).  The loop is entered with the first row already chosen.
   while (!ln[0].done) {
-    uint32_t best = 0;
-    for (int j = 0; j < LPQ; j++) {
-      const uint32_t k = select_local(K, ln[j], j);
-      best = k > best ? k : best;
-    }
-    double slack = 0.0;
-    bool fresh[LPQ];
-    for (int j = 0; j < LPQ; j++) slack += select_commit(K, ln[j], j, best, fresh[j]);
-    for (int j = 0; j < LPQ; j++)
-      if (fresh[j]) ln[j].sp = slack;
     StepTmp<LPL> T[LPQ];
     double ub = 1.0, rb = 0.0;
     int kb = -1;
@@ -49,6 +46,16 @@ static void solve_loop(const FastParams& K, State& st, const double* G0) {
       if (j == 0) std::memcpy(Gnew, sj + kSideG, sizeof(Gnew));
     }
     std::memcpy(G, Gnew, sizeof(Gnew));
+    uint32_t best = 0;
+    for (int j = 0; j < LPQ; j++) {
+      const uint32_t k = select_local(K, ln[j], j);
+      best = k > best ? k : best;
+    }
+    double s2 = 0.0;
+    bool fresh[LPQ];
+    for (int j = 0; j < LPQ; j++) s2 += select_commit(K, ln[j], j, best, fresh[j]);
+    for (int j = 0; j < LPQ; j++)
+      if (fresh[j]) ln[j].sp = s2;
   }
   st.word = ln[0].word;
   st.status = ln[0].status;
@@ -64,12 +71,22 @@ extern "C" int tpq_host_control_batch(const qpb_params* P, const qpb_state_rec* 
     uint32_t cbytes, hint;
     std::memcpy(&cbytes, in[i].contact, 4);
     std::memcpy(&hint, in[i].pad, 4);
-    State st;
-    double b6[6], G[21];
-    setup(*P, K, rec, cbytes, hint, st, b6, G);
-    if (lpq == 4) solve_loop<4>(K, st, G);
-    else if (lpq == 2) solve_loop<2>(K, st, G);
-    else solve_loop<1>(K, st, G);
+    State st, keep;
+    double b6[6], G[21], Gkeep[21];
+    uint32_t key = 0;
+    auto commit = [&](const State& s, const double (&g)[21], uint32_t k) {
+      keep = s;
+      std::memcpy(Gkeep, g, sizeof(Gkeep));
+      key = k;
+    };
+    setup(*P, K, rec, cbytes, hint, st, b6, G, commit);
+    st = keep;  // the loop starts from the last dual-feasible pair the set-up committed
+    std::memcpy(G, Gkeep, sizeof(G));
+    if (st.status == QPB_OK && key != 0u) {  // the set-up's pair is not optimal yet: the loop (the kernel's worklist)
+      if (lpq == 4) solve_loop<4>(K, st, G, key);
+      else if (lpq == 2) solve_loop<2>(K, st, G, key);
+      else solve_loop<1>(K, st, G, key);
+    }
     if (do_polish) polish(K, st, b6);
     double grf[12], tau[12];
     finish(*P, rec, rec + qpb::kQ, st, grf, tau);

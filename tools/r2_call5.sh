@@ -1,0 +1,16 @@
+#!/bin/bash
+# Round 2, GPU call 5: block pre-solve in the set-up pass: parity, start-budget and occupancy A/B, per-kernel times.
+O=gpurun_out
+mkdir -p $O
+QPB_TPQ_MIN_N=0 timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "profiles or mask or bad_input or degenerate or warm or three_entry or general" 2>&1 | tail -3 | sed "s/^/minN0 lpq2: /"
+QPB_TPQ_LPQ=1 timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -q -x 2>&1 | tail -3 | sed "s/^/default lpq1: /"
+for LIB in quadruped_control_b200/libqpb200.so scratch/libs/libqpb_a1d2.so scratch/libs/libqpb_a3d2.so scratch/libs/libqpb_a4d3.so scratch/libs/libqpb_e3.so scratch/libs/libqpb_e4.so; do
+ for L in 1 2; do
+  QPB_LIB=$PWD/$LIB QPB_TPQ_LPQ=$L timeout 200 python bench.py --steps 30 --warmup 5 2>/dev/null | cut -c1-120 | sed "s|^|$(basename $LIB) lpq$L cfg2: |"
+  QPB_LIB=$PWD/$LIB QPB_TPQ_LPQ=$L timeout 200 python bench.py --workload cfg3 --steps 10 --warmup 3 2>/dev/null | cut -c1-120 | sed "s|^|$(basename $LIB) lpq$L cfg3: |"
+ done
+done
+for W in cfg2 cfg3; do
+QPB_TPQ_LPQ=1 timeout 200 ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum,smsp__issue_active.avg.pct_of_peak_sustained_active,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:tpq_ -s 3 -c 3 --csv --log-file $O/r2c5_launches_${W}_lpq1.csv python tools/prof_run.py $W 3 > /dev/null 2>&1
+echo "== launches $W lpq1"; grep -E "tpq_" $O/r2c5_launches_${W}_lpq1.csv | awk -F'","' '{print substr($5,1,40), $(NF-2), $(NF)}' | cut -c1-160
+done
