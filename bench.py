@@ -173,6 +173,22 @@ def cpu_baseline(params, S, budget_s=12.0, check=None):
             "one_thread": one, "c_port_all_cores": port}, err
 
 
+def static_config(desc, n, profile):
+    """The part of `config` both arms print identically (the driver compares the two dicts key by key)."""
+    return {"workload": desc, "qps_per_step_per_gpu": n, "profile": profile, "mu": MU}
+
+
+# FP64 work of the range-space path per QP, as a model (qpb_tpq_core.h): PD target + lever arms (~450 flops), one 6x6
+# solve on a set of faces (~700: G from four legs, Cholesky, two triangular solves, per-leg projections and multipliers)
+# for the starting pair and once more for the polish, ~650 per working-set change (block round or loop iteration:
+# Cholesky + solves + rank-one update + per-leg step and multiplier directions), ~600 for the epilogue (12 sincos, J^T f).
+def balance_algorithmic_flops(iters):
+    return 450.0 + 2 * 700.0 + 600.0 + 650.0 * np.asarray(iters, dtype=np.float64)
+
+
+FP64_PEAK_TFLOPS = 37.2  # DFMA rate measured with tools/ubench_fp64 on the pool's B200 (profiles/r01_ubench_fp64.txt)
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU path for this hot path on the host cores (see _cpu_arm), with all
     the host threads, on our arm's config.  Rank 0 only; other ranks exit without work."""
@@ -207,12 +223,146 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": wdesc, "qps_per_step": per_step, "note": "CPU path on the host cores, rank 0 only; qpOASES/Armadillo/Drake are not installable here (DESIGN.md section 5)"},
+        "config": static_config(wdesc, n, profile),
+        "details": {"qps_per_step": per_step, "note": "CPU path on the host cores, rank 0 only; qpOASES/Armadillo/Drake are not installable here (DESIGN.md section 5)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def kernel_path():
+    """Which balance kernels the default bench command runs (QPB_QPS_PER_WARP / QPB_TPQ_LPQ select experiments)."""
+    m = os.environ.get("QPB_QPS_PER_WARP", "")
+    if m == "1":
+        return "balance_qp_kernel<PackedIO>"
+    if m == "2":
+        return "balance_qp_kernel16<PackedIO>"
+    return f"tpq_setup_kernel<PackedIO> + tpq_loop_kernel<{os.environ.get('QPB_TPQ_LPQ', '1')}> + tpq_finish_kernel<PackedIO>"
+
+
+def fp64_block(iters, n, step_ms):
+    """The explanatory roofline of the balance path: algorithmic FP64 work (balance_algorithmic_flops) over the FP64 pipe."""
+    flops = float(balance_algorithmic_flops(iters).mean())
+    achieved = flops * n / (step_ms * 1e-3) / 1e12
+    return {"achieved": achieved, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": achieved / FP64_PEAK_TFLOPS, "flop_per_qp": flops,
+            "model": "450 + 2 x 700 + 600 + 650 x working-set changes (balance_algorithmic_flops); peak = DFMA rate of tools/ubench_fp64"}
+
+
+def bind_to_local_cpus(local_rank):
+    """Pin this rank to the CPUs next to its GPU (sysfs local_cpulist of the device's PCI function), so that the pinned
+    buffers it allocates next land on that NUMA node and its copies do not cross the socket interconnect."""
+    try:
+        import torch
+
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
+        dom = torch.cuda.get_device_properties(local_rank).pci_domain_id
+        devn = torch.cuda.get_device_properties(local_rank).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{devn:02x}.0/local_cpulist"
+        cpus = set()
+        for part in open(path).read().strip().split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return sorted(cpus)
+    except Exception:
+        pass
+    return None
+
+
+def pcie_bound(pin_in, pin_out, n, dev, barrier, reps=6):
+    """Concurrent pinned H2D + D2H of one step's bytes on two streams, no kernels: ms per step on this rank."""
+    import torch
+
+    d_i = torch.empty(n * STATE_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+    d_o = torch.empty(n * OUT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+    h_i = [torch.from_numpy(b.array.view(np.uint8).reshape(-1)) for b in pin_in]
+    h_o = [torch.from_numpy(b.array.view(np.uint8).reshape(-1)) for b in pin_out]
+    s1, s2 = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+
+    def step(i):
+        with torch.cuda.stream(s1):
+            d_i.copy_(h_i[i % 2], non_blocking=True)
+        with torch.cuda.stream(s2):
+            h_o[i % 2].copy_(d_o, non_blocking=True)
+
+    step(0)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(reps):
+        step(i)
+    s1.synchronize()
+    s2.synchronize()
+    ms = (time.perf_counter() - t0) * 1e3 / reps
+    return {"ms_per_step": ms}
+
+
+def secondary_block(solver, params, rank, world, local_rank, dev, dist, barrier):
+    """BASELINE configs beside the headline one, each timed with >= 3 launches after the headline region:
+    cfg3 (1 048 576 mixed-contact states per GPU) at every N, cfg5 (8 388 608 states over 8 GPUs) when N = 8, and the
+    10-step MPC QP of cfg4.  Values are whole-job QP/s (max over ranks of the device time)."""
+    import torch
+
+    from quadruped_control_b200 import lib
+    from quadruped_control_b200.records import MPC_OUT_DTYPE, default_mpc_params
+
+    out = {}
+    stream = torch.cuda.current_stream()
+    peak, _ = measured_peak_hbm()
+
+    def timed(fn, launches):
+        fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(launches):
+            fn()
+        e1.record(stream)
+        barrier()
+        ms, _ = reduce_report(e0.elapsed_time(e1), [0], dist, dev)
+        return ms / launches
+
+    jobs = [("cfg3", "cfg3")] + ([("cfg5", "cfg5")] if world == 8 else [])
+    for name, wl in jobs:
+        n, seed, masks, profile, desc = WORKLOADS[wl]
+        S = states.generate_states(n, seed, lo=rank * n, profile=profile, masks=masks)
+        d_in = torch.from_numpy(S.view(np.uint8).reshape(-1)).to(dev)
+        d_out = torch.empty(n * OUT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+        ms = timed(lambda: solver.control_packed(d_in, d_out, n, stream.cuda_stream), 3)
+        res = d_out.cpu().numpy().view(OUT_DTYPE)
+        entry = {"workload": desc, "value": world * n / (ms * 1e-3), "unit": UNIT, "ms_per_launch": ms, "launches": 3,
+                 "failed_qps": int((res["status"] != 0).sum()), "iters_mean": float(res["iters"].mean()),
+                 "hbm_frac": ALGO_BYTES_PER_QP * n / (ms * 1e-3) / 1e9 / peak,
+                 "fp64_frac": fp64_block(res["iters"], n, ms)["frac"]}
+        if rank == 0:
+            import oracle
+
+            stride = max(1, n // 1024)
+            ref = oracle.control_batch(params, np.ascontiguousarray(S[::stride]), os.cpu_count() or 1)
+            entry["max_rel_grf_err_vs_oracle"] = float((np.abs(res[::stride]["grf_body"] - ref["grf_body"]).max(axis=1) /
+                                                        np.maximum(np.abs(ref["grf_body"]).max(axis=1), 1.0)).max())
+        out[name] = entry
+        del d_in, d_out, S
+    # cfg4: the 10-step convex-MPC QP
+    mp = default_mpc_params(MU)
+    mpc = lib.MpcSolver(mp, device=local_rank)
+    R = states.generate_mpc(MPC_N, MPC_SEED, lo=rank * MPC_N)
+    d_in = torch.from_numpy(R.view(np.uint8).reshape(-1)).to(dev)
+    d_out = torch.empty(MPC_N * MPC_OUT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+    ms = timed(lambda: mpc.solve_packed(d_in, d_out, MPC_N, stream.cuda_stream), 3)
+    res = d_out.cpu().numpy().view(MPC_OUT_DTYPE)
+    flops = float(mpc_algorithmic_flops(R["contact"], res["iters"]).mean())
+    out["cfg4_mpc"] = {"workload": MPC_DESC, "value": world * MPC_N / (ms * 1e-3), "unit": UNIT, "ms_per_launch": ms, "launches": 3,
+                       "failed_qps": int((res["status"] != 0).sum()), "iters_mean": float(res["iters"].mean()),
+                       "fp64_frac": flops * MPC_N / (ms * 1e-3) / 1e12 / 37.0, "parity": "unpinned by construction: no reference MPC code (DESIGN.md section 9)"}
+    mpc.close()
+    return out
 
 
 def run_ours(args):
@@ -282,22 +432,41 @@ def run_ours(args):
     total_qps = world * n * args.steps / (elapsed_ms * 1e-3)
 
     # ---- end to end through the C ABI with HOST buffers (pinned), copies inside the timed region --
+    # Every step uploads its own 512-B records from pinned host memory and downloads its 256-B results.  Steps are queued
+    # with the asynchronous entry point, two batches in flight, so the upload of step k+1 overlaps the download of step k
+    # (PCIe is full duplex); the final qpb_host_sync() is inside the timed region.  The synchronous call is timed beside it.
+    bind_to_local_cpus(local_rank)
     pin_in = [lib.PinnedBuffer(n, STATE_DTYPE) for _ in range(2)]
-    pin_out = lib.PinnedBuffer(n, OUT_DTYPE)
+    pin_out = [lib.PinnedBuffer(n, OUT_DTYPE) for _ in range(2)]
     for k in range(2):
         pin_in[k].array[:] = host_batches[k % n_rot]
     e2e_steps = max(3, min(args.steps, 20))
     for i in range(2):
-        solver.control_host(pin_in[i % 2].array, pin_out.array)
+        solver.control_host(pin_in[i % 2].array, pin_out[i % 2].array)
     barrier()
     t0 = time.perf_counter()
     for i in range(e2e_steps):
-        solver.control_host(pin_in[i % 2].array, pin_out.array)
+        solver.control_host(pin_in[i % 2].array, pin_out[i % 2].array)
+    sync_local = (time.perf_counter() - t0) * 1e3
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        solver.control_host_async(pin_in[i % 2].array, pin_out[i % 2].array)
+    solver.host_sync()
     e2e_local = (time.perf_counter() - t0) * 1e3
     barrier()
     e2e_ms, _ = reduce_report(e2e_local, [0], dist, dev)
+    sync_ms, _ = reduce_report(sync_local, [0], dist, dev)
     e2e_qps = world * n * e2e_steps / (e2e_ms * 1e-3)
-    e2e_checksum_ok = bool((pin_out.array["status"] == 0).all())
+    e2e_sync_qps = world * n * e2e_steps / (sync_ms * 1e-3)
+    e2e_checksum_ok = bool((pin_out[0].array["status"] == 0).all() and (pin_out[1].array["status"] == 0).all())
+    # the same bytes with no solver in between: what the PCIe link (and the host memory behind it) gives this rank while
+    # every rank does the same -- the bound of the end-to-end number
+    pcie = pcie_bound(pin_in, pin_out, n, dev, barrier)
+    pcie_ms, _ = reduce_report(pcie["ms_per_step"], [0], dist, dev)
+    pcie_qps = world * n / (pcie_ms * 1e-3)
+
+    secondary = secondary_block(solver, params, rank, world, local_rank, dev, dist, barrier) if (args.secondary and args.workload == "cfg2") else None
 
     if rank == 0:
         # the CPU-baseline leg also checks what was just timed against the oracle (strided sample of the last step)
@@ -311,29 +480,35 @@ def run_ours(args):
             "metric": METRIC, "value": total_qps, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": desc, "qps_per_step_per_gpu": n, "global_batch": world * n, "parallelism": f"batch-sharded x{world}",
-                       "l2": f"{n_rot} distinct device batches rotate ({n_rot * n * 768 / 1e6:.0f} MB > 126 MB L2)" if n_rot * n * 768 > 126e6 else "inputs larger than L2",
-                       "iters_mean": float(last["iters"].mean()), "iters_max": int(last["iters"].max()),
-                       "profile": profile,
-                       "active_rows_hist": active_rows_histogram(host_batches[(args.steps - 1) % n_rot], last, params.mu, params.fzmin, params.fzmax)},
+            "config": static_config(desc, n, profile),
+            "details": {"global_batch": world * n, "parallelism": f"batch-sharded x{world}",
+                        "l2": f"{n_rot} distinct device batches rotate ({n_rot * n * 768 / 1e6:.0f} MB > 126 MB L2)" if n_rot * n * 768 > 126e6 else "inputs larger than L2",
+                        "iters_mean": float(last["iters"].mean()), "iters_max": int(last["iters"].max()),
+                        "kernel_path": kernel_path(),
+                        "active_rows_hist": active_rows_histogram(host_batches[(args.steps - 1) % n_rot], last, params.mu, params.fzmin, params.fzmax)},
             "max_rel_grf_err_vs_oracle": err, "failed_qps": int(tot_failed),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic_per_launch(args.workload), "peak_source": peak_src,
-                         "ncu": ncu_explanatory(args.workload),
-                         "algorithmic_bytes_per_qp": ALGO_BYTES_PER_QP, "kernel": {"1": "balance_qp_kernel<PackedIO>", "2": "balance_qp_kernel16<PackedIO>"}.get(os.environ.get("QPB_QPS_PER_WARP", ""), "balance_qp_tpq_kernel<PackedIO>"),
+                         "ncu": ncu_explanatory(args.workload), "static": "traffic and ncu are copied from profiles/ncu_summary.json (one ncu capture of this command), not measured by this run",
+                         "algorithmic_bytes_per_qp": ALGO_BYTES_PER_QP, "kernel": kernel_path(),
                          "kernel_ms": kernel_ms,
+                         "fp64": fp64_block(last["iters"], n, kernel_ms),
                          "note": "the path is FP64-issue/latency bound, not DRAM bound (DESIGN.md); per-GPU figure"},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_qps, "unit": UNIT, "h2d_bytes_per_step": n * STATE_DTYPE.itemsize,
                     "d2h_bytes_per_step": n * OUT_DTYPE.itemsize, "steps": e2e_steps, "ok": e2e_checksum_ok,
-                    "api": "qpb_control_batch_host (pinned host buffers; the kernel reads records and writes results over PCIe itself)"},
+                    "api": "qpb_control_batch_host_async x steps + qpb_host_sync (pinned host buffers, two batches in flight, staged H2D / kernels / D2H)",
+                    "sync_call_value": e2e_sync_qps, "sync_api": "qpb_control_batch_host (returns when the batch is complete)",
+                    "pcie_bound_qps": pcie_qps, "pcie_bound_gbs": pcie_qps * (STATE_DTYPE.itemsize + OUT_DTYPE.itemsize) / 1e9,
+                    "pcie_frac": e2e_qps / pcie_qps,
+                    "pcie_note": "bound = the same pinned buffers copied H2D and D2H concurrently (cudaMemcpyAsync on two streams) on every rank at once, no kernels"},
+            "secondary": secondary,
             "gpu_launches": int(tot_launches),
             "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
-    for b in pin_in:
+    for b in pin_in + pin_out:
         b.free()
-    pin_out.free()
     solver.close()
     if dist is not None:
         dist.barrier()
@@ -670,6 +845,8 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=("ours", "reference"), default="ours")
+    ap.add_argument("--no-secondary", dest="secondary", action="store_false",
+                    help="skip the cfg3 / cfg5 / cfg4 block timed after the headline region (default: on for the cfg2 line)")
     ap.add_argument("--workload", choices=sorted(WORKLOADS) + ["cfg4", "tick"], default="cfg2")
     ap.add_argument("--profile", choices=("default", "light", "stress"), default=None,
                     help="disturbance profile of the synthetic states (SURVEY.md 8d); default: the workload's own")

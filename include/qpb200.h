@@ -113,6 +113,15 @@ int qpb_control_batch(qpb_handle* h, int64_t n, const double* Rwb, const double*
  * chunks, solved and copied back, overlapping the three on internal streams. */
 int qpb_control_batch_host(qpb_handle* h, int64_t n, const qpb_state_rec* h_states, qpb_out_rec* h_out);
 
+/* Asynchronous form for callers that step many batches (a simulator bridge): queues the uploads, kernels and downloads
+ * of this batch on the handle's internal streams and returns; h_out is complete after qpb_host_sync().  Several calls
+ * may be in flight, so the upload of batch k+1 overlaps the download of batch k (PCIe is full duplex).  The buffers must
+ * stay valid and untouched until the sync; pass pinned memory (qpb_host_alloc), pageable buffers make the copies
+ * synchronous.  Not re-entrant: one calling thread per handle, as for BalanceController::control (mutable solver state,
+ * balance_controller.hpp:161, 171-176). */
+int qpb_control_batch_host_async(qpb_handle* h, int64_t n, const qpb_state_rec* h_states, qpb_out_rec* h_out);
+int qpb_host_sync(qpb_handle* h);
+
 /* jacobianTransposeControl() alone (kinematics.cpp:218-231): tau = J(q)^T f for stance legs,
  * 0 for swing legs.  Device pointers: q [n*12], grf_body [n*12], contact [n*4] (NULL = all stance). */
 int qpb_jt_batch(qpb_handle* h, int64_t n, const double* q, const double* grf_body, const uint8_t* contact,

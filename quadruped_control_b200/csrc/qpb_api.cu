@@ -99,6 +99,7 @@ struct qpb_handle {
   unsigned char* h_small = nullptr;  // host address of the pinned block
   unsigned char* d_small = nullptr;  // its device alias
   int64_t host_chunk = 8192;  // records per H2D/kernel/D2H pipeline stage (QPB_HOST_CHUNK overrides)
+  uint64_t host_slot = 0;     // next stage of the host pipeline (stages of successive asynchronous calls keep rotating)
   int zero_copy = 1;          // pinned host buffers are read/written by the kernel itself over PCIe (QPB_ZEROCOPY=0: always stage)
 };
 
@@ -124,15 +125,18 @@ inline qpb::SplitIO offset_io(const qpb::SplitIO& io, int64_t lo) {
 }
 
 template <class IO>
-int launch_balance(qpb_handle* h, const IO& io, int64_t n, int ctas_per_sm, cudaStream_t stream) {
+int launch_balance(qpb_handle* h, const IO& io, int64_t n, int ctas_per_sm, cudaStream_t stream, int force_path = 0) {
   if (n == 0) return QPB_SUCCESS;
   if (n > kMaxRecordsPerLaunch) return fail(QPB_ERR_INVALID_ARG, "more than 2^31 records in one call: split the batch");
-  int per_warp = h->qps_per_warp;  // 1: one warp per QP; 2: two QPs per warp (half-warp kernel); 32: range-space path
+  // 1: one warp per QP; 2: two QPs per warp (half-warp kernel); 32: range-space path.  force_path: a caller that cuts a
+  // batch into pieces (the host pipeline) picks the path once, by the size of the whole batch, so that a record's result
+  // does not depend on which piece it fell into.
+  int per_warp = h->qps_per_warp;
   // Launch i draws its work tickets from pair i % R of the ring; the last CTA of a launch re-arms the pair, so a launch
   // is self-contained (safe under CUDA-graph replay) as long as fewer than R = 4096 launches of a handle are in flight.
   const uint32_t slot = h->ticket_slot.fetch_add(1, std::memory_order_relaxed) % kTicketSlots;
   unsigned long long* t0 = h->d_tickets + 4 * (size_t)slot;  // {work ticket, CTAs finished, worklist entries, -}
-  if (per_warp == 32 && n >= h->tpq_min_n) {
+  if (per_warp == 32 && (force_path ? force_path == 32 : n >= h->tpq_min_n)) {
     // Three passes over scratch memory (qpb_tpq.cuh): set-up -> prepared records, the active-set loop, polish + epilogue.
     // The scratch comes from the stream-ordered allocator, so concurrent calls on different streams never share it.
     const int lpq = h->tpq_lpq;
@@ -147,15 +151,16 @@ int launch_balance(qpb_handle* h, const IO& io, int64_t n, int ctas_per_sm, cuda
       unsigned long long* tk = h->d_tickets + 4 * (size_t)slot2;
       const unsigned edge = (unsigned)((m + qpb::tpq::kEdgeThreads - 1) / qpb::tpq::kEdgeThreads);
       qpb::tpq::tpq_setup_kernel<IO><<<edge, qpb::tpq::kEdgeThreads, 0, stream>>>(h->params, h->fast, part, m, prep, work, tk);
-      const int64_t want = (m * lpq + qpb::tpq::kLoopThreads - 1) / qpb::tpq::kLoopThreads;
+      const int lthreads = lpq == 1 ? qpb::tpq::LoopShape<1>::THREADS : (lpq == 2 ? qpb::tpq::LoopShape<2>::THREADS : qpb::tpq::LoopShape<4>::THREADS);
+      const int64_t want = (m * lpq + lthreads - 1) / lthreads;
       const int64_t cap = (int64_t)h->num_sms * h->ctas_per_sm_tpq[lpq];
       const int grid = (int)(want < cap ? want : cap);
       if (lpq == 1)
-        qpb::tpq::tpq_loop_kernel<1><<<grid, qpb::tpq::kLoopThreads, 0, stream>>>(h->fast, prep, work, tk);
+        qpb::tpq::tpq_loop_kernel<1><<<grid, lthreads, 0, stream>>>(h->fast, prep, work, tk);
       else if (lpq == 2)
-        qpb::tpq::tpq_loop_kernel<2><<<grid, qpb::tpq::kLoopThreads, 0, stream>>>(h->fast, prep, work, tk);
+        qpb::tpq::tpq_loop_kernel<2><<<grid, lthreads, 0, stream>>>(h->fast, prep, work, tk);
       else
-        qpb::tpq::tpq_loop_kernel<4><<<grid, qpb::tpq::kLoopThreads, 0, stream>>>(h->fast, prep, work, tk);
+        qpb::tpq::tpq_loop_kernel<4><<<grid, lthreads, 0, stream>>>(h->fast, prep, work, tk);
       qpb::tpq::tpq_finish_kernel<IO><<<edge, qpb::tpq::kEdgeThreads, 0, stream>>>(h->params, h->fast, part, m, prep);
       h->launches.fetch_add(3, std::memory_order_relaxed);
       QPB_CUDA(cudaGetLastError());
@@ -210,11 +215,26 @@ int ensure_small(qpb_handle* h) {
 // Host-buffer path shared by qpb_control_batch_host and qpb_tick_batch_host.  Pinned buffers of the balance path are
 // handed to the kernel directly; otherwise stages of records are uploaded, solved and downloaded on a ring of
 // streams so the three overlap (the tick always stages: its second kernel would re-read the records over PCIe).
-int host_pipeline(qpb_handle* h, int64_t n, const qpb_state_rec* h_states, const qpb_swing_rec* h_swing, qpb_out_rec* h_out) {
+int sync_pipeline(qpb_handle* h) {
+  cudaError_t first = cudaSuccess;
+  for (int s = 0; s < kHostSlots; s++)
+    if (h->streams[s]) {
+      const cudaError_t e = cudaStreamSynchronize(h->streams[s]);
+      if (e != cudaSuccess && first == cudaSuccess) first = e;
+    }
+  if (first != cudaSuccess) return fail(QPB_ERR_CUDA, std::string("cudaStreamSynchronize: ") + cudaGetErrorString(first));
+  return QPB_SUCCESS;
+}
+
+int host_pipeline(qpb_handle* h, int64_t n, const qpb_state_rec* h_states, const qpb_swing_rec* h_swing, qpb_out_rec* h_out,
+                  bool async = false) {
   if (n == 0) return QPB_SUCCESS;
   DeviceGuard guard(h->device);
   if (!guard.ok) return fail(QPB_ERR_CUDA, "cudaSetDevice failed");
-  if (h->zero_copy && n <= kSmallCall) {
+  // one path for the whole batch, whatever the pieces it is cut into
+  const bool range_space = h->qps_per_warp == 32 && n >= h->tpq_min_n;
+  const int path = range_space ? 32 : (h->qps_per_warp == 32 ? 2 : h->qps_per_warp);
+  if (!async && h->zero_copy && n <= kSmallCall) {
     // Latency path for per-tick callers: stage through the handle's pinned block, kernels work on its device alias.
     const int rc0 = ensure_small(h);
     if (rc0 != QPB_SUCCESS) return rc0;
@@ -224,7 +244,7 @@ int host_pipeline(qpb_handle* h, int64_t n, const qpb_state_rec* h_states, const
     const qpb_state_rec* ds = reinterpret_cast<const qpb_state_rec*>(h->d_small);
     qpb_out_rec* dout = reinterpret_cast<qpb_out_rec*>(h->d_small + off_out);
     qpb::PackedIO io{ ds, dout };
-    int rc = launch_balance(h, io, n, h->ctas_per_sm_packed, h->streams[0]);
+    int rc = launch_balance(h, io, n, h->ctas_per_sm_packed, h->streams[0], path);
     if (rc == QPB_SUCCESS && h_swing)
       rc = launch_swing(h, n, ds, reinterpret_cast<const qpb_swing_rec*>(h->d_small + off_sw), dout, h->streams[0]);
     if (rc != QPB_SUCCESS) return rc;
@@ -232,16 +252,16 @@ int host_pipeline(qpb_handle* h, int64_t n, const qpb_state_rec* h_states, const
     std::memcpy(h_out, h->h_small + off_out, (size_t)n * sizeof(qpb_out_rec));
     return QPB_SUCCESS;
   }
-  if (h->zero_copy && !h_swing) {
-    // Pinned (hence mapped) buffers: one launch reads the records and writes the results straight over PCIe.  No
-    // staging copies, no pipeline fill/drain: 0.73 ms instead of 0.88 ms per 65 536 records (H2D alone takes 0.65 ms).
-    // Pageable buffers fall through to the staged pipeline below.
+  if (!async && h->zero_copy && !h_swing && !range_space) {
+    // Pinned (hence mapped) buffers and the one-launch kernels: the launch reads the records and writes the results
+    // straight over PCIe, one coalesced 512-B request per record.  No staging copies, no pipeline fill/drain.  (The
+    // range-space path makes three passes over its records, so it always stages them in device memory.)
     cudaPointerAttributes ai, ao;
     if (cudaPointerGetAttributes(&ai, h_states) == cudaSuccess && cudaPointerGetAttributes(&ao, h_out) == cudaSuccess &&
         ai.type == cudaMemoryTypeHost && ao.type == cudaMemoryTypeHost && ai.devicePointer && ao.devicePointer) {
       if (!h->streams[0]) QPB_CUDA(cudaStreamCreateWithFlags(&h->streams[0], cudaStreamNonBlocking));
       qpb::PackedIO io{ static_cast<const qpb_state_rec*>(ai.devicePointer), static_cast<qpb_out_rec*>(ao.devicePointer) };
-      const int rc = launch_balance(h, io, n, h->ctas_per_sm_packed, h->streams[0]);
+      const int rc = launch_balance(h, io, n, h->ctas_per_sm_packed, h->streams[0], path);
       if (rc != QPB_SUCCESS) return rc;
       QPB_CUDA(cudaStreamSynchronize(h->streams[0]));
       return QPB_SUCCESS;
@@ -255,26 +275,42 @@ int host_pipeline(qpb_handle* h, int64_t n, const qpb_state_rec* h_states, const
     if (!h->d_out[s]) QPB_CUDA(cudaMalloc(&h->d_out[s], kHostChunkMax * sizeof(qpb_out_rec)));
     if (h_swing && !h->d_sw[s]) QPB_CUDA(cudaMalloc(&h->d_sw[s], kHostChunkMax * sizeof(qpb_swing_rec)));
   }
-  int slot = 0;
-  // Stage sizes halve towards the end of the batch so the last kernel + download (the part of the pipeline that
-  // cannot overlap an upload) is short.
+  // Stages of records are uploaded, solved and downloaded on a ring of streams, so the copy engines and the SMs overlap.
+  // One-launch kernels: stage sizes halve towards the end of the batch so the last kernel + download (the part that
+  // cannot overlap an upload) is short.  Range-space path (three launches per stage): about eight equal stages.
   const int64_t chunk = h->host_chunk, min_chunk = 1024;
-  for (int64_t lo = 0, m = 0; lo < n; lo += m, slot = (slot + 1) % kHostSlots) {
+  int64_t even = ((n + 7) / 8 + 1023) / 1024 * 1024;
+  if (even < 4096) even = 4096;
+  if (even > kHostChunkMax) even = kHostChunkMax;
+  int rc = QPB_SUCCESS;
+  cudaError_t ce = cudaSuccess;
+  for (int64_t lo = 0, m = 0; lo < n && rc == QPB_SUCCESS && ce == cudaSuccess; lo += m) {
     const int64_t left = n - lo;
-    m = left / 2 > chunk ? chunk : (left / 2 > min_chunk ? left / 2 : (left < min_chunk * 2 ? left : min_chunk));
-    if (m > chunk) m = chunk;
+    if (range_space) {
+      m = left < even ? left : even;
+    } else {
+      m = left / 2 > chunk ? chunk : (left / 2 > min_chunk ? left / 2 : (left < min_chunk * 2 ? left : min_chunk));
+      if (m > chunk) m = chunk;
+    }
+    const int slot = (int)(h->host_slot++ % kHostSlots);
     cudaStream_t st = h->streams[slot];
-    QPB_CUDA(cudaMemcpyAsync(h->d_in[slot], h_states + lo, m * sizeof(qpb_state_rec), cudaMemcpyHostToDevice, st));
-    if (h_swing)
-      QPB_CUDA(cudaMemcpyAsync(h->d_sw[slot], h_swing + lo, m * sizeof(qpb_swing_rec), cudaMemcpyHostToDevice, st));
+    ce = cudaMemcpyAsync(h->d_in[slot], h_states + lo, m * sizeof(qpb_state_rec), cudaMemcpyHostToDevice, st);
+    if (ce == cudaSuccess && h_swing)
+      ce = cudaMemcpyAsync(h->d_sw[slot], h_swing + lo, m * sizeof(qpb_swing_rec), cudaMemcpyHostToDevice, st);
+    if (ce != cudaSuccess) break;
     qpb::PackedIO io{ h->d_in[slot], h->d_out[slot] };
-    int rc = launch_balance(h, io, m, h->ctas_per_sm_packed, st);
+    rc = launch_balance(h, io, m, h->ctas_per_sm_packed, st, path);
     if (rc == QPB_SUCCESS && h_swing) rc = launch_swing(h, m, h->d_in[slot], h->d_sw[slot], h->d_out[slot], st);
-    if (rc != QPB_SUCCESS) return rc;
-    QPB_CUDA(cudaMemcpyAsync(h_out + lo, h->d_out[slot], m * sizeof(qpb_out_rec), cudaMemcpyDeviceToHost, st));
+    if (rc != QPB_SUCCESS) break;
+    ce = cudaMemcpyAsync(h_out + lo, h->d_out[slot], m * sizeof(qpb_out_rec), cudaMemcpyDeviceToHost, st);
   }
-  for (int s = 0; s < kHostSlots; s++) QPB_CUDA(cudaStreamSynchronize(h->streams[s]));
-  return QPB_SUCCESS;
+  if (rc != QPB_SUCCESS || ce != cudaSuccess) {
+    // earlier stages may still be copying into the caller's buffers: never return while they are in flight
+    const std::string msg = ce != cudaSuccess ? std::string("host pipeline: ") + cudaGetErrorString(ce) : g_last_error;
+    (void)sync_pipeline(h);
+    return fail(ce != cudaSuccess ? QPB_ERR_CUDA : rc, msg);
+  }
+  return async ? QPB_SUCCESS : sync_pipeline(h);
 }
 
 }  // namespace
@@ -376,9 +412,9 @@ int qpb_create(const qpb_params* params, int device, qpb_handle** out) {
       e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, qpb::balance_qp_kernel16<qpb::SplitIO>, qpb::WARPS_PER_CTA * 32, 0);
     h->ctas_per_sm_16 = a < b ? a : b;
   }
-  if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->ctas_per_sm_tpq[1], qpb::tpq::tpq_loop_kernel<1>, qpb::tpq::kLoopThreads, 0);
-  if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->ctas_per_sm_tpq[2], qpb::tpq::tpq_loop_kernel<2>, qpb::tpq::kLoopThreads, 0);
-  if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->ctas_per_sm_tpq[4], qpb::tpq::tpq_loop_kernel<4>, qpb::tpq::kLoopThreads, 0);
+  if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->ctas_per_sm_tpq[1], qpb::tpq::tpq_loop_kernel<1>, qpb::tpq::LoopShape<1>::THREADS, 0);
+  if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->ctas_per_sm_tpq[2], qpb::tpq::tpq_loop_kernel<2>, qpb::tpq::LoopShape<2>::THREADS, 0);
+  if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->ctas_per_sm_tpq[4], qpb::tpq::tpq_loop_kernel<4>, qpb::tpq::LoopShape<4>::THREADS, 0);
   if (e == cudaSuccess) {  // keep freed scratch in the stream-ordered pool instead of returning it to the OS after every call
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -471,6 +507,19 @@ int qpb_control_batch_host(qpb_handle* h, int64_t n, const qpb_state_rec* h_stat
   if (!h || n < 0 || (n > 0 && (!h_states || !h_out)))
     return fail(QPB_ERR_INVALID_ARG, "qpb_control_batch_host: bad argument");
   return host_pipeline(h, n, h_states, nullptr, h_out);
+}
+
+int qpb_control_batch_host_async(qpb_handle* h, int64_t n, const qpb_state_rec* h_states, qpb_out_rec* h_out) {
+  if (!h || n < 0 || (n > 0 && (!h_states || !h_out)))
+    return fail(QPB_ERR_INVALID_ARG, "qpb_control_batch_host_async: bad argument");
+  return host_pipeline(h, n, h_states, nullptr, h_out, true);
+}
+
+int qpb_host_sync(qpb_handle* h) {
+  if (!h) return fail(QPB_ERR_INVALID_ARG, "qpb_host_sync: null handle");
+  DeviceGuard guard(h->device);
+  if (!guard.ok) return fail(QPB_ERR_CUDA, "cudaSetDevice failed");
+  return sync_pipeline(h);
 }
 
 int qpb_set_joint_gains(qpb_handle* h, const qpb_joint_gains* gains) {

@@ -28,7 +28,6 @@
 namespace qpb {
 namespace tpq {
 
-constexpr int kLoopThreads = 128;   // loop kernel: 4 warps per CTA
 constexpr int kEdgeThreads = 128;   // set-up / finishing kernels
 
 // minimum CTAs per SM = the register cap (65536 / (128 threads * MIN_CTAS)); overridable for experiments
@@ -44,10 +43,12 @@ constexpr int kEdgeThreads = 128;   // set-up / finishing kernels
 #ifndef QPB_TPQ_EDGE_MINCTAS
 #define QPB_TPQ_EDGE_MINCTAS 2
 #endif
+// loop kernel shape per lanes-per-QP: threads per CTA (static shared memory must stay under 48 KB), minimum CTAs per SM,
+// records per staged batch
 template <int LPQ> struct LoopShape;
-template <> struct LoopShape<1> { static constexpr int MIN_CTAS = QPB_TPQ_MINCTAS_1; };
-template <> struct LoopShape<2> { static constexpr int MIN_CTAS = QPB_TPQ_MINCTAS_2; };
-template <> struct LoopShape<4> { static constexpr int MIN_CTAS = QPB_TPQ_MINCTAS_4; };
+template <> struct LoopShape<1> { static constexpr int THREADS = 64, MIN_CTAS = 2 * QPB_TPQ_MINCTAS_1, STAGE = 16; };
+template <> struct LoopShape<2> { static constexpr int THREADS = 128, MIN_CTAS = QPB_TPQ_MINCTAS_2, STAGE = 12; };
+template <> struct LoopShape<4> { static constexpr int THREADS = 128, MIN_CTAS = QPB_TPQ_MINCTAS_4, STAGE = 8; };
 
 // ---- exchanges between the LPQ lanes of a QP (xor butterflies inside aligned groups of LPQ lanes) -----------------------
 template <int LPQ>
@@ -220,22 +221,67 @@ tpq_setup_kernel(const __grid_constant__ qpb_params P, const __grid_constant__ F
 }
 
 // ---- pass 2: the active-set loop ----------------------------------------------------------------------------------------
+// Prepared records reach the warp through a staging buffer in shared memory, filled a batch (STAGE records) at a time by
+// asynchronous copies (cp.async, 16 B per lane, one record per instruction) that are issued when the previous batch runs
+// out and waited for only when a lane needs them; the worklist positions and record numbers of the batches after that
+// are claimed (atomicAdd on the ticket) and loaded one and two batches ahead.  An idle lane therefore never sits on a
+// chain of atomic -> index load -> record load (2 us, a whole loop iteration) as it did when every refill went to
+// global memory on the spot (profiles/r02_ncu_tpq_v4_loop_cfg3_digest.txt: long-scoreboard stalls 1.96 per issue).
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 template <int LPQ>
-__global__ void __launch_bounds__(kLoopThreads, LoopShape<LPQ>::MIN_CTAS)
+__global__ void __launch_bounds__(LoopShape<LPQ>::THREADS, LoopShape<LPQ>::MIN_CTAS)
 tpq_loop_kernel(const __grid_constant__ FastParams K, double* __restrict__ prep, const uint32_t* __restrict__ work,
                 unsigned long long* __restrict__ ticket) {
   constexpr int LPL = 4 / LPQ, NS = 32 / LPQ;  // legs per lane, QP slots per warp
+  constexpr int STAGE = LoopShape<LPQ>::STAGE, kLoopThreads = LoopShape<LPQ>::THREADS;
   __shared__ double side_all[(kLoopThreads / LPQ) * kSideSize];
+  __shared__ __align__(16) double stage_all[(kLoopThreads / 32) * STAGE * kPrepSize];
   const int lane = threadIdx.x & 31;
   const int j = lane & (LPQ - 1);                             // lane within its QP
   const uint32_t leaders = 0xffffffffu / ((1u << LPQ) - 1u);  // bit of the first lane of every group
   const uint32_t glt = (1u << (lane & ~(LPQ - 1))) - 1u;      // lanes below this lane's group
   double* side = side_all + (threadIdx.x / LPQ) * kSideSize;
+  double* stage = stage_all + (threadIdx.x >> 5) * STAGE * kPrepSize;
   constexpr int kRefill = (QPB_TPQ_REFILL + LPQ - 1) / LPQ;  // idle QP slots that trigger a retire + refill
 
   const int64_t n = (int64_t)*reinterpret_cast<volatile unsigned long long*>(ticket + 2);  // entries of the worklist
-  bool have = false;   // this lane's group holds a QP
-  bool more = true;    // the ticket has not run past the end of the worklist yet (warp-uniform)
+  // three batches in the pipe: A = staged (copies issued), B = record numbers loaded, C = worklist position claimed
+  auto claim = [&]() -> int64_t {
+    unsigned long long b = 0;
+    if (lane == 0) b = atomicAdd(ticket, (unsigned long long)STAGE);
+    return (int64_t)__shfl_sync(FULL, b, 0);
+  };
+  auto load_recs = [&](int64_t base) -> uint32_t { return (lane < STAGE && base + lane < n) ? __ldg(work + base + lane) : 0u; };
+  int64_t baseB = claim();
+  uint32_t recB = load_recs(baseB);
+  int64_t baseC = claim();
+  uint32_t recA = 0;    // lane i: record of staged entry i
+  int st_n = 0, st_used = 0;  // staged entries of batch A and how many have been handed out
+  bool st_flying = false;     // copies of batch A issued but not waited for yet
+  auto issue_batch = [&]() {  // batch B -> A (start its copies), C -> B (load its record numbers), claim a new C
+    const int64_t left = n - baseB;
+    st_n = left <= 0 ? 0 : (left < STAGE ? (int)left : STAGE);
+    st_used = 0;
+    recA = recB;
+    for (int e = 0; e < st_n; e++) {
+      const uint32_t r = __shfl_sync(FULL, recA, e);
+      cp_async16(stage + e * kPrepSize + 2 * lane, prep + (int64_t)r * kPrepSize + 2 * lane);
+    }
+    cp_async_commit();
+    st_flying = st_n > 0;
+    baseB = baseC;
+    recB = load_recs(baseB);
+    if (baseB < n) baseC = claim();
+  };
+  issue_batch();
+
+  bool have = false;  // this lane's group holds a QP
   int64_t rec = 0;
   Lane<LPL> ln;
   {
@@ -252,46 +298,46 @@ tpq_loop_kernel(const __grid_constant__ FastParams K, double* __restrict__ prep,
         if (j == 0) prep[rec * kPrepSize + kPrepMeta] = pack_meta(ln.word, ln.stance, ln.status, ln.iters, 0u);
         have = false;
       }
-      // refill: idle groups claim the next entries of the worklist (one atomic per warp) and load their share
+      // refill: idle groups take the next staged records
       const uint32_t idle = ~__ballot_sync(FULL, have) & leaders;
       const int want = __popc(idle);
-      if (want > 0 && more) {
-        unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(ticket, (unsigned long long)want);
-        base = __shfl_sync(FULL, base, 0);
-        const int64_t mine = (int64_t)base + __popc(idle & glt);
-        more = (int64_t)base + want < n;
-        const bool take = !have && mine < n;
+      if (want > 0 && st_used < st_n) {
+        if (st_flying) {
+          cp_async_wait_all();
+          __syncwarp();
+          st_flying = false;
+        }
+        const int slot = st_used + __popc(idle & glt);
+        const bool take = !have && slot < st_n;
+        const uint32_t r = __shfl_sync(FULL, recA, take ? slot : 0);
         if (take) {
-          rec = (int64_t)__ldg(work + mine);
-          const double* e = prep + rec * kPrepSize;
-          const double meta = __ldg(e + kPrepMeta);
+          rec = (int64_t)r;
+          const double* e = stage + slot * kPrepSize;
+          const double meta = e[kPrepMeta];
           const uint32_t lo = (uint32_t)__double2loint(meta), hi = (uint32_t)__double2hiint(meta);
-          double f[3 * LPL], u[3 * LPL], r[3 * LPL];
-#pragma unroll
-          for (int i = 0; i < 3 * LPL; i++) {
-            f[i] = __ldg(e + kPrepF + 3 * LPL * j + i);
-            u[i] = __ldg(e + kPrepU + 3 * LPL * j + i);
-            r[i] = __ldg(e + kPrepR + 3 * LPL * j + i);
-          }
-          // lane_init indexes all twelve with the lane's position; it gets arrays that hold just this lane's share
-          lane_init<LPL>(ln, 0, f, r, u, lo & 0xffffffu, (lo >> 24) & 15u, (int)((lo >> 28) & 3u), (int)(hi & 0xffffu),
-                         ((hi >> 16) & 31u) | ((hi >> 21) << 31));
+          // lane_init indexes all twelve with the lane's position in its QP
+          lane_init<LPL>(ln, j, e + kPrepF, e + kPrepR, e + kPrepU, lo & 0xffffffu, (lo >> 24) & 15u, (int)((lo >> 28) & 3u),
+                         (int)(hi & 0xffffu), ((hi >> 16) & 31u) | ((hi >> 21) << 31));
 #pragma unroll
           for (int i = 0; i < (21 + LPQ - 1) / LPQ; i++) {
             const int k = j + LPQ * i;
-            if (k < 21) side[kSideG + k] = __ldg(e + kPrepG + k);
+            if (k < 21) side[kSideG + k] = e[kPrepG + k];
           }
 #pragma unroll
-          for (int i = 0; i < 12 / LPQ; i++) side[kSideR + j + LPQ * i] = __ldg(e + kPrepR + j + LPQ * i);
+          for (int i = 0; i < 12 / LPQ; i++) side[kSideR + j + LPQ * i] = e[kPrepR + j + LPQ * i];
           have = true;
         }
         // the slack of the first row: the lane that owns its leg has it, the others get it here
         const double slack = group_sum<LPQ>(take ? row_slack_share<LPL>(K, ln, j) : 0.0);
         if (take) ln.sp = slack;
+        st_used += want < st_n - st_used ? want : st_n - st_used;
         __syncwarp();
       }
-      if (__ballot_sync(FULL, have) == 0u) break;  // nothing held, nothing left to claim
+      if (st_used == st_n && baseB < n) issue_batch();  // start the next batch; lanes still idle pick it up a round later
+      if (__ballot_sync(FULL, have) == 0u) {
+        if (st_used == st_n) break;  // nothing held, nothing staged, nothing left to claim
+        continue;
+      }
     }
     iterate_group<LPQ>(K, ln, j, side);
     __syncwarp();  // G written by the first lane of a QP is read by its other lanes in the next round

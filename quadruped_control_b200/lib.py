@@ -24,6 +24,8 @@ EXPORTS = (
     "qpb_control_batch_packed",
     "qpb_control_batch",
     "qpb_control_batch_host",
+    "qpb_control_batch_host_async",
+    "qpb_host_sync",
     "qpb_jt_batch",
     "qpb_fk_batch",
     "qpb_jt_batch_host",
@@ -80,6 +82,8 @@ def load():
     L.qpb_control_batch_packed.argtypes = [vp, i64, vp, vp, vp]
     L.qpb_control_batch.argtypes = [vp, i64] + [dp] * 14 + [vp]
     L.qpb_control_batch_host.argtypes = [vp, i64, vp, vp]
+    L.qpb_control_batch_host_async.argtypes = [vp, i64, vp, vp]
+    L.qpb_host_sync.argtypes = [vp]
     L.qpb_jt_batch.argtypes = [vp, i64, dp, dp, dp, dp, vp]
     L.qpb_fk_batch.argtypes = [vp, i64, dp, dp, vp]
     L.qpb_jt_batch_host.argtypes = [vp, i64, dp, dp, dp, dp]
@@ -221,6 +225,7 @@ class MultiBalanceSolver:
         assert states.dtype == STATE_DTYPE and swing.dtype == SWING_DTYPE and len(states) == len(swing)
         if out is None:
             out = np.empty(states.shape[0], dtype=OUT_DTYPE)
+        assert out.dtype == OUT_DTYPE and out.shape[0] == states.shape[0] and out.flags.c_contiguous
         _check(load().qpb_multi_tick_batch_host(self._h, states.shape[0], states.ctypes.data, swing.ctypes.data,
                                                 out.ctypes.data), "qpb_multi_tick_batch_host")
         return out
@@ -273,6 +278,16 @@ class BalanceSolver:
         _check(load().qpb_control_batch_host(self._h, states.shape[0], states.ctypes.data, out.ctypes.data), "qpb_control_batch_host")
         return out
 
+    def control_host_async(self, states: np.ndarray, out: np.ndarray):
+        """Queue one batch (pinned buffers, see PinnedBuffer) and return; ``out`` is complete after host_sync()."""
+        assert states.dtype == STATE_DTYPE and states.flags.c_contiguous
+        assert out.dtype == OUT_DTYPE and out.shape[0] == states.shape[0] and out.flags.c_contiguous
+        _check(load().qpb_control_batch_host_async(self._h, states.shape[0], states.ctypes.data, out.ctypes.data),
+               "qpb_control_batch_host_async")
+
+    def host_sync(self):
+        _check(load().qpb_host_sync(self._h), "qpb_host_sync")
+
     # -- whole control tick: balance QP for stance legs + joint PD for swing legs (commander_node.cpp:482-533) --
     def set_joint_gains(self, gains: JointGains):
         _check(load().qpb_set_joint_gains(self._h, ctypes.byref(gains)), "qpb_set_joint_gains")
@@ -285,6 +300,7 @@ class BalanceSolver:
         assert states.dtype == STATE_DTYPE and swing.dtype == SWING_DTYPE and len(states) == len(swing)
         if out is None:
             out = np.empty(states.shape[0], dtype=OUT_DTYPE)
+        assert out.dtype == OUT_DTYPE and out.shape[0] == states.shape[0] and out.flags.c_contiguous
         _check(load().qpb_tick_batch_host(self._h, states.shape[0], states.ctypes.data, swing.ctypes.data, out.ctypes.data), "qpb_tick_batch_host")
         return out
 
