@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define QPB_VERSION 100
+#define QPB_VERSION 200
 
 typedef enum qpb_error {
   QPB_SUCCESS = 0,
@@ -63,6 +63,11 @@ typedef struct qpb_state_rec {
   double feet[12]; /* body-frame foot positions (FootholdMap), leg-major */
   double q[12];    /* joint angles (JointStatesMap.q), leg-major: hip, thigh, calf */
   uint8_t contact[4];
+  /* pad[0..3]: optional warm start, the counterpart of SQProblem::hotstart between ticks (balance_controller.cpp:177-202).
+   * A little-endian uint32: bit 31 set = bits 0..23 hold the working set qpb_out_rec.pad[0..3] reported for this robot on
+   * the previous tick (copy the four bytes over); 0 = cold start.  The hint only changes the number of working-set
+   * changes, never the result (the optimum is unique); a stale or malformed hint falls back to the cold start.
+   * pad[4..27]: ignored. */
   uint8_t pad[28];
 } qpb_state_rec;
 
@@ -74,6 +79,9 @@ typedef struct qpb_out_rec {
   double tau[12];
   int32_t status;
   int32_t iters; /* working-set changes used */
+  /* pad[0..3]: the working set at the optimum as a little-endian uint32 with bit 31 set (2 bits per leg and row group:
+   * 0 none, 1 / 2 = which side of |fx| <= mu fz, |fy| <= mu fz, fzmin <= fz <= fzmax is active), to be fed back as the
+   * next tick's warm start; 0 when the kernel in use does not report one.  pad[4..55]: zero. */
   uint8_t pad[56];
 } qpb_out_rec;
 
@@ -87,6 +95,10 @@ const char* qpb_last_error(void);
 int qpb_default_params(qpb_params* out);
 
 /* Replaces the BalanceController + QuadrupedKinematics constructors (commander_node.cpp:337-338, 358).
+ * Picks the kernels once: W = w*I with fzmin >= 0 (the reference's configuration, commander_node.cpp:289, 305) takes the
+ * range-space path (three launches: set-up, active-set loop, polish + epilogue; batches below 4096 records and general
+ * W take the one-launch half-warp kernel).  QPB_QPS_PER_WARP=1|2|32, QPB_TPQ_LPQ=1|2|4 and QPB_TPQ_MIN_N in the
+ * environment override the choice (experiments, tests).
  * Rejects (QPB_ERR_BAD_PARAMS): non-finite values, mu <= 0, fzmin > fzmax, fzmax < 0,
  * S or W not symmetric positive definite, max_iter < 1, and 2*mu*fzmax > 1e6 (the reference's
  * finite "far" bounds of +-1e6, balance_controller.cpp:296-297, are provably inactive below that
@@ -95,7 +107,9 @@ int qpb_create(const qpb_params* params, int device, qpb_handle** out);
 int qpb_destroy(qpb_handle* h);
 
 /* control() + jacobianTransposeControl() for n robots; packed records resident on the device.
- * stream is a cudaStream_t (NULL = default stream).  Asynchronous. */
+ * stream is a cudaStream_t (NULL = default stream).  Asynchronous and capturable in a CUDA graph: the work counters a
+ * launch draws from are re-armed by the launch itself, and its scratch comes from the stream-ordered allocator
+ * (cudaMallocAsync).  At most 4096 launches of one handle may be in flight at a time. */
 int qpb_control_batch_packed(qpb_handle* h, int64_t n, const qpb_state_rec* d_states, qpb_out_rec* d_out,
                              void* stream);
 
@@ -108,9 +122,10 @@ int qpb_control_batch(qpb_handle* h, int64_t n, const double* Rwb, const double*
                       const double* w_d, const double* feet_body, const uint8_t* contact, const double* q,
                       double* grf_body, double* tau, int32_t* status, void* stream);
 
-/* Host-buffer entry point; returns when h_out is complete.  Pinned buffers (qpb_host_alloc / cudaHostAlloc) are
- * read and written by the kernel itself over PCIe in one launch; pageable buffers are copied to the device in
- * chunks, solved and copied back, overlapping the three on internal streams. */
+/* Host-buffer entry point; returns when h_out is complete.  The records are copied to the device in stages, solved
+ * and copied back, overlapping the three on internal streams (pinned buffers from qpb_host_alloc make the copies
+ * asynchronous); with the one-launch kernels, pinned buffers are instead read and written by the kernel itself over
+ * PCIe.  The kernels are chosen by the size of the whole batch, so a record's result does not depend on its stage. */
 int qpb_control_batch_host(qpb_handle* h, int64_t n, const qpb_state_rec* h_states, qpb_out_rec* h_out);
 
 /* Asynchronous form for callers that step many batches (a simulator bridge): queues the uploads, kernels and downloads

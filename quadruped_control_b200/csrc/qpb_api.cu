@@ -78,8 +78,8 @@ struct qpb_handle {
   // at qpb_create time overrides the choice (32 is refused when the parameters do not qualify).
   int qps_per_warp = 2;
   int ctas_per_sm_tpq[5] = {};  // indexed by lanes per QP (1, 2, 4)
-  int tpq_lpq = 2;              // lanes per QP of the range-space loop kernel (QPB_TPQ_LPQ=1|2|4 overrides)
-  int64_t tpq_min_n = 4096;     // smaller batches take the half-warp kernel: one launch, lower latency (QPB_TPQ_MIN_N)
+  int tpq_lpq = 1;              // lanes per QP of the range-space loop kernel (QPB_TPQ_LPQ=1|2|4 overrides)
+  int64_t tpq_min_n = 12288;    // smaller batches take the half-warp kernel: one launch, lower latency (QPB_TPQ_MIN_N)
   qpb::tpq::FastParams fast;
   qpb_params params;
   qpb_params* d_params = nullptr;
@@ -143,25 +143,26 @@ int launch_balance(qpb_handle* h, const IO& io, int64_t n, int ctas_per_sm, cuda
     for (int64_t lo = 0; lo < n; lo += kTpqChunk) {
       const int64_t m = n - lo < kTpqChunk ? n - lo : kTpqChunk;
       const IO part = offset_io(io, lo);
-      double* prep = nullptr;  // m prepared records, then the worklist of the loop pass (m record indices)
+      double* prep = nullptr;  // m prepared records, m result words, the worklist of the loop pass (m record indices)
       const size_t prep_bytes = (size_t)m * qpb::tpq::kPrepSize * sizeof(double);
-      QPB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&prep), prep_bytes + (size_t)m * sizeof(uint32_t), stream));
-      uint32_t* work = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(prep) + prep_bytes);
+      QPB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&prep), prep_bytes + (size_t)m * (sizeof(double) + sizeof(uint32_t)), stream));
+      double* res = prep + (size_t)m * qpb::tpq::kPrepSize;
+      uint32_t* work = reinterpret_cast<uint32_t*>(res + m);
       const uint32_t slot2 = lo == 0 ? slot : h->ticket_slot.fetch_add(1, std::memory_order_relaxed) % kTicketSlots;
       unsigned long long* tk = h->d_tickets + 4 * (size_t)slot2;
       const unsigned edge = (unsigned)((m + qpb::tpq::kEdgeThreads - 1) / qpb::tpq::kEdgeThreads);
-      qpb::tpq::tpq_setup_kernel<IO><<<edge, qpb::tpq::kEdgeThreads, 0, stream>>>(h->params, h->fast, part, m, prep, work, tk);
+      qpb::tpq::tpq_setup_kernel<IO><<<edge, qpb::tpq::kEdgeThreads, 0, stream>>>(h->params, h->fast, part, m, prep, res, work, tk);
       const int lthreads = lpq == 1 ? qpb::tpq::LoopShape<1>::THREADS : (lpq == 2 ? qpb::tpq::LoopShape<2>::THREADS : qpb::tpq::LoopShape<4>::THREADS);
       const int64_t want = (m * lpq + lthreads - 1) / lthreads;
       const int64_t cap = (int64_t)h->num_sms * h->ctas_per_sm_tpq[lpq];
       const int grid = (int)(want < cap ? want : cap);
       if (lpq == 1)
-        qpb::tpq::tpq_loop_kernel<1><<<grid, lthreads, 0, stream>>>(h->fast, prep, work, tk);
+        qpb::tpq::tpq_loop_kernel<1><<<grid, lthreads, 0, stream>>>(h->fast, prep, res, work, tk);
       else if (lpq == 2)
-        qpb::tpq::tpq_loop_kernel<2><<<grid, lthreads, 0, stream>>>(h->fast, prep, work, tk);
+        qpb::tpq::tpq_loop_kernel<2><<<grid, lthreads, 0, stream>>>(h->fast, prep, res, work, tk);
       else
-        qpb::tpq::tpq_loop_kernel<4><<<grid, lthreads, 0, stream>>>(h->fast, prep, work, tk);
-      qpb::tpq::tpq_finish_kernel<IO><<<edge, qpb::tpq::kEdgeThreads, 0, stream>>>(h->params, h->fast, part, m, prep);
+        qpb::tpq::tpq_loop_kernel<4><<<grid, lthreads, 0, stream>>>(h->fast, prep, res, work, tk);
+      qpb::tpq::tpq_finish_kernel<IO><<<edge, qpb::tpq::kEdgeThreads, 0, stream>>>(h->params, h->fast, part, m, prep, res);
       h->launches.fetch_add(3, std::memory_order_relaxed);
       QPB_CUDA(cudaGetLastError());
       QPB_CUDA(cudaFreeAsync(prep, stream));

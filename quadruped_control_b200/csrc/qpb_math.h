@@ -11,6 +11,14 @@
 #define QPB_HD inline
 #endif
 
+// warp-wide barrier + memory ordering where lanes of a warp hand data to each other through shared memory; a no-op in
+// the host build (there the lanes of a QP are stepped one after the other)
+#if defined(__CUDA_ARCH__)
+#define QPB_SYNCWARP() __syncwarp()
+#else
+#define QPB_SYNCWARP() ((void)0)
+#endif
+
 namespace qpb {
 
 // MUFU seeds carry >= 20 good bits (e <= 2^-20); one third-order step leaves e^3 <= 2^-60.

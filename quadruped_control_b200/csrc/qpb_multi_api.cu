@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 
 #include <condition_variable>
+#include <exception>
 #include <mutex>
 #include <new>
 #include <string>
@@ -129,31 +130,43 @@ int qpb_multi_shard_range(int64_t n, int shard, int num_shards, int64_t* lo, int
 int qpb_multi_create(const qpb_params* params, const int* devices, int num_devices, qpb_multi_handle** out) {
   if (!params || !out) return qpb_internal_fail(QPB_ERR_INVALID_ARG, "qpb_multi_create: null argument");
   *out = nullptr;
-  std::vector<int> devs;
-  if (devices) {
-    if (num_devices < 1) return qpb_internal_fail(QPB_ERR_INVALID_ARG, "qpb_multi_create: num_devices < 1");
-    devs.assign(devices, devices + num_devices);
-  } else {
-    int c = 0;
-    const int rc = qpb_device_count(&c);
-    if (rc != QPB_SUCCESS) return rc;
-    if (c < 1) return qpb_internal_fail(QPB_ERR_CUDA, "qpb_multi_create: no CUDA device (there is no CPU fallback)");
-    for (int d = 0; d < c; d++) devs.push_back(d);
-  }
-  qpb_multi_handle* m = new (std::nothrow) qpb_multi_handle;
-  if (!m) return qpb_internal_fail(QPB_ERR_NO_MEMORY, "qpb_multi_create: out of host memory");
-  m->workers.resize(devs.size());
-  for (size_t r = 0; r < devs.size(); r++) {
-    m->workers[r].device = devs[r];
-    const int rc = qpb_create(params, devs[r], &m->workers[r].h);
-    if (rc != QPB_SUCCESS) {
-      const std::string msg = qpb_last_error();
-      for (size_t k = 0; k < r; k++) qpb_destroy(m->workers[k].h);
-      delete m;
-      return qpb_internal_fail(rc, "qpb_multi_create: device " + std::to_string(devs[r]) + ": " + msg);
+  if (devices && num_devices < 1) return qpb_internal_fail(QPB_ERR_INVALID_ARG, "qpb_multi_create: num_devices < 1");
+  qpb_multi_handle* m = nullptr;
+  // The C ABI never throws: vector growth, std::string and std::thread construction can (bad_alloc, system_error), so
+  // everything that allocates sits in one try block, and a failure at any point unwinds what was already built --
+  // started workers are told to quit and joined, created handles destroyed.
+  try {
+    std::vector<int> devs;
+    if (devices) {
+      devs.assign(devices, devices + num_devices);
+    } else {
+      int c = 0;
+      const int rc = qpb_device_count(&c);
+      if (rc != QPB_SUCCESS) return rc;
+      if (c < 1) return qpb_internal_fail(QPB_ERR_CUDA, "qpb_multi_create: no CUDA device (there is no CPU fallback)");
+      for (int d = 0; d < c; d++) devs.push_back(d);
     }
+    m = new (std::nothrow) qpb_multi_handle;
+    if (!m) return qpb_internal_fail(QPB_ERR_NO_MEMORY, "qpb_multi_create: out of host memory");
+    m->workers.resize(devs.size());
+    for (size_t r = 0; r < devs.size(); r++) {
+      m->workers[r].device = devs[r];
+      const int rc = qpb_create(params, devs[r], &m->workers[r].h);
+      if (rc != QPB_SUCCESS) {
+        const std::string msg = qpb_last_error();
+        qpb_multi_destroy(m);  // destroys the handles created so far (no worker has been started yet)
+        return qpb_internal_fail(rc, "qpb_multi_create: device " + std::to_string(devs[r]) + ": " + msg);
+      }
+    }
+    for (size_t r = 0; r < devs.size(); r++) m->workers[r].thread = std::thread(worker_main, m, (int)r);
+  } catch (const std::exception& e) {
+    const std::string what = e.what();
+    if (m) qpb_multi_destroy(m);  // sets quit, joins the workers that did start, destroys every handle
+    return qpb_internal_fail(QPB_ERR_NO_MEMORY, "qpb_multi_create: " + what);
+  } catch (...) {
+    if (m) qpb_multi_destroy(m);
+    return qpb_internal_fail(QPB_ERR_NO_MEMORY, "qpb_multi_create: allocation failed");
   }
-  for (size_t r = 0; r < devs.size(); r++) m->workers[r].thread = std::thread(worker_main, m, (int)r);
   *out = m;
   return QPB_SUCCESS;
 }

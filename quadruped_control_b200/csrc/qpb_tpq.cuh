@@ -173,8 +173,11 @@ __device__ __forceinline__ void tpq_store(const SplitIO& io, int64_t rec, const 
 struct PrepCommit {
   double* e;
   uint32_t key;  // first row of the loop at the last pair committed (0: that pair is optimal, no loop needed)
+  double meta;   // meta word of the last pair committed
   __device__ __forceinline__ void operator()(const State& st, const double (&G)[21], uint32_t k) {
     key = k;
+    meta = pack_meta(st.word, st.stance, st.status, st.iters, k);
+    if (k == 0u) return;  // optimal (or unsolvable) already: the loop never sees this record, the finishing pass needs only r, b
     double2* o = reinterpret_cast<double2*>(e);
 #pragma unroll
     for (int i = 0; i < 6; i++) {
@@ -183,14 +186,14 @@ struct PrepCommit {
     }
 #pragma unroll
     for (int i = 0; i < 10; i++) o[kPrepG / 2 + i] = make_double2(G[2 * i], G[2 * i + 1]);
-    o[kPrepG / 2 + 10] = make_double2(G[20], pack_meta(st.word, st.stance, st.status, st.iters, k));
+    o[kPrepG / 2 + 10] = make_double2(G[20], meta);
   }
 };
 
 template <class IO>
 __global__ void __launch_bounds__(kEdgeThreads, QPB_TPQ_EDGE_MINCTAS)
 tpq_setup_kernel(const __grid_constant__ qpb_params P, const __grid_constant__ FastParams K, IO io, int64_t n, double* __restrict__ prep,
-                 uint32_t* __restrict__ work, unsigned long long* __restrict__ ticket) {
+                 double* __restrict__ res, uint32_t* __restrict__ work, unsigned long long* __restrict__ ticket) {
   const int64_t rec = (int64_t)blockIdx.x * kEdgeThreads + threadIdx.x;
   bool need = false;  // this record goes through the active-set loop (its starting pair is not optimal yet)
   if (rec < n) {
@@ -199,7 +202,7 @@ tpq_setup_kernel(const __grid_constant__ qpb_params P, const __grid_constant__ F
     tpq_load(io, rec, v, cbytes, hint);
     State st;
     double b6[6], G[21];
-    PrepCommit commit{ prep + rec * kPrepSize, 0u };
+    PrepCommit commit{ prep + rec * kPrepSize, 0u, 0.0 };
     setup(P, K, v, cbytes, hint, st, b6, G, commit);
     // what does not depend on the working set: lever arms and the right-hand side (after a non-finite input they are zero)
     double2* o = reinterpret_cast<double2*>(commit.e);
@@ -207,6 +210,7 @@ tpq_setup_kernel(const __grid_constant__ qpb_params P, const __grid_constant__ F
     for (int i = 0; i < 6; i++) o[kPrepR / 2 + i] = make_double2(st.r[2 * i], st.r[2 * i + 1]);
 #pragma unroll
     for (int i = 0; i < 3; i++) o[kPrepB / 2 + i] = make_double2(b6[2 * i], b6[2 * i + 1]);
+    res[rec] = commit.meta;  // the result word: final as it stands unless the loop pass takes the record
     need = commit.key != 0u;
   }
   // worklist of the loop pass: one atomic per warp (ticket[2] counts the entries; the loop's last CTA re-arms it)
@@ -236,8 +240,8 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 
 template <int LPQ>
 __global__ void __launch_bounds__(LoopShape<LPQ>::THREADS, LoopShape<LPQ>::MIN_CTAS)
-tpq_loop_kernel(const __grid_constant__ FastParams K, double* __restrict__ prep, const uint32_t* __restrict__ work,
-                unsigned long long* __restrict__ ticket) {
+tpq_loop_kernel(const __grid_constant__ FastParams K, const double* __restrict__ prep, double* __restrict__ res,
+                const uint32_t* __restrict__ work, unsigned long long* __restrict__ ticket) {
   constexpr int LPL = 4 / LPQ, NS = 32 / LPQ;  // legs per lane, QP slots per warp
   constexpr int STAGE = LoopShape<LPQ>::STAGE, kLoopThreads = LoopShape<LPQ>::THREADS;
   __shared__ double side_all[(kLoopThreads / LPQ) * kSideSize];
@@ -295,7 +299,7 @@ tpq_loop_kernel(const __grid_constant__ FastParams K, double* __restrict__ prep,
     if (NS - __popc(busy) >= kRefill || busy == 0u) {
       // retire: a finished QP hands its final working set and iteration count to the finishing pass
       if (have && ln.done) {
-        if (j == 0) prep[rec * kPrepSize + kPrepMeta] = pack_meta(ln.word, ln.stance, ln.status, ln.iters, 0u);
+        if (j == 0) res[rec] = pack_meta(ln.word, ln.stance, ln.status, ln.iters, 0u);
         have = false;
       }
       // refill: idle groups take the next staged records
@@ -360,13 +364,13 @@ tpq_loop_kernel(const __grid_constant__ FastParams K, double* __restrict__ prep,
 template <class IO>
 __global__ void __launch_bounds__(kEdgeThreads, QPB_TPQ_EDGE_MINCTAS)
 tpq_finish_kernel(const __grid_constant__ qpb_params P, const __grid_constant__ FastParams K, IO io, int64_t n,
-                  const double* __restrict__ prep) {
+                  const double* __restrict__ prep, const double* __restrict__ res) {
   const int64_t rec = (int64_t)blockIdx.x * kEdgeThreads + threadIdx.x;
   if (rec >= n) return;
   const double* e = prep + rec * kPrepSize;
   State st;
   double b6[6];
-  const double w = __ldg(e + kPrepMeta);
+  const double w = __ldg(res + rec);
   const uint32_t lo = (uint32_t)__double2loint(w);
   st.word = lo & 0xffffffu;
   st.stance = (lo >> 24) & 15u;

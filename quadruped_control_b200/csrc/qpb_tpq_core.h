@@ -516,10 +516,9 @@ QPB_HD double row_slack_share(const FastParams& K, const Lane<LPL>& ln, int j) {
 // side block of a QP while it is iterated on (shared memory on the device): G (21), lever arms of all legs (12)
 enum : int { kSideG = 0, kSideR = 21, kSideSize = 33 };
 
-// Prepared record: what the set-up pass hands to the loop and the loop hands to the finishing pass (64 doubles):
-// f (12), r (12), u (12), b (6), G (21), meta.  meta: low word = working set | stance << 24 | status << 28, high word =
-// working-set changes used (written by the loop).
-enum : int { kPrepF = 0, kPrepR = 12, kPrepU = 24, kPrepB = 36, kPrepG = 42, kPrepMeta = 63, kPrepSize = 64 };
+// Prepared record: what the set-up pass hands to the loop (64 doubles): r (12), b (6), f (12), u (12), G (21), meta.
+// The finishing pass reads only r and b -- the first 144 bytes -- and the QP's result word from a separate array.
+enum : int { kPrepR = 0, kPrepB = 12, kPrepF = 18, kPrepU = 30, kPrepG = 42, kPrepMeta = 63, kPrepSize = 64 };
 
 // Exchange 1 (integer max over the group): the most violated row among the groups that are not active (leg_key).
 // 0 from lanes that are not selecting.
@@ -691,6 +690,12 @@ QPB_HD void advance(const FastParams& K, Lane<LPL>& ln, int j, double* side, con
     A_t(tk, rx, ry, rz, v);
     cc = rcp_fast(nk[0] * tk[0] + nk[1] * tk[1] + nk[2] * tk[2]);
   }
+  // every lane of the QP updates its own copy of G from the old one; the first lane writes it back once all have read it
+  double G[21];
+#pragma unroll
+  for (int i = 0; i < 21; i++) G[i] = Gs[i];
+  rank1(G, v, cc);
+  QPB_SYNCWARP();
   if (T.act) {
     ln.word = word;
     const double uv = full ? ln.up : 0.0;
@@ -698,10 +703,6 @@ QPB_HD void advance(const FastParams& K, Lane<LPL>& ln, int j, double* side, con
     for (int i = 0; i < 3 * LPL; i++)
       if (3 * LPL * j + i == idx) ln.u[i] = uv;
     if (full) ln.p = -1;
-    double G[21];
-#pragma unroll
-    for (int i = 0; i < 21; i++) G[i] = Gs[i];
-    rank1(G, v, cc);
     if (store_G) {
 #pragma unroll
       for (int i = 0; i < 21; i++) Gs[i] = G[i];

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol(built):
     for name in names:
         assert hasattr(L, name), f"{name} declared in qpb200.h but not exported"
     assert set(names) == set(lib.EXPORTS)
-    assert L.qpb_version() == 100
+    assert L.qpb_version() == 200
 
 
 def test_struct_layouts_match_header(built, tmp_path):

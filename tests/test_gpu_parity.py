@@ -450,3 +450,44 @@ def test_warm_start_across_ticks(built, params06):
     S["pad"][:, :4] = word
     _compare(solver.control_host(S), ref)
     solver.close()
+
+
+def test_cuda_path_against_the_reference_sources_directly(built, params06):
+    """The CUDA results compared with oracle/_ref -- the reference's OWN balance_controller.cpp + kinematics.cpp compiled
+    from /root/reference against stand-in third-party headers -- without the plain-C port in between: the whole of
+    BASELINE config 2 (65 536 states), a stride of config 3, and every contact mask.  (For the QP solve itself the
+    stand-in qpOASES facade hands the reference's matrices to the oracle's solver, so on that step this check is not
+    independent of the port; the solver-free KKT certificate of test_kkt_certificate_on_gpu_output is.)"""
+    assert oracle.ref_available(), "oracle/_ref/libqpb_ref.so must travel with the tree"
+    solver = lib.BalanceSolver(params06)
+    cases = [states.generate_states(65536, 20260102),
+             np.ascontiguousarray(states.generate_states(1048576, 20260103, masks="mixed")[::37])]
+    S16 = states.generate_states(4096, 16, profile="stress", masks="mixed")
+    S16["contact"] = (np.arange(len(S16))[:, None] % 16 >> np.arange(4)) & 1
+    cases.append(S16)
+    for S in cases:
+        out = solver.control_host(S)
+        ref = oracle.ref_control_batch(params06, S, NCPU)
+        ef, et = _compare(out, ref)
+        assert ef <= 1e-7 and et <= 1e-7, (ef, et)
+    solver.close()
+
+
+def test_async_host_calls_overlap_and_match(built, params06):
+    """qpb_control_batch_host_async + qpb_host_sync: several batches in flight on pinned buffers give byte-for-byte the
+    results of the synchronous call."""
+    solver = lib.BalanceSolver(params06)
+    n = 20000
+    batches = [states.generate_states(n, 100 + k, masks="mixed") for k in range(3)]
+    pin_in = [lib.PinnedBuffer(n, STATE_DTYPE) for _ in batches]
+    pin_out = [lib.PinnedBuffer(n, OUT_DTYPE) for _ in batches]
+    for b, S in zip(pin_in, batches):
+        b.array[:] = S
+    for b_in, b_out in zip(pin_in, pin_out):
+        solver.control_host_async(b_in.array, b_out.array)
+    solver.host_sync()
+    for S, b_out in zip(batches, pin_out):
+        assert b_out.array.tobytes() == solver.control_host(S).tobytes()
+    for b in pin_in + pin_out:
+        b.free()
+    solver.close()
