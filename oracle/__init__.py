@@ -337,6 +337,19 @@ def ref_plan_batch(pp, states, plan, swing):
     R.ref_plan_batch(ctypes.byref(pp), states.ctypes.data, plan.ctypes.data, swing.ctypes.data, len(states))
 
 
+def ref_two_tick_replan(pp, leg_a, a_start, a_final, phase_a, leg_b, b_start, b_final, phase_b):
+    """Foot reference states of legs a and b after leg b re-planned while leg a was mid-swing, through ONE
+    FootTrajectoryManager of the reference (oracle/_ref) -> (pos+vel of a, pos+vel of b)."""
+    R = ref_lib()
+    dp = ctypes.POINTER(ctypes.c_double)
+    R.ref_two_tick_replan.argtypes = [ctypes.c_void_p, ctypes.c_int, dp, dp, ctypes.c_double, ctypes.c_int, dp, dp, ctypes.c_double, dp, dp]
+    arrs = [np.ascontiguousarray(v, dtype=np.float64) for v in (a_start, a_final, b_start, b_final)]
+    oa, ob = np.zeros(6), np.zeros(6)
+    R.ref_two_tick_replan(ctypes.byref(pp), int(leg_a), _dp(arrs[0]), _dp(arrs[1]), float(phase_a), int(leg_b), _dp(arrs[2]),
+                          _dp(arrs[3]), float(phase_b), _dp(oa), _dp(ob))
+    return oa, ob
+
+
 def ref_single_foot(t_stance, leg, state):
     state = np.ascontiguousarray(state).reshape(1)
     out = np.empty(3)

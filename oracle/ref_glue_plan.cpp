@@ -89,6 +89,41 @@ void ref_plan(const orc_plan_params* p, const orc_state* s, orc_plan_rec* plan, 
   }
 }
 
+// Two ticks through ONE FootTrajectoryManager, i.e. with the state the reference keeps between ticks (traj_map_):
+// tick 1 plans leg a; tick 2 plans leg b while leg a is mid-swing.  referenceStates(gait_map, bounds) clears traj_map_
+// before it adds the newly planned legs (trajectory.cpp:316), so after tick 2 the reference no longer has a trajectory
+// for leg a and referenceState(a) returns a zero FootState (trajectory.cpp:366-388).  out_a / out_b: position (3) +
+// velocity (3) of the two legs after tick 2; found_a: whether leg a still had a trajectory.
+void ref_two_tick_replan(const orc_plan_params* p, int leg_a, const double a_start[3], const double a_final[3], double phase_a,
+                         int leg_b, const double b_start[3], const double b_final[3], double phase_b, double out_a[6],
+                         double out_b[6])
+{
+  const FootTrajectoryManager manager(p->height, p->t_swing, p->t_stance);
+  GaitMap gait_map;
+  for (int leg = 0; leg < 4; leg++)
+  {
+    const bool swing = leg == leg_a || leg == leg_b;
+    gait_map.emplace(kLegNames[leg], std::make_pair(swing ? LegState::swing : LegState::stance,
+                                                    leg == leg_a ? phase_a : (leg == leg_b ? phase_b : 0.0)));
+  }
+  FootTrajBoundsMap first, second;
+  first.emplace(kLegNames[leg_a], FootTrajBounds(to_vec3(a_start), to_vec3(a_final)));
+  second.emplace(kLegNames[leg_b], FootTrajBounds(to_vec3(b_start), to_vec3(b_final)));
+  GaitMap tick1 = gait_map;
+  tick1.at(kLegNames[leg_b]).first = LegState::stance;  // leg b lifts off one tick later
+  manager.referenceStates(tick1, first);
+  manager.referenceStates(gait_map, second);
+  const FootState sa = manager.referenceState(kLegNames[leg_a], phase_a);  // commander_node.cpp:487-488
+  const FootState sb = manager.referenceState(kLegNames[leg_b], phase_b);
+  for (int i = 0; i < 3; i++)
+  {
+    out_a[i] = sa.position(i);
+    out_a[3 + i] = sa.velocity(i);
+    out_b[i] = sb.position(i);
+    out_b[3 + i] = sb.velocity(i);
+  }
+}
+
 void ref_plan_batch(const orc_plan_params* p, const orc_state* s, orc_plan_rec* plan, orc_swing* sw, long long n)
 {
   for (long long i = 0; i < n; i++) ref_plan(p, &s[i], &plan[i], &sw[i]);

@@ -43,6 +43,17 @@ QPB_HD double rsqrt_fast(double x) {
   return 1.0 / sqrt(x);
 #endif
 }
+// the same with one second-order step: e^2 <= 2^-40 -- for the active-set loop, which only decides with it
+QPB_HD double rsqrt_loop(double x) {
+#if defined(__CUDA_ARCH__)
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double e = fma(-(x * y), y, 1.0);  // 1 - x y^2
+  return fma(0.5 * y, e, y);               // y (1 + e/2)
+#else
+  return 1.0 / sqrt(x);
+#endif
+}
 QPB_HD double sqrt_fast(double x) { return x > 0.0 ? x * rsqrt_fast(x) : 0.0; }
 
 // atan on [0, inf) x [0, inf): first-quadrant atan2(n, w) (n, w >= 0, not both 0).  Octant reduction

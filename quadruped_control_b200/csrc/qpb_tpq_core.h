@@ -170,7 +170,10 @@ QPB_HD void add_leg(double (&G)[21], const Leg& L, double rx, double ry, double 
 }
 
 // In-place Cholesky of the packed 6x6 matrix: G <- L (the diagonal holds 1 / L_jj).  False if not positive definite.
-// (Loops have constant trip counts with guards: the front end then keeps G in registers.)
+// (Loops have constant trip counts with guards: the front end then keeps G in registers.)  LOOP: the factorisation of
+// the active-set loop, which only takes decisions with it (the polish recomputes the answer): a 2^-40 rsqrt shortens the
+// six-deep chain of dependent operations that bounds an iteration.
+template <bool LOOP = false>
 QPB_HD bool chol6(double (&G)[21]) {
   bool ok = true;
 #pragma unroll
@@ -180,7 +183,7 @@ QPB_HD bool chol6(double (&G)[21]) {
     for (int k = 0; k < 6; k++)
       if (k < j) d = fma(-G[ix(j, k)], G[ix(j, k)], d);
     ok = ok && (d > 0.0) && (d < 1e300);
-    const double rs = rsqrt_fast(d);
+    const double rs = LOOP ? rsqrt_loop(d) : rsqrt_fast(d);
     G[ix(j, j)] = rs;
 #pragma unroll
     for (int i = 0; i < 6; i++)
@@ -588,7 +591,7 @@ QPB_HD void direction(const FastParams& K, Lane<LPL>& ln, int j, const double* s
   double G[21];
 #pragma unroll
   for (int i = 0; i < 21; i++) G[i] = Gs[i];
-  const bool pd = chol6(G);
+  const bool pd = chol6<true>(G);
   double yh[6];
 #pragma unroll
   for (int i = 0; i < 6; i++) yh[i] = 0.5 * T.a[i];

@@ -96,6 +96,40 @@ def test_plan_oracle_matches_reference_sources(built, params06):
         assert np.array_equal(oracle.single_foot(pp, leg, S[5]), oracle.ref_single_foot(pp.t_stance, leg, S[5]))
 
 
+def test_replanning_another_leg_keeps_a_swinging_leg_on_its_trajectory(built):
+    """A deliberate deviation from the reference, pinned here.  FootTrajectoryManager::referenceStates(gait_map, bounds)
+    clears every stored trajectory before adding the newly planned legs (trajectory.cpp:316), so when leg b re-plans while
+    leg a is mid-swing the reference loses leg a's trajectory: referenceState(a) logs "Failed to find trajectory" and
+    returns a zero FootState (trajectory.cpp:366-388), i.e. the swing foot is sent towards the world origin.  With the
+    gaits the reference ships this never happens (trot: both legs of a pair re-plan in the same tick; crawl: one leg
+    swings at a time).  The batched planner keeps p_start / p_final of every swinging leg in the caller's qpb_plan_rec, so
+    leg a continues on its sextic.  This test runs both through ONE manager of the reference (oracle/_ref) and through
+    the oracle port, and documents the difference."""
+    import oracle
+
+    assert oracle.ref_available()
+    pp = default_plan_params()
+    S = states.generate_states(1, 77, masks="all4")
+    S["contact"][0] = (1, 0, 0, 1)  # legs FL (1) and RR (2) in swing
+    a_start, a_final = np.array([0.20, 0.13, 0.0]), np.array([0.31, 0.14, 0.0])
+    b_start, b_final = np.array([-0.19, -0.12, 0.0]), np.array([-0.08, -0.13, 0.0])
+    phase_a, phase_b = 0.93, 0.83
+    ref_a, ref_b = oracle.ref_two_tick_replan(pp, 1, a_start, a_final, phase_a, 2, b_start, b_final, phase_b)
+    assert not ref_a.any()  # the reference dropped leg a's trajectory
+    plan = np.zeros(1, dtype=PLAN_DTYPE)
+    plan["phase"][0] = (0.0, phase_a, phase_b, 0.0)
+    plan["p_start"][0, 3:6], plan["p_final"][0, 3:6] = a_start, a_final  # planned on an earlier tick
+    plan["p_start"][0, 6:9], plan["p_final"][0, 6:9] = b_start, b_final
+    sw = np.zeros(1, dtype=SWING_DTYPE)
+    oracle.plan_batch(pp, S, plan, sw)
+    # leg b: identical to the reference; leg a: what the reference itself returns when its trajectory is not cleared
+    assert np.abs(sw["foot_ref_pos"][0, 6:9] - ref_b[:3]).max() <= 1e-13 and np.abs(sw["foot_ref_vel"][0, 6:9] - ref_b[3:]).max() <= 1e-12
+    keep_a, _ = oracle.ref_two_tick_replan(pp, 2, b_start, b_final, phase_b, 1, a_start, a_final, phase_a)  # a planned last: kept
+    _, kept = oracle.ref_two_tick_replan(pp, 2, b_start, b_final, phase_b, 1, a_start, a_final, phase_a)
+    assert np.abs(sw["foot_ref_pos"][0, 3:6] - kept[:3]).max() <= 1e-13 and np.abs(sw["foot_ref_vel"][0, 3:6] - kept[3:]).max() <= 1e-12
+    assert sw["foot_ref_pos"][0, 3:6].any()
+
+
 def test_plan_oracle_matches_golden_reference_outputs(built):
     """tests/golden/plan_golden.npz holds outputs of the reference's own planner sources (generated where /root/reference
     exists); the oracle port must reproduce them anywhere."""
