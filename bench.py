@@ -356,6 +356,41 @@ def secondary_block(solver, params, rank, world, local_rank, dev, dist, barrier)
                                                         np.maximum(np.abs(ref["grf_body"]).max(axis=1), 1.0)).max())
         out[name] = entry
         del d_in, d_out, S
+    # cfg2 as a controller sees it in its loop: every record carries the working set its previous tick ended on (the
+    # reference's hotstart), the states have moved by 1 ms of a 1 kHz loop since.  One launch (tpq_one_kernel).
+    n, seed, masks, profile, desc = WORKLOADS["cfg2"]
+    S = states.generate_states(n, seed, lo=rank * n, profile=profile, masks=masks)
+    d_in = torch.from_numpy(S.view(np.uint8).reshape(-1)).to(dev)
+    d_out = torch.empty(n * OUT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+    solver.control_packed(d_in, d_out, n, stream.cuda_stream)
+    prev = d_out.cpu().numpy().view(OUT_DTYPE)
+    rng = np.random.default_rng(1000 + rank)
+    S["pad"][:, :4] = prev["pad"][:, :4]
+    S["x"] += rng.normal(0, 2e-4, S["x"].shape)
+    S["xdot"] += rng.normal(0, 2e-3, S["xdot"].shape)
+    S["w"] += rng.normal(0, 2e-3, S["w"].shape)
+    d_in = torch.from_numpy(S.view(np.uint8).reshape(-1)).to(dev)
+    solver.set_warm_batches(True)
+    try:
+        l0 = solver.launches
+        ms = timed(lambda: solver.control_packed(d_in, d_out, n, stream.cuda_stream), 5)
+        per_call = (solver.launches - l0) // 6
+    finally:
+        solver.set_warm_batches(False)
+    res = d_out.cpu().numpy().view(OUT_DTYPE)
+    entry = {"workload": desc + "; the next tick (states moved by 1 ms), records carry the previous tick's working sets",
+             "value": world * n / (ms * 1e-3), "unit": UNIT, "ms_per_launch": ms, "launches": 5, "kernels_per_call": per_call,
+             "failed_qps": int((res["status"] != 0).sum()), "iters_mean": float(res["iters"].mean()),
+             "hbm_frac": ALGO_BYTES_PER_QP * n / (ms * 1e-3) / 1e9 / peak}
+    if rank == 0:
+        import oracle
+
+        stride = max(1, n // 1024)
+        ref = oracle.control_batch(params, np.ascontiguousarray(S[::stride]), os.cpu_count() or 1)
+        entry["max_rel_grf_err_vs_oracle"] = float((np.abs(res[::stride]["grf_body"] - ref["grf_body"]).max(axis=1) /
+                                                    np.maximum(np.abs(ref["grf_body"]).max(axis=1), 1.0)).max())
+    out["cfg2_warm_tick"] = entry
+    del d_in, d_out, S
     # cfg4: the 10-step convex-MPC QP
     mp = default_mpc_params(MU)
     mpc = lib.MpcSolver(mp, device=local_rank)

@@ -67,6 +67,7 @@ typedef struct qpb_state_rec {
    * A little-endian uint32: bit 31 set = bits 0..23 hold the working set qpb_out_rec.pad[0..3] reported for this robot on
    * the previous tick (copy the four bytes over); 0 = cold start.  The hint only changes the number of working-set
    * changes, never the result (the optimum is unique); a stale or malformed hint falls back to the cold start.
+   * Honoured when W = w I and fzmin >= 0 (the range-space kernels); the general-W kernels ignore it.
    * pad[4..27]: ignored. */
   uint8_t pad[28];
 } qpb_state_rec;
@@ -81,7 +82,7 @@ typedef struct qpb_out_rec {
   int32_t iters; /* working-set changes used */
   /* pad[0..3]: the working set at the optimum as a little-endian uint32 with bit 31 set (2 bits per leg and row group:
    * 0 none, 1 / 2 = which side of |fx| <= mu fz, |fy| <= mu fz, fzmin <= fz <= fzmax is active), to be fed back as the
-   * next tick's warm start; 0 when the kernel in use does not report one.  pad[4..55]: zero. */
+   * next tick's warm start (every kernel reports it).  pad[4..55]: zero. */
   uint8_t pad[56];
 } qpb_out_rec;
 
@@ -136,6 +137,14 @@ int qpb_control_batch_host(qpb_handle* h, int64_t n, const qpb_state_rec* h_stat
  * balance_controller.hpp:161, 171-176). */
 int qpb_control_batch_host_async(qpb_handle* h, int64_t n, const qpb_state_rec* h_states, qpb_out_rec* h_out);
 int qpb_host_sync(qpb_handle* h);
+
+/* Tell the handle that the records of its DEVICE-resident calls (qpb_control_batch_packed, qpb_tick_batch_packed) carry
+ * warm-start words in pad[0..3] -- a controller in its loop, every tick handing the previous tick's qpb_out_rec.pad[0..3]
+ * back, which is how the reference uses SQProblem::hotstart (balance_controller.cpp:177-202).  Such batches take a
+ * one-launch kernel at every size (a warm QP is almost always optimal after its first 6x6 solve, so the three-pass
+ * path's scratch traffic buys nothing).  Host-buffer calls need no flag: they look at the first record.  Records
+ * without a valid word are still solved correctly, from a cold start, only slower than on the default path. */
+int qpb_set_warm_batches(qpb_handle* h, int on);
 
 /* jacobianTransposeControl() alone (kinematics.cpp:218-231): tau = J(q)^T f for stance legs,
  * 0 for swing legs.  Device pointers: q [n*12], grf_body [n*12], contact [n*4] (NULL = all stance). */

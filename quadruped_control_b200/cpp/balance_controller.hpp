@@ -218,8 +218,10 @@ public:
     if (!handle_ || qpb_control_batch_host(handle_, 1, &s, &o) != QPB_SUCCESS)
     {
       detail::log_error("Balance Controller", "GPU balance QP call failed");
+      working_set_ = 0;
       return force_map;
     }
+    remember(o);
     if (o.status != QPB_OK)
     {
       detail::log_error("Balance Controller", "Balance Controller QP Solver Failed");
@@ -247,7 +249,14 @@ public:
       for (unsigned int k = 0; k < 3; k++) s.q[3 * c + k] = js.q(k);
     }
     qpb_out_rec o;
-    if (!handle_ || qpb_control_batch_host(handle_, 1, &s, &o) != QPB_SUCCESS || o.status != QPB_OK)
+    if (!handle_ || qpb_control_batch_host(handle_, 1, &s, &o) != QPB_SUCCESS)
+    {
+      detail::log_error("Balance Controller", "GPU balance QP call failed");
+      working_set_ = 0;
+      return result;
+    }
+    remember(o);
+    if (o.status != QPB_OK)
     {
       detail::log_error("Balance Controller", "Balance Controller QP Solver Failed");
       return result;
@@ -289,8 +298,19 @@ private:
       for (unsigned int k = 0; k < 3; k++) s.feet[3 * c + k] = p(k);
       s.contact[c] = (gait_map.at(leg_name).first == LegState::stance) ? 1 : 0;  // :223, :312
     }
+    // the previous tick's final working set: the library starts its active-set method there (qpb200.h, pad[0:4])
+    std::memcpy(s.pad, &working_set_, sizeof(working_set_));
   }
 
+  /** Keep the working set this tick ended on for the next one -- what SQProblem::hotstart does inside the reference's
+   *  mutable QPSolver_ (balance_controller.hpp:161, balance_controller.cpp:176-199).  A failed solve starts cold. */
+  void remember(const qpb_out_rec& o) const
+  {
+    working_set_ = 0;
+    if (o.status == QPB_OK) std::memcpy(&working_set_, o.pad, sizeof(working_set_));
+  }
+
+  mutable uint32_t working_set_ = 0;  // bit 31 set = bits 0..23 hold a working set (as the library returns it)
   qpb_handle* handle_ = nullptr;
   std::vector<std::string> leg_names_;
 };

@@ -3,12 +3,14 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
+#include <type_traits>
 
 #include "qpb_internal.h"
 #include "qpb_kernel.cuh"
@@ -62,7 +64,8 @@ constexpr int64_t kMaxRecordsPerLaunch = (int64_t)1 << 31;  // the kernels index
 constexpr uint32_t kTicketSlots = 4096;  // ring of {work counter, CTAs finished} pairs; the kernels re-arm their own pair
 constexpr int64_t kSmallCall = 128;      // host calls up to this many robots go through one pinned, mapped staging block
 constexpr int64_t kTpqChunk = (int64_t)1 << 20;  // records per set-up / loop / finish triple (512 MiB of scratch)
-constexpr size_t kSmallBytes = (size_t)kSmallCall * 1536;  // states + results + swing records (or the kinematics arrays)
+constexpr size_t kSmallFlagsOff = (size_t)kSmallCall * 1536;  // states + results + swing records (or the kinematics arrays)
+constexpr size_t kSmallBytes = kSmallFlagsOff + (size_t)kSmallCall * sizeof(uint32_t);  // + one completion word per record
 
 }  // namespace
 
@@ -79,7 +82,10 @@ struct qpb_handle {
   int qps_per_warp = 2;
   int ctas_per_sm_tpq[5] = {};  // indexed by lanes per QP (1, 2, 4)
   int tpq_lpq = 1;              // lanes per QP of the range-space loop kernel (QPB_TPQ_LPQ=1|2|4 overrides)
-  int64_t tpq_min_n = 12288;    // smaller batches take the half-warp kernel: one launch, lower latency (QPB_TPQ_MIN_N)
+  int64_t tpq_min_n = 12288;    // smaller batches take a one-launch kernel: lower latency (QPB_TPQ_MIN_N)
+  int64_t tpq_one_max = 1;      // ... up to here the range-space one (tpq_one_kernel), above it the half-warp kernel (QPB_TPQ_ONE_MAX)
+  int warm_batches = 0;         // device-resident calls: the records carry warm-start words (qpb_set_warm_batches)
+  int64_t tpq_warm_one_max = (int64_t)1 << 40;  // warm batches up to this size take tpq_one_kernel (QPB_TPQ_WARM_ONE_MAX)
   qpb::tpq::FastParams fast;
   qpb_params params;
   qpb_params* d_params = nullptr;
@@ -100,6 +106,8 @@ struct qpb_handle {
   unsigned char* d_small = nullptr;  // its device alias
   int64_t host_chunk = 8192;  // records per H2D/kernel/D2H pipeline stage (QPB_HOST_CHUNK overrides)
   uint64_t host_slot = 0;     // next stage of the host pipeline (stages of successive asynchronous calls keep rotating)
+  uint32_t small_seq = 0;     // completion stamp of the latency path's last call
+  int small_poll = 1;         // the latency path waits on completion words in pinned memory (QPB_SMALL_POLL=0: stream sync)
   int zero_copy = 1;          // pinned host buffers are read/written by the kernel itself over PCIe (QPB_ZEROCOPY=0: always stage)
 };
 
@@ -125,7 +133,8 @@ inline qpb::SplitIO offset_io(const qpb::SplitIO& io, int64_t lo) {
 }
 
 template <class IO>
-int launch_balance(qpb_handle* h, const IO& io, int64_t n, int ctas_per_sm, cudaStream_t stream, int force_path = 0) {
+int launch_balance(qpb_handle* h, const IO& io, int64_t n, int ctas_per_sm, cudaStream_t stream, int force_path = 0,
+                   uint32_t* flags = nullptr, uint32_t seq = 0) {
   if (n == 0) return QPB_SUCCESS;
   if (n > kMaxRecordsPerLaunch) return fail(QPB_ERR_INVALID_ARG, "more than 2^31 records in one call: split the batch");
   // 1: one warp per QP; 2: two QPs per warp (half-warp kernel); 32: range-space path.  force_path: a caller that cuts a
@@ -136,6 +145,10 @@ int launch_balance(qpb_handle* h, const IO& io, int64_t n, int ctas_per_sm, cuda
   // is self-contained (safe under CUDA-graph replay) as long as fewer than R = 4096 launches of a handle are in flight.
   const uint32_t slot = h->ticket_slot.fetch_add(1, std::memory_order_relaxed) % kTicketSlots;
   unsigned long long* t0 = h->d_tickets + 4 * (size_t)slot;  // {work ticket, CTAs finished, worklist entries, -}
+  // A warm batch (records carrying last tick's working sets) is at its optimum after the set-up's first solve almost
+  // always, so the one-launch kernel wins at every size: no scratch, no second and third pass.
+  if (per_warp == 32 && !force_path && h->warm_batches && std::is_same<IO, qpb::PackedIO>::value)
+    force_path = n <= h->tpq_warm_one_max ? 33 : 32;
   if (per_warp == 32 && (force_path ? force_path == 32 : n >= h->tpq_min_n)) {
     // Three passes over scratch memory (qpb_tpq.cuh): set-up -> prepared records, the active-set loop, polish + epilogue.
     // The scratch comes from the stream-ordered allocator, so concurrent calls on different streams never share it.
@@ -169,7 +182,20 @@ int launch_balance(qpb_handle* h, const IO& io, int64_t n, int ctas_per_sm, cuda
     }
     return QPB_SUCCESS;
   }
-  if (per_warp == 32) per_warp = 2;  // small batches: the half-warp kernel has the lower latency (one launch, 16 lanes per QP)
+  if (per_warp == 32 && (force_path ? force_path == 33 : n <= h->tpq_one_max)) {
+    // small batches: set-up, loop and finish in one launch, a warp per record while there are warps to go round
+    int64_t per_cta = (n + (int64_t)h->num_sms * 8 - 1) / ((int64_t)h->num_sms * 8);
+    if (per_cta > qpb::tpq::kOneThreads) per_cta = qpb::tpq::kOneThreads;
+    const unsigned grid = (unsigned)((n + per_cta - 1) / per_cta);
+    if (per_cta == 1)  // a warp per record: the epilogue is shared out over its lanes
+      qpb::tpq::tpq_one_kernel<IO, true><<<grid, qpb::tpq::kOneThreads, 0, stream>>>(h->params, h->fast, io, n, 1, flags, seq);
+    else
+      qpb::tpq::tpq_one_kernel<IO, false><<<grid, qpb::tpq::kOneThreads, 0, stream>>>(h->params, h->fast, io, n, (int)per_cta, nullptr, 0u);
+    h->launches.fetch_add(1, std::memory_order_relaxed);
+    QPB_CUDA(cudaGetLastError());
+    return QPB_SUCCESS;
+  }
+  if (per_warp == 32) per_warp = 2;  // in between: the half-warp kernel (one launch, 16 lanes per QP)
   const int64_t units = (n + per_warp - 1) / per_warp;
   const int64_t want = (units + qpb::WARPS_PER_CTA - 1) / qpb::WARPS_PER_CTA;
   const int64_t cap = (int64_t)h->num_sms * (per_warp == 2 ? h->ctas_per_sm_16 : ctas_per_sm);
@@ -202,6 +228,7 @@ int ensure_small(qpb_handle* h) {
   if (h->h_small) return QPB_SUCCESS;
   void* p = nullptr;
   QPB_CUDA(cudaHostAlloc(&p, kSmallBytes, cudaHostAllocMapped));
+  std::memset(p, 0, kSmallBytes);
   void* d = nullptr;
   if (cudaHostGetDevicePointer(&d, p, 0) != cudaSuccess) {
     cudaFreeHost(p);
@@ -233,8 +260,10 @@ int host_pipeline(qpb_handle* h, int64_t n, const qpb_state_rec* h_states, const
   DeviceGuard guard(h->device);
   if (!guard.ok) return fail(QPB_ERR_CUDA, "cudaSetDevice failed");
   // one path for the whole batch, whatever the pieces it is cut into
-  const bool range_space = h->qps_per_warp == 32 && n >= h->tpq_min_n;
-  const int path = range_space ? 32 : (h->qps_per_warp == 32 ? 2 : h->qps_per_warp);
+  // (host records can be looked at: a batch whose first record carries a warm-start word is taken to be a warm batch)
+  const bool warm = h->qps_per_warp == 32 && (h->warm_batches || (h_states[0].pad[3] & 0x80u) != 0);
+  const bool range_space = h->qps_per_warp == 32 && (warm ? n > h->tpq_warm_one_max : n >= h->tpq_min_n);
+  const int path = range_space ? 32 : (h->qps_per_warp == 32 ? ((warm || n <= h->tpq_one_max) ? 33 : 2) : h->qps_per_warp);
   if (!async && h->zero_copy && n <= kSmallCall) {
     // Latency path for per-tick callers: stage through the handle's pinned block, kernels work on its device alias.
     const int rc0 = ensure_small(h);
@@ -245,11 +274,35 @@ int host_pipeline(qpb_handle* h, int64_t n, const qpb_state_rec* h_states, const
     const qpb_state_rec* ds = reinterpret_cast<const qpb_state_rec*>(h->d_small);
     qpb_out_rec* dout = reinterpret_cast<qpb_out_rec*>(h->d_small + off_out);
     qpb::PackedIO io{ ds, dout };
-    int rc = launch_balance(h, io, n, h->ctas_per_sm_packed, h->streams[0], path);
+    // One-launch range-space kernel, a warp per record: each warp stamps a completion word in the pinned block once its
+    // result is visible to the host, and the host waits on those words instead of synchronising the stream (1.3 us less
+    // per call on the B200 box, profiles/r02_launch_floor.txt).  Anything else, or no stamp within 2 ms: stream sync.
+    const bool poll = h->small_poll && path == 33 && !h_swing && n <= (int64_t)h->num_sms * 8;
+    uint32_t seq = 0;
+    if (poll) {
+      if (++h->small_seq == 0u) h->small_seq = 1u;
+      seq = h->small_seq;
+    }
+    int rc = launch_balance(h, io, n, h->ctas_per_sm_packed, h->streams[0], path,
+                            poll ? reinterpret_cast<uint32_t*>(h->d_small + kSmallFlagsOff) : nullptr, seq);
     if (rc == QPB_SUCCESS && h_swing)
       rc = launch_swing(h, n, ds, reinterpret_cast<const qpb_swing_rec*>(h->d_small + off_sw), dout, h->streams[0]);
     if (rc != QPB_SUCCESS) return rc;
-    QPB_CUDA(cudaStreamSynchronize(h->streams[0]));
+    bool stamped = false;
+    if (poll) {
+      const volatile uint32_t* flags = reinterpret_cast<const volatile uint32_t*>(h->h_small + kSmallFlagsOff);
+      const auto t0 = std::chrono::steady_clock::now();
+      stamped = true;
+      uint32_t spins = 0;
+      for (int64_t i = 0; i < n && stamped; i++)
+        while (flags[i] != seq)
+          if ((++spins & 0x3ffu) == 0u && std::chrono::steady_clock::now() - t0 > std::chrono::milliseconds(2)) {
+            stamped = false;
+            break;
+          }
+      std::atomic_thread_fence(std::memory_order_acquire);
+    }
+    if (!stamped) QPB_CUDA(cudaStreamSynchronize(h->streams[0]));
     std::memcpy(h_out, h->h_small + off_out, (size_t)n * sizeof(qpb_out_rec));
     return QPB_SUCCESS;
   }
@@ -451,7 +504,16 @@ int qpb_create(const qpb_params* params, int device, qpb_handle** out) {
     const long long v = std::atoll(env);
     if (v >= 0) h->tpq_min_n = v;
   }
+  if (const char* env = std::getenv("QPB_TPQ_WARM_ONE_MAX")) {
+    const long long v = std::atoll(env);
+    if (v >= 0) h->tpq_warm_one_max = v;
+  }
+  if (const char* env = std::getenv("QPB_TPQ_ONE_MAX")) {
+    const long long v = std::atoll(env);
+    if (v >= 0) h->tpq_one_max = v;
+  }
   if (const char* env = std::getenv("QPB_ZEROCOPY")) h->zero_copy = std::atoi(env);
+  if (const char* env = std::getenv("QPB_SMALL_POLL")) h->small_poll = std::atoi(env);
   if (const char* env = std::getenv("QPB_HOST_CHUNK")) {
     const long long v = std::atoll(env);
     if (v >= 256 && v <= kHostChunkMax) h->host_chunk = v;
@@ -521,6 +583,12 @@ int qpb_host_sync(qpb_handle* h) {
   DeviceGuard guard(h->device);
   if (!guard.ok) return fail(QPB_ERR_CUDA, "cudaSetDevice failed");
   return sync_pipeline(h);
+}
+
+int qpb_set_warm_batches(qpb_handle* h, int on) {
+  if (!h) return fail(QPB_ERR_INVALID_ARG, "qpb_set_warm_batches: null handle");
+  h->warm_batches = on ? 1 : 0;
+  return QPB_SUCCESS;
 }
 
 int qpb_set_joint_gains(qpb_handle* h, const qpb_joint_gains* gains) {

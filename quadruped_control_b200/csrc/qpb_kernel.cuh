@@ -119,21 +119,23 @@ __device__ __forceinline__ double2 load_rec(const SplitIO& io, int64_t idx, int 
   return v;
 }
 
+// wword: the working set at the optimum (bit 2 (3 leg + axis) = row A, the next one = row B -- the same 24-bit word the
+// range-space kernels use) with bit 31 set, the next tick's warm start.
 __device__ __forceinline__ void store_rec(const PackedIO& io, int64_t idx, int lane, double grf, double tau,
-                                          int status, int iters) {
+                                          int status, int iters, uint32_t wword) {
   double* o = reinterpret_cast<double*>(io.out + idx);
   if (lane < 12) {
     o[lane] = grf;
     o[12 + lane] = tau;
   } else if (lane < 16) {
-    // bytes 192..255: status, iters, zero padding -- the whole 256-B record is written
+    // bytes 192..255: status, iters, working-set word, zero padding -- the whole 256-B record is written
     int4 v = make_int4(0, 0, 0, 0);
-    if (lane == 12) { v.x = status; v.y = iters; }
+    if (lane == 12) { v.x = status; v.y = iters; v.z = (int)wword; }
     reinterpret_cast<int4*>(o + 24)[lane - 12] = v;
   }
 }
 __device__ __forceinline__ void store_rec(const SplitIO& io, int64_t idx, int lane, double grf, double tau,
-                                          int status, int /*iters*/) {
+                                          int status, int /*iters*/, uint32_t /*wword*/) {
   if (lane < 12) {
     io.grf[idx * 12 + lane] = grf;
     if (io.tau) io.tau[idx * 12 + lane] = tau;
@@ -209,6 +211,7 @@ balance_qp_kernel(const qpb_params* __restrict__ gparams, IO io, int64_t n, unsi
     const bool stance = isP && ((smask >> leg) & 1u);
 
     int status = QPB_OK, iters = 0;
+    uint32_t wset = 0;  // working set the solve ended on
     double x = 0.0;  // f_w component (lanes 0..11)
 
     if (ok) {
@@ -424,6 +427,7 @@ balance_qp_kernel(const qpb_params* __restrict__ gparams, IO io, int64_t n, unsi
 #pragma unroll
           for (int j = 0; j < 12; j++) M[j] = fma(-coef, zt[j], M[j]);
         }
+        wset = active;
       } else {
         status = QPB_BAD_INPUT;
       }
@@ -451,7 +455,7 @@ balance_qp_kernel(const qpb_params* __restrict__ gparams, IO io, int64_t n, unsi
     double tau = Jx * fbx + Jy * fby + Jz * fbz;
     if (P.clamp_tau) tau = fmin(fmax(tau, P.tau_min), P.tau_max);  // commander_node.cpp:526
     if (!(good && stance)) tau = 0.0;
-    store_rec(io, idx, lane, fb, tau, status, iters);
+    store_rec(io, idx, lane, fb, tau, status, iters, wset | 0x80000000u);
     idx = nwarps + (int64_t)__shfl_sync(FULL, next_ticket, 0);
   }
   // The last CTA out re-arms the work counter: the launch is self-contained, so the same counter slot serves graph

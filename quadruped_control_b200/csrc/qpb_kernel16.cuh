@@ -394,7 +394,7 @@ balance_qp_kernel16(const qpb_params* __restrict__ gparams, IO io, int64_t n, un
     double tau = Jx * fbx + Jy * fby + Jz * fbz;
     if (P.clamp_tau) tau = fmin(fmax(tau, P.tau_min), P.tau_max);
     if (!(good && stance)) tau = 0.0;
-    if (have) store_rec(io, rec, l, fb, tau, status, iters);
+    if (have) store_rec(io, rec, l, fb, tau, status, iters, active | 0x80000000u);
     pair = nwarps + __shfl_sync(FULL, next_ticket, 0);
   }
   // The last CTA out re-arms the work counter: the launch is self-contained, so the same counter slot serves graph

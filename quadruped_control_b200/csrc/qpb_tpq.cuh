@@ -43,6 +43,9 @@ constexpr int kEdgeThreads = 128;   // set-up / finishing kernels
 #ifndef QPB_TPQ_EDGE_MINCTAS
 #define QPB_TPQ_EDGE_MINCTAS 2
 #endif
+#ifndef QPB_TPQ_FINISH_MINCTAS
+#define QPB_TPQ_FINISH_MINCTAS QPB_TPQ_EDGE_MINCTAS
+#endif
 // loop kernel shape per lanes-per-QP: threads per CTA (static shared memory must stay under 48 KB), minimum CTAs per SM,
 // records per staged batch
 template <int LPQ> struct LoopShape;
@@ -143,6 +146,11 @@ __device__ __forceinline__ void tpq_load_Rq(const SplitIO& io, int64_t rec, doub
 #pragma unroll
   for (int j = 0; j < 12; j++) q[j] = __ldg(io.q + rec * 12 + j);
 }
+// joint angle i of a record whose slots 0..47 are already in registers (packed records carry q in slots 48..59)
+__device__ __forceinline__ double tpq_q(const PackedIO& io, int64_t rec, const double (&)[48], int i) {
+  return __ldg(reinterpret_cast<const double*>(io.in + rec) + kQ + i);
+}
+__device__ __forceinline__ double tpq_q(const SplitIO& io, int64_t rec, const double (&)[48], int i) { return __ldg(io.q + rec * 12 + i); }
 __device__ __forceinline__ void tpq_store(const PackedIO& io, int64_t rec, const double (&grf)[12], const double (&tau)[12],
                                           int status, int iters, uint32_t wword) {
   double2* o = reinterpret_cast<double2*>(io.out + rec);
@@ -362,7 +370,7 @@ tpq_loop_kernel(const __grid_constant__ FastParams K, const double* __restrict__
 
 // ---- pass 3: polish + epilogue, one thread per record -------------------------------------------------------------------
 template <class IO>
-__global__ void __launch_bounds__(kEdgeThreads, QPB_TPQ_EDGE_MINCTAS)
+__global__ void __launch_bounds__(kEdgeThreads, QPB_TPQ_FINISH_MINCTAS)
 tpq_finish_kernel(const __grid_constant__ qpb_params P, const __grid_constant__ FastParams K, IO io, int64_t n,
                   const double* __restrict__ prep, const double* __restrict__ res) {
   const int64_t rec = (int64_t)blockIdx.x * kEdgeThreads + threadIdx.x;
@@ -397,6 +405,162 @@ tpq_finish_kernel(const __grid_constant__ qpb_params P, const __grid_constant__ 
   for (int i = 0; i < 12; i++) qfin = qfin && (fabs(q[i]) <= 1.79769313486231570e308);
   if (!qfin && st.status == QPB_OK) st.status = QPB_BAD_INPUT;
   polish(K, st, b6);  // the minimiser on the final faces, from scratch
+  finish(P, R, q, st, grf, tau);
+  tpq_store(io, rec, grf, tau, st.status, st.iters, st.word | 0x80000000u);
+}
+
+// ---- small batches: the three passes in ONE launch, one thread per record -------------------------------------------
+// A per-tick caller (one robot, or a few hundred) waits for the answer, so what counts is the latency of a single QP,
+// not throughput: one launch instead of three and no scratch memory; every record gets a warp to itself as long as
+// there are warps to go round (records_per_cta = 1 up to 8 CTAs per SM), so no QP waits for another one's working-set
+// changes.  The starting pair and R, q wait in shared memory instead of the prepared record; when the set-up's pair is
+// already optimal (the usual outcome of a warm start) its forces ARE the minimiser on the final faces from one fresh
+// solve, so the polish is skipped.  Same arithmetic as the three passes otherwise (tests compare the two).
+constexpr int kOneThreads = 32;
+enum : int { kKeepF = 0, kKeepU = 12, kKeepG = 24, kKeepR = 45, kKeepQ = 54, kKeepSize = 66 };
+
+struct KeepCommit {
+  double* e;  // this thread's column of the keep block (element i at e[i * kOneThreads])
+  uint32_t key, word;
+  int status, iters;
+  __device__ __forceinline__ void operator()(const State& st, const double (&G)[21], uint32_t k) {
+    key = k;
+    word = st.word;
+    status = st.status;
+    iters = st.iters;
+#pragma unroll
+    for (int i = 0; i < 12; i++) e[(kKeepF + i) * kOneThreads] = st.f[i];
+    if (k == 0u) return;  // optimal already: the loop will not run, its multipliers and G are not needed
+#pragma unroll
+    for (int i = 0; i < 12; i++) e[(kKeepU + i) * kOneThreads] = st.u[i];
+#pragma unroll
+    for (int i = 0; i < 21; i++) e[(kKeepG + i) * kOneThreads] = G[i];
+  }
+};
+
+// flags (COOP only, may be null): completion words in pinned host memory, one per record, set to seq once the record's
+// result is visible to the host -- the one-robot caller waits on them instead of synchronising the stream.
+// COOP: one record per warp (records_per_cta = 1).  Lane 0 solves; the epilogue -- twelve sincos, the Jacobian columns,
+// the store -- is spread over lanes 0..15 the way the half-warp kernel does it, a third of the instructions of the whole
+// QP when one thread runs through them (a lone warp pays an instruction-cache miss for nearly every instruction it
+// executes once: profiles/r02_ncu_one_n1_digest.txt).
+template <class IO, bool COOP>
+__global__ void __launch_bounds__(kOneThreads)
+tpq_one_kernel(const __grid_constant__ qpb_params P, const __grid_constant__ FastParams K, IO io, int64_t n, int records_per_cta,
+               uint32_t* __restrict__ flags, uint32_t seq) {
+  __shared__ double side_all[kOneThreads * kSideSize];
+  __shared__ double keep_all[kOneThreads * kKeepSize];
+  const int t = threadIdx.x;
+  const int64_t rec = COOP ? (int64_t)blockIdx.x : (int64_t)blockIdx.x * records_per_cta + t;
+  const bool active = COOP ? t == 0 : (t < records_per_cta && rec < n);
+  double* side = side_all + t * kSideSize;
+  double* keep = keep_all + t;
+  State st;
+  double b6[6];
+  Lane<4> ln;
+  ln.done = true;
+  st.status = QPB_OK;
+  st.iters = 0;
+  st.word = st.stance = 0u;
+  bool looped = false, qfin = true;
+  uint32_t key = 0u;  // first row of the loop (0: the set-up's pair is optimal already)
+  if (active) {
+    double v[48];
+    uint32_t cbytes, hint;
+    tpq_load(io, rec, v, cbytes, hint);
+#pragma unroll
+    for (int i = 0; i < 9; i++) keep[(kKeepR + i) * kOneThreads] = v[kR + i];
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+      const double qi = tpq_q(io, rec, v, i);
+      qfin = qfin && (fabs(qi) <= 1.79769313486231570e308);  // the set-up checks slots 0..47, the joint angles are checked here
+      keep[(kKeepQ + i) * kOneThreads] = qi;
+    }
+    double G[21];
+    KeepCommit commit{ keep, 0u, 0u, QPB_OK, 0 };
+    setup(P, K, v, cbytes, hint, st, b6, G, commit);
+    // the last pair committed is where the solve stands (a later block round may have been tried and rejected)
+    st.word = commit.word;
+    st.status = commit.status;
+    st.iters = commit.iters;
+    key = commit.key;
+    looped = key != 0u;
+#pragma unroll
+    for (int i = 0; i < 12; i++) st.f[i] = keep[(kKeepF + i) * kOneThreads];
+    if (looped) {
+#pragma unroll
+      for (int i = 0; i < 12; i++) st.u[i] = keep[(kKeepU + i) * kOneThreads];
+    }
+  }
+  if (__any_sync(FULL, looped)) {
+    // every lane of the warp walks through the loop (finished and idle ones with their stores predicated off)
+    const double zero[12] = { 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0 };
+    lane_init<4>(ln, 0, zero, zero, zero, 0u, 0u, QPB_OK, 0, 0u);
+    ln.done = true;
+    if (looped) {
+      lane_init<4>(ln, 0, st.f, st.r, st.u, st.word, st.stance, st.status, st.iters, key);
+#pragma unroll
+      for (int i = 0; i < 21; i++) side[kSideG + i] = keep[(kKeepG + i) * kOneThreads];
+#pragma unroll
+      for (int i = 0; i < 12; i++) side[kSideR + i] = st.r[i];
+      ln.sp = row_slack_share<4>(K, ln, 0);
+    }
+    while (__any_sync(FULL, !ln.done)) iterate_group<1>(K, ln, 0, side);
+    if (looped) {
+      st.word = ln.word;
+      st.status = ln.status;
+      st.iters = ln.iters;
+    }
+  }
+  if (!qfin && st.status == QPB_OK) st.status = QPB_BAD_INPUT;
+  if (looped) polish(K, st, b6);  // (a pair the set-up found optimal IS the minimiser on its faces from one fresh solve)
+  if (COOP) {
+    if (active) {
+#pragma unroll
+      for (int i = 0; i < 12; i++) keep[(kKeepF + i) * kOneThreads] = st.f[i];
+    }
+    __syncwarp();
+    const int status = __shfl_sync(FULL, st.status, 0);
+    const int iters = __shfl_sync(FULL, st.iters, 0);
+    const uint32_t word = __shfl_sync(FULL, st.word, 0), stance = __shfl_sync(FULL, st.stance, 0);
+    const int vi = t < 12 ? t : 0, leg = vi / 3, ax = vi - 3 * leg;
+    const double* kp = keep_all;  // the record of lane 0: element i at kp[i * kOneThreads]
+    const double qraw = kp[(kKeepQ + vi) * kOneThreads];
+    const bool on = status == QPB_OK && ((stance >> leg) & 1u), qok = status != QPB_BAD_INPUT;
+    const double f0 = kp[(kKeepF + 3 * leg) * kOneThreads], f1 = kp[(kKeepF + 3 * leg + 1) * kOneThreads],
+                 f2 = kp[(kKeepF + 3 * leg + 2) * kOneThreads];
+    const double fb = on ? -1.0 * (kp[(kKeepR + ax) * kOneThreads] * f0 + kp[(kKeepR + 3 + ax) * kOneThreads] * f1 +
+                                   kp[(kKeepR + 6 + ax) * kOneThreads] * f2)
+                         : 0.0;
+    const double qa = qraw + (ax == 2 ? kp[(kKeepQ + 3 * leg + 1) * kOneThreads] : 0.0);  // t1, t2, t2 + t3
+    double sn, cs;
+    sincos(qok ? qa : 0.0, &sn, &cs);
+    const double s1 = __shfl_sync(FULL, sn, 3 * leg), c1 = __shfl_sync(FULL, cs, 3 * leg);
+    const double s2 = __shfl_sync(FULL, sn, 3 * leg + 1), c2 = __shfl_sync(FULL, cs, 3 * leg + 1);
+    const double s23 = __shfl_sync(FULL, sn, 3 * leg + 2), c23 = __shfl_sync(FULL, cs, 3 * leg + 2);
+    const double fbx = __shfl_sync(FULL, fb, 3 * leg), fby = __shfl_sync(FULL, fb, 3 * leg + 1), fbz = __shfl_sync(FULL, fb, 3 * leg + 2);
+    double Jx, Jy, Jz;
+    leg_jacobian_col(ax, P.link[3 * leg], P.link[3 * leg + 1], P.link[3 * leg + 2], s1, c1, s2, c2, s23, c23, Jx, Jy, Jz);
+    double tau = Jx * fbx + Jy * fby + Jz * fbz;
+    if (P.clamp_tau) tau = fmin(fmax(tau, P.tau_min), P.tau_max);
+    if (!on) tau = 0.0;
+    store_rec(io, rec, t, fb, tau, status, iters, word | 0x80000000u);
+    if (flags) {
+      // a host thread is spinning on flags[rec] (pinned memory): the record first, system-wide, then the flag
+      __syncwarp();
+      if (t == 0) {
+        __threadfence_system();
+        *reinterpret_cast<volatile uint32_t*>(flags + rec) = seq;
+      }
+    }
+    return;
+  }
+  if (!active) return;
+  double R[9], q[12], grf[12], tau[12];
+#pragma unroll
+  for (int i = 0; i < 9; i++) R[i] = keep[(kKeepR + i) * kOneThreads];
+#pragma unroll
+  for (int i = 0; i < 12; i++) q[i] = keep[(kKeepQ + i) * kOneThreads];
   finish(P, R, q, st, grf, tau);
   tpq_store(io, rec, grf, tau, st.status, st.iters, st.word | 0x80000000u);
 }

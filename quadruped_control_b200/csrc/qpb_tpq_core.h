@@ -307,15 +307,11 @@ QPB_HD bool face_solve(const FastParams& K, State& st, const double (&b6)[6], do
 
 // keep only well-formed codes of stance legs (a hint is untrusted input)
 QPB_HD uint32_t wset_sanitize(uint32_t word, uint32_t stance) {
-  uint32_t out = 0;
+  const uint32_t both = word & (word >> 1) & 0x555555u;  // groups whose code is 3 (both rows at once): not a face
+  uint32_t legs = 0u;
 #pragma unroll
-  for (int i = 0; i < 4; i++)
-#pragma unroll
-    for (int g = 0; g < 3; g++) {
-      const uint32_t c = (word >> (6 * i + 2 * g)) & 3u;
-      if (((stance >> i) & 1u) && c != 3u) out |= c << (6 * i + 2 * g);
-    }
-  return out;
+  for (int i = 0; i < 4; i++) legs |= ((stance >> i) & 1u) ? (63u << (6 * i)) : 0u;
+  return word & ~(both | (both << 1)) & legs;
 }
 
 // Selection key of one leg: the most violated row among its groups that are not active, 0 if none.  The high word of
@@ -411,7 +407,7 @@ QPB_HD void start(const FastParams& K, State& st, const double (&b6)[6], uint32_
       }
       commit(st, G, key);
       committed = true;
-      const uint32_t viol = violated_rows(K, st);
+      const uint32_t viol = key ? violated_rows(K, st) : 0u;  // (key = 0: no slack is negative, the word would be empty)
       if (viol == 0u || adds >= kStartAdds || rounds >= K.max_iter) break;  // optimal already / budget spent
       word |= viol;
       adds++;

@@ -30,6 +30,7 @@ EXPORTS = (
     "qpb_fk_batch",
     "qpb_jt_batch_host",
     "qpb_fk_batch_host",
+    "qpb_set_warm_batches",
     "qpb_set_joint_gains",
     "qpb_tick_batch_packed",
     "qpb_tick_batch_host",
@@ -88,6 +89,7 @@ def load():
     L.qpb_fk_batch.argtypes = [vp, i64, dp, dp, vp]
     L.qpb_jt_batch_host.argtypes = [vp, i64, dp, dp, dp, dp]
     L.qpb_fk_batch_host.argtypes = [vp, i64, dp, dp]
+    L.qpb_set_warm_batches.argtypes = [vp, ctypes.c_int]
     L.qpb_set_joint_gains.argtypes = [vp, ctypes.POINTER(JointGains)]
     L.qpb_tick_batch_packed.argtypes = [vp, i64, vp, vp, vp, vp]
     L.qpb_tick_batch_host.argtypes = [vp, i64, vp, vp, vp]
@@ -287,6 +289,10 @@ class BalanceSolver:
 
     def host_sync(self):
         _check(load().qpb_host_sync(self._h), "qpb_host_sync")
+
+    def set_warm_batches(self, on: bool = True):
+        """Device-resident calls carry warm-start words (state.pad[0:4] = last tick's out.pad[0:4]): one-launch kernel."""
+        _check(load().qpb_set_warm_batches(self._h, 1 if on else 0), "qpb_set_warm_batches")
 
     # -- whole control tick: balance QP for stance legs + joint PD for swing legs (commander_node.cpp:482-533) --
     def set_joint_gains(self, gains: JointGains):

@@ -86,19 +86,90 @@ def test_every_contact_mask_and_swing_legs_zero(solver06, params06):
 
 
 def test_small_batches_take_the_one_launch_kernel_and_agree(built, params06):
-    """Dispatch: below QPB_TPQ_MIN_N (12 288) records a batch takes the half-warp kernel (one launch, lower latency), at or
-    above it the three-launch range-space path; both must give the oracle's answer."""
+    """Dispatch: below QPB_TPQ_MIN_N (12 288) records a cold batch takes the half-warp kernel (one launch, lower latency),
+    at or above it the three-launch range-space path; both must give the oracle's answer and the same working sets."""
     S = states.generate_states(20000, 31, masks="mixed")
     solver = lib.BalanceSolver(params06)
     ref = oracle.control_batch(params06, S, NCPU)
     l0 = solver.launches
     small = solver.control_host(S[:4000])
-    assert solver.launches - l0 <= 8 and not small["pad"].any()  # staged one-launch kernels, no working-set word
+    assert solver.launches - l0 <= 8  # staged one-launch kernels
     big = solver.control_host(S)
-    assert (big["pad"][:, 3] & 0x80).all()
+    assert (big["pad"][:, 3] & 0x80).all() and (small["pad"][:, 3] & 0x80).all()
+    ok = (small["status"] == 0) & (small["iters"] > 0)
+    same = (small["pad"][ok] == big["pad"][:4000][ok]).all(axis=1)
+    assert same.mean() >= 0.98, same.mean()  # the optimal working set, but for degenerate rows (zero multiplier)
     _compare(small, ref[:4000])
     _compare(big, ref)
     assert rel_err(small["grf_body"], big["grf_body"][:4000]) <= 1e-7
+    solver.close()
+
+
+def test_one_launch_range_space_kernel(built, params06, monkeypatch):
+    """tpq_one_kernel (set-up, loop and finish in one launch; the latency path of small batches): against the oracle, against
+    the three-launch path on the same records (same arithmetic: same working sets, same iteration counts), ragged sizes
+    around the records-per-CTA steps, and the warm start -- with a record's own final working set as the hint the solve
+    must end (almost always) with no working-set change at all."""
+    S = states.generate_states(6000, 77, masks="mixed")
+    ref = oracle.control_batch(params06, S, NCPU)
+    monkeypatch.setenv("QPB_TPQ_MIN_N", "0")
+    three = lib.BalanceSolver(params06)
+    base = three.control_host(S)
+    three.close()
+    monkeypatch.setenv("QPB_TPQ_MIN_N", str(1 << 31))
+    monkeypatch.setenv("QPB_TPQ_ONE_MAX", str(1 << 30))
+    one = lib.BalanceSolver(params06)
+    for n in (1, 2, 33, 1184, 1185, 2369, 6000):
+        l0 = one.launches
+        out = one.control_host(S[:n])
+        assert one.launches - l0 <= 8
+        _compare(out, ref[:n])
+        assert np.array_equal(out["status"], base["status"][:n]) and np.array_equal(out["iters"], base["iters"][:n])
+        assert np.array_equal(out["pad"], base["pad"][:n])  # same final working sets
+        assert rel_err(out["grf_body"], base["grf_body"][:n]) <= 1e-9 and rel_err(out["tau"], base["tau"][:n]) <= 1e-9
+    W = S.copy()
+    W["pad"][:, :4] = base["pad"][:, :4]
+    warm = one.control_host(W)
+    ok = base["status"] == 0
+    assert warm["iters"][ok].mean() <= 0.02 and warm["iters"][ok].max() <= 3  # (a degenerate row may be dropped and re-added)
+    assert np.array_equal(warm["status"], base["status"])
+    assert rel_err(warm["grf_body"], base["grf_body"]) <= 1e-9 and rel_err(warm["tau"], base["tau"]) <= 1e-9
+    one.close()
+
+
+def test_warm_batches_flag_on_device_calls(built, params06):
+    """qpb_set_warm_batches: device-resident records that carry last tick's working sets take the one-launch kernel at any
+    size (the host entry points find out by looking at the first record; a device pointer cannot be looked at)."""
+    torch = _torch()
+    n = 40000
+    S = states.generate_states(n, 99, masks="mixed")
+    solver = lib.BalanceSolver(params06)
+    d_in = torch.from_numpy(S.view(np.uint8).reshape(-1).copy()).cuda()
+    d_out = torch.zeros(n * 256, dtype=torch.uint8, device="cuda")
+    l0 = solver.launches
+    solver.control_packed(d_in, d_out, n)
+    torch.cuda.synchronize()
+    assert solver.launches - l0 == 3  # cold: set-up, loop, finish
+    cold = d_out.cpu().numpy().view(OUT_DTYPE).copy()
+    W = S.copy()
+    W["pad"][:, :4] = cold["pad"][:, :4]
+    d_in = torch.from_numpy(W.view(np.uint8).reshape(-1).copy()).cuda()
+    solver.set_warm_batches(True)
+    l0 = solver.launches
+    solver.control_packed(d_in, d_out, n)
+    torch.cuda.synchronize()
+    assert solver.launches - l0 == 1
+    warm = d_out.cpu().numpy().view(OUT_DTYPE).copy()
+    assert np.array_equal(warm["status"], cold["status"]) and warm["iters"].mean() <= 0.02
+    assert rel_err(warm["grf_body"], cold["grf_body"]) <= 1e-9 and rel_err(warm["tau"], cold["tau"]) <= 1e-9
+    # records without a word are still solved, from a cold start
+    d_in = torch.from_numpy(S.view(np.uint8).reshape(-1).copy()).cuda()
+    solver.control_packed(d_in, d_out, n)
+    torch.cuda.synchronize()
+    again = d_out.cpu().numpy().view(OUT_DTYPE).copy()
+    assert np.array_equal(again["status"], cold["status"]) and np.array_equal(again["iters"], cold["iters"])
+    assert rel_err(again["grf_body"], cold["grf_body"]) <= 1e-9
+    solver.set_warm_batches(False)
     solver.close()
 
 
@@ -435,14 +506,13 @@ def test_single_process_multi_device_sharding(solver06, params06):
     multi.close()
 
 
-def test_warm_start_across_ticks(built, params06, monkeypatch):
+def test_warm_start_across_ticks(built, params06):
     """The reference hot-starts qpOASES from the previous tick's working set (balance_controller.cpp:177-202).  Here the
     working set travels as a word in the records' padding: out.pad[0:4] of tick k is copied into state.pad[0:4] of tick
     k+1.  Results must equal the cold solve (unique optimum) while the working-set changes per tick collapse."""
     rng = np.random.default_rng(11)
     S = states.generate_states(8192, 20260103, masks="mixed")
-    monkeypatch.setenv("QPB_TPQ_MIN_N", "0")  # batches below 12 288 records would take the half-warp kernel (no hints)
-    solver = lib.BalanceSolver(params06)
+    solver = lib.BalanceSolver(params06)  # tick 0 is cold (half-warp kernel at this size), the warm ticks take tpq_one_kernel
     word = np.zeros((len(S), 4), dtype=np.uint8)
     warm_iters, cold_iters = [], []
     for tick in range(6):

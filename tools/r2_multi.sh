@@ -5,7 +5,7 @@ O=gpurun_out
 mkdir -p $O
 NG=$(nvidia-smi -L | wc -l)
 echo "GPUs: $NG"; nvidia-smi topo -m 2>/dev/null | head -14 > $O/r2m_topo.txt; lscpu | grep -E "NUMA|Socket|^CPU\(s\)" >> $O/r2m_topo.txt
-for N in 1 2 4 8; do
+for N in ${NLIST:-1 2 4 8}; do
   [ $N -gt $NG ] && continue
   if [ $N -eq 1 ]; then
     timeout 600 python bench.py --steps 20 --warmup 3 > $O/r2m_bench_n1.json 2> $O/r2m_bench_n1.err
