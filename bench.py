@@ -909,6 +909,12 @@ def main():
                     help="disturbance profile of the synthetic states (SURVEY.md 8d); default: the workload's own")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    # stdout carries exactly ONE line, the JSON: while the run is going on, file descriptor 1 points at stderr, so that
+    # whatever a library prints there (NCCL's version banner at communicator creation) cannot get in front of it
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w", buffering=1)
     if args.workload == "tick":
         if args.impl == "reference":
             raise SystemExit("--workload tick has no reference arm (use the default workload)")

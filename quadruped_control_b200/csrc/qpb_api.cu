@@ -134,7 +134,7 @@ inline qpb::SplitIO offset_io(const qpb::SplitIO& io, int64_t lo) {
 
 template <class IO>
 int launch_balance(qpb_handle* h, const IO& io, int64_t n, int ctas_per_sm, cudaStream_t stream, int force_path = 0,
-                   uint32_t* flags = nullptr, uint32_t seq = 0) {
+                   uint32_t* flags = nullptr, uint32_t seq = 0, int64_t whole_n = 0) {
   if (n == 0) return QPB_SUCCESS;
   if (n > kMaxRecordsPerLaunch) return fail(QPB_ERR_INVALID_ARG, "more than 2^31 records in one call: split the batch");
   // 1: one warp per QP; 2: two QPs per warp (half-warp kernel); 32: range-space path.  force_path: a caller that cuts a
@@ -187,7 +187,9 @@ int launch_balance(qpb_handle* h, const IO& io, int64_t n, int ctas_per_sm, cuda
     int64_t per_cta = (n + (int64_t)h->num_sms * 8 - 1) / ((int64_t)h->num_sms * 8);
     if (per_cta > qpb::tpq::kOneThreads) per_cta = qpb::tpq::kOneThreads;
     const unsigned grid = (unsigned)((n + per_cta - 1) / per_cta);
-    if (per_cta == 1)  // a warp per record: the epilogue is shared out over its lanes
+    // a warp per record: the epilogue is shared out over its lanes (decided on the batch a shard is cut from: the two
+    // epilogues round differently in the last bit)
+    if (per_cta == 1 && (whole_n > n ? whole_n : n) <= (int64_t)h->num_sms * 8)
       qpb::tpq::tpq_one_kernel<IO, true><<<grid, qpb::tpq::kOneThreads, 0, stream>>>(h->params, h->fast, io, n, 1, flags, seq);
     else
       qpb::tpq::tpq_one_kernel<IO, false><<<grid, qpb::tpq::kOneThreads, 0, stream>>>(h->params, h->fast, io, n, (int)per_cta, nullptr, 0u);
@@ -254,16 +256,20 @@ int sync_pipeline(qpb_handle* h) {
   return QPB_SUCCESS;
 }
 
+// whole_n / whole_warm: when the n records are one shard of a larger batch (qpb_multi_*), the size of that batch and
+// whether ITS first record carries a warm-start word -- the kernels are chosen for the batch, not for the shard.
 int host_pipeline(qpb_handle* h, int64_t n, const qpb_state_rec* h_states, const qpb_swing_rec* h_swing, qpb_out_rec* h_out,
-                  bool async = false) {
+                  bool async = false, int64_t whole_n = -1, int whole_warm = -1) {
   if (n == 0) return QPB_SUCCESS;
   DeviceGuard guard(h->device);
   if (!guard.ok) return fail(QPB_ERR_CUDA, "cudaSetDevice failed");
   // one path for the whole batch, whatever the pieces it is cut into
   // (host records can be looked at: a batch whose first record carries a warm-start word is taken to be a warm batch)
-  const bool warm = h->qps_per_warp == 32 && (h->warm_batches || (h_states[0].pad[3] & 0x80u) != 0);
-  const bool range_space = h->qps_per_warp == 32 && (warm ? n > h->tpq_warm_one_max : n >= h->tpq_min_n);
-  const int path = range_space ? 32 : (h->qps_per_warp == 32 ? ((warm || n <= h->tpq_one_max) ? 33 : 2) : h->qps_per_warp);
+  const int64_t dn = whole_n >= 0 ? whole_n : n;
+  const bool hinted = whole_warm >= 0 ? whole_warm != 0 : (h_states[0].pad[3] & 0x80u) != 0;
+  const bool warm = h->qps_per_warp == 32 && (h->warm_batches || hinted);
+  const bool range_space = h->qps_per_warp == 32 && (warm ? dn > h->tpq_warm_one_max : dn >= h->tpq_min_n);
+  const int path = range_space ? 32 : (h->qps_per_warp == 32 ? ((warm || dn <= h->tpq_one_max) ? 33 : 2) : h->qps_per_warp);
   if (!async && h->zero_copy && n <= kSmallCall) {
     // Latency path for per-tick callers: stage through the handle's pinned block, kernels work on its device alias.
     const int rc0 = ensure_small(h);
@@ -277,14 +283,14 @@ int host_pipeline(qpb_handle* h, int64_t n, const qpb_state_rec* h_states, const
     // One-launch range-space kernel, a warp per record: each warp stamps a completion word in the pinned block once its
     // result is visible to the host, and the host waits on those words instead of synchronising the stream (1.3 us less
     // per call on the B200 box, profiles/r02_launch_floor.txt).  Anything else, or no stamp within 2 ms: stream sync.
-    const bool poll = h->small_poll && path == 33 && !h_swing && n <= (int64_t)h->num_sms * 8;
+    const bool poll = h->small_poll && path == 33 && !h_swing && dn <= (int64_t)h->num_sms * 8;
     uint32_t seq = 0;
     if (poll) {
       if (++h->small_seq == 0u) h->small_seq = 1u;
       seq = h->small_seq;
     }
     int rc = launch_balance(h, io, n, h->ctas_per_sm_packed, h->streams[0], path,
-                            poll ? reinterpret_cast<uint32_t*>(h->d_small + kSmallFlagsOff) : nullptr, seq);
+                            poll ? reinterpret_cast<uint32_t*>(h->d_small + kSmallFlagsOff) : nullptr, seq, dn);
     if (rc == QPB_SUCCESS && h_swing)
       rc = launch_swing(h, n, ds, reinterpret_cast<const qpb_swing_rec*>(h->d_small + off_sw), dout, h->streams[0]);
     if (rc != QPB_SUCCESS) return rc;
@@ -315,7 +321,7 @@ int host_pipeline(qpb_handle* h, int64_t n, const qpb_state_rec* h_states, const
         ai.type == cudaMemoryTypeHost && ao.type == cudaMemoryTypeHost && ai.devicePointer && ao.devicePointer) {
       if (!h->streams[0]) QPB_CUDA(cudaStreamCreateWithFlags(&h->streams[0], cudaStreamNonBlocking));
       qpb::PackedIO io{ static_cast<const qpb_state_rec*>(ai.devicePointer), static_cast<qpb_out_rec*>(ao.devicePointer) };
-      const int rc = launch_balance(h, io, n, h->ctas_per_sm_packed, h->streams[0], path);
+      const int rc = launch_balance(h, io, n, h->ctas_per_sm_packed, h->streams[0], path, nullptr, 0u, dn);
       if (rc != QPB_SUCCESS) return rc;
       QPB_CUDA(cudaStreamSynchronize(h->streams[0]));
       return QPB_SUCCESS;
@@ -353,7 +359,7 @@ int host_pipeline(qpb_handle* h, int64_t n, const qpb_state_rec* h_states, const
       ce = cudaMemcpyAsync(h->d_sw[slot], h_swing + lo, m * sizeof(qpb_swing_rec), cudaMemcpyHostToDevice, st);
     if (ce != cudaSuccess) break;
     qpb::PackedIO io{ h->d_in[slot], h->d_out[slot] };
-    rc = launch_balance(h, io, m, h->ctas_per_sm_packed, st, path);
+    rc = launch_balance(h, io, m, h->ctas_per_sm_packed, st, path, nullptr, 0u, dn);
     if (rc == QPB_SUCCESS && h_swing) rc = launch_swing(h, m, h->d_in[slot], h->d_sw[slot], h->d_out[slot], st);
     if (rc != QPB_SUCCESS) break;
     ce = cudaMemcpyAsync(h_out + lo, h->d_out[slot], m * sizeof(qpb_out_rec), cudaMemcpyDeviceToHost, st);
@@ -570,6 +576,12 @@ int qpb_control_batch_host(qpb_handle* h, int64_t n, const qpb_state_rec* h_stat
   if (!h || n < 0 || (n > 0 && (!h_states || !h_out)))
     return fail(QPB_ERR_INVALID_ARG, "qpb_control_batch_host: bad argument");
   return host_pipeline(h, n, h_states, nullptr, h_out);
+}
+
+int qpb_internal_host_shard(qpb_handle* h, int64_t n, const qpb_state_rec* h_states, const qpb_swing_rec* h_swing,
+                            qpb_out_rec* h_out, int64_t whole_n, int whole_warm) {
+  if (!h || n < 0 || (n > 0 && (!h_states || !h_out))) return fail(QPB_ERR_INVALID_ARG, "host shard: bad argument");
+  return host_pipeline(h, n, h_states, h_swing, h_out, false, whole_n, whole_warm);
 }
 
 int qpb_control_batch_host_async(qpb_handle* h, int64_t n, const qpb_state_rec* h_states, qpb_out_rec* h_out) {

@@ -24,6 +24,8 @@ struct qpb_multi_handle {
     const qpb_state_rec* states = nullptr;
     const qpb_swing_rec* swing = nullptr;  // non-null: whole tick
     qpb_out_rec* out = nullptr;
+    int64_t whole_n = 0;  // size of the batch this shard is cut from, and whether its first record carries a warm-start
+    int whole_warm = 0;   // word: every shard takes the kernels the whole batch would take on one device
   };
   struct Worker {
     qpb_handle* h = nullptr;
@@ -64,8 +66,7 @@ void worker_main(qpb_multi_handle* m, int r) {
     const qpb_multi_handle::Job& j = w.job;
     int rc = QPB_SUCCESS;
     if (j.n > 0)
-      rc = j.swing ? qpb_tick_batch_host(w.h, j.n, j.states, j.swing, j.out)
-                   : qpb_control_batch_host(w.h, j.n, j.states, j.out);
+      rc = qpb_internal_host_shard(w.h, j.n, j.states, j.swing, j.out, j.whole_n, j.whole_warm);
     w.rc = rc;
     w.err = rc == QPB_SUCCESS ? "" : qpb_last_error();  // the error text is thread-local: carry it to the caller
     {
@@ -88,6 +89,8 @@ int run_sharded(qpb_multi_handle* m, int64_t n, const qpb_state_rec* states, con
       j.states = states + lo;
       j.swing = swing ? swing + lo : nullptr;
       j.out = out + lo;
+      j.whole_n = n;
+      j.whole_warm = (states[0].pad[3] & 0x80u) != 0;
     }
     m->pending = g;
     m->epoch++;
