@@ -23,7 +23,8 @@ sys.path.insert(0, ROOT)
 # stdout carries exactly one JSON line: whatever NCCL logs (the version banner when NCCL_DEBUG is set) goes to stderr
 os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
-from quadruped_control_b200 import ALGO_BYTES_PER_QP, OUT_DTYPE, STATE_DTYPE, default_params, states  # noqa: E402
+from quadruped_control_b200 import (ALGO_BYTES_PER_QP, OUT_DTYPE, STATE_DTYPE, WIRE_OUT_DTYPE, WIRE_STATE_DTYPE,  # noqa: E402
+                                    default_params, states, to_wire)
 from quadruped_control_b200.sharding import reduce_report  # noqa: E402
 
 WORKLOADS = {
@@ -287,8 +288,8 @@ def pcie_bound(pin_in, pin_out, n, dev, barrier, reps=6):
     """Concurrent pinned H2D + D2H of one step's bytes on two streams, no kernels: ms per step on this rank."""
     import torch
 
-    d_i = torch.empty(n * STATE_DTYPE.itemsize, dtype=torch.uint8, device=dev)
-    d_o = torch.empty(n * OUT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+    d_i = torch.empty(pin_in[0].nbytes, dtype=torch.uint8, device=dev)
+    d_o = torch.empty(pin_out[0].nbytes, dtype=torch.uint8, device=dev)
     h_i = [torch.from_numpy(b.array.view(np.uint8).reshape(-1)) for b in pin_in]
     h_o = [torch.from_numpy(b.array.view(np.uint8).reshape(-1)) for b in pin_out]
     s1, s2 = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
@@ -485,38 +486,52 @@ def run_ours(args):
     total_qps = world * n * args.steps / (elapsed_ms * 1e-3)
 
     # ---- end to end through the C ABI with HOST buffers (pinned), copies inside the timed region --
-    # Every step uploads its own 512-B records from pinned host memory and downloads its 256-B results.  Steps are queued
-    # with the asynchronous entry point, two batches in flight, so the upload of step k+1 overlaps the download of step k
-    # (PCIe is full duplex); the final qpb_host_sync() is inside the timed region.  The synchronous call is timed beside it.
+    # Every step uploads its own records from pinned host memory and downloads its results, in the wire format of the
+    # host-buffer calls (qpb_wire_state 488 B up, qpb_wire_out 200 B down: the device records without their padding --
+    # the call is bound by the PCIe link, so bytes are speed).  Steps are queued with the asynchronous entry point, two
+    # batches in flight, so the upload of step k+1 overlaps the download of step k (PCIe is full duplex); the final
+    # qpb_host_sync() is inside the timed region.  The synchronous call and the padded 512 / 256-B records are timed beside it.
     bind_to_local_cpus(local_rank)
-    pin_in = [lib.PinnedBuffer(n, STATE_DTYPE) for _ in range(2)]
-    pin_out = [lib.PinnedBuffer(n, OUT_DTYPE) for _ in range(2)]
-    for k in range(2):
-        pin_in[k].array[:] = host_batches[k % n_rot]
     e2e_steps = max(3, min(args.steps, 20))
-    for i in range(2):
-        solver.control_host(pin_in[i % 2].array, pin_out[i % 2].array)
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(e2e_steps):
-        solver.control_host(pin_in[i % 2].array, pin_out[i % 2].array)
-    sync_local = (time.perf_counter() - t0) * 1e3
-    barrier()
-    for i in range(2):  # untimed: the asynchronous path creates its streams and staging buffers on first use
-        solver.control_host_async(pin_in[i % 2].array, pin_out[i % 2].array)
-    solver.host_sync()
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(e2e_steps):
-        solver.control_host_async(pin_in[i % 2].array, pin_out[i % 2].array)
-    solver.host_sync()
-    e2e_local = (time.perf_counter() - t0) * 1e3
-    barrier()
-    e2e_ms, _ = reduce_report(e2e_local, [0], dist, dev)
-    sync_ms, _ = reduce_report(sync_local, [0], dist, dev)
-    e2e_qps = world * n * e2e_steps / (e2e_ms * 1e-3)
-    e2e_sync_qps = world * n * e2e_steps / (sync_ms * 1e-3)
-    e2e_checksum_ok = bool((pin_out[0].array["status"] == 0).all() and (pin_out[1].array["status"] == 0).all())
+
+    def time_host_calls(dt_in, dt_out, fill, call_sync, call_async):
+        pin_i = [lib.PinnedBuffer(n, dt_in) for _ in range(2)]
+        pin_o = [lib.PinnedBuffer(n, dt_out) for _ in range(2)]
+        for k in range(2):
+            fill(pin_i[k].array, host_batches[k % n_rot])
+        for i in range(2):
+            call_sync(pin_i[i % 2].array, pin_o[i % 2].array)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            call_sync(pin_i[i % 2].array, pin_o[i % 2].array)
+        sync_local = (time.perf_counter() - t0) * 1e3
+        barrier()
+        for i in range(2):  # untimed: the asynchronous path creates its streams and staging buffers on first use
+            call_async(pin_i[i % 2].array, pin_o[i % 2].array)
+        solver.host_sync()
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            call_async(pin_i[i % 2].array, pin_o[i % 2].array)
+        solver.host_sync()
+        async_local = (time.perf_counter() - t0) * 1e3
+        barrier()
+        async_ms, _ = reduce_report(async_local, [0], dist, dev)
+        sync_ms, _ = reduce_report(sync_local, [0], dist, dev)
+        ok = bool((pin_o[0].array["status"] == 0).all() and (pin_o[1].array["status"] == 0).all())
+        return pin_i, pin_o, world * n * e2e_steps / (async_ms * 1e-3), world * n * e2e_steps / (sync_ms * 1e-3), ok
+
+    def fill_padded(dst, src):
+        dst[:] = src
+
+    pad_in, pad_out, padded_qps, padded_sync_qps, padded_ok = time_host_calls(
+        STATE_DTYPE, OUT_DTYPE, fill_padded, solver.control_host, solver.control_host_async)
+    for b in pad_in + pad_out:
+        b.free()
+    pin_in, pin_out, e2e_qps, e2e_sync_qps, e2e_checksum_ok = time_host_calls(
+        WIRE_STATE_DTYPE, WIRE_OUT_DTYPE, lambda dst, src: to_wire(src, dst), solver.control_wire_host, solver.control_wire_host_async)
+    e2e_checksum_ok = e2e_checksum_ok and padded_ok
     # the same bytes with no solver in between: what the PCIe link (and the host memory behind it) gives this rank while
     # every rank does the same -- the bound of the end-to-end number
     pcie = pcie_bound(pin_in, pin_out, n, dev, barrier)
@@ -552,11 +567,13 @@ def run_ours(args):
                          "fp64": fp64_block(last["iters"], n, kernel_ms),
                          "note": "the path is FP64-issue/latency bound, not DRAM bound (DESIGN.md); per-GPU figure"},
             "cpu_baseline": cpu,
-            "e2e": {"value": e2e_qps, "unit": UNIT, "h2d_bytes_per_step": n * STATE_DTYPE.itemsize,
-                    "d2h_bytes_per_step": n * OUT_DTYPE.itemsize, "steps": e2e_steps, "ok": e2e_checksum_ok,
-                    "api": "qpb_control_batch_host_async x steps + qpb_host_sync (pinned host buffers, two batches in flight, staged H2D / kernels / D2H)",
-                    "sync_call_value": e2e_sync_qps, "sync_api": "qpb_control_batch_host (returns when the batch is complete)",
-                    "pcie_bound_qps": pcie_qps, "pcie_bound_gbs": pcie_qps * (STATE_DTYPE.itemsize + OUT_DTYPE.itemsize) / 1e9,
+            "e2e": {"value": e2e_qps, "unit": UNIT, "h2d_bytes_per_step": n * WIRE_STATE_DTYPE.itemsize,
+                    "d2h_bytes_per_step": n * WIRE_OUT_DTYPE.itemsize, "steps": e2e_steps, "ok": e2e_checksum_ok,
+                    "api": "qpb_control_batch_wire_host_async x steps + qpb_host_sync (pinned host buffers of 488-B / 200-B wire records, two batches in flight, staged H2D / kernels / D2H)",
+                    "sync_call_value": e2e_sync_qps, "sync_api": "qpb_control_batch_wire_host (returns when the batch is complete)",
+                    "padded_records_value": padded_qps, "padded_records_sync_value": padded_sync_qps,
+                    "padded_records_api": "qpb_control_batch_host_async / qpb_control_batch_host on the 512-B / 256-B device records (round 1's and the C++ shim's format)",
+                    "pcie_bound_qps": pcie_qps, "pcie_bound_gbs": pcie_qps * (WIRE_STATE_DTYPE.itemsize + WIRE_OUT_DTYPE.itemsize) / 1e9,
                     "pcie_frac": e2e_qps / pcie_qps,
                     "pcie_note": "bound = the same pinned buffers copied H2D and D2H concurrently (cudaMemcpyAsync on two streams) on every rank at once, no kernels"},
             "secondary": secondary,

@@ -138,6 +138,31 @@ int qpb_control_batch_host(qpb_handle* h, int64_t n, const qpb_state_rec* h_stat
 int qpb_control_batch_host_async(qpb_handle* h, int64_t n, const qpb_state_rec* h_states, qpb_out_rec* h_out);
 int qpb_host_sync(qpb_handle* h);
 
+/* Wire format of the host-buffer calls: the same fields without the padding that rounds the device records up to 512 and
+ * 256 bytes -- 488 B up and 200 B down per robot instead of 768 B in all.  A host-buffer call is bound by the PCIe link
+ * (bench.py `e2e.pcie_bound_qps`), so the bytes on the wire are its speed; the records are widened to qpb_state_rec and
+ * narrowed from qpb_out_rec on the device, one small kernel either side of the solve. */
+typedef struct qpb_wire_state {
+  double Rwb[9], Rwb_d[9];
+  double x[3], xdot[3], w[3], x_d[3], xdot_d[3], w_d[3];
+  double feet[12];
+  double q[12];
+  uint8_t contact[4];
+  uint32_t warm; /* = qpb_state_rec.pad[0..3]: last tick's qpb_wire_out.wset, or 0 */
+} qpb_wire_state;  /* 488 bytes */
+
+typedef struct qpb_wire_out {
+  double grf_body[12];
+  double tau[12];
+  int16_t status;
+  int16_t iters; /* saturates at 32767 */
+  uint32_t wset; /* = qpb_out_rec.pad[0..3] */
+} qpb_wire_out;    /* 200 bytes */
+
+/* qpb_control_batch_host / _async on wire records; same results, field for field (tests/test_gpu_parity.py). */
+int qpb_control_batch_wire_host(qpb_handle* h, int64_t n, const qpb_wire_state* h_states, qpb_wire_out* h_out);
+int qpb_control_batch_wire_host_async(qpb_handle* h, int64_t n, const qpb_wire_state* h_states, qpb_wire_out* h_out);
+
 /* Tell the handle that the records of its DEVICE-resident calls (qpb_control_batch_packed, qpb_tick_batch_packed) carry
  * warm-start words in pad[0..3] -- a controller in its loop, every tick handing the previous tick's qpb_out_rec.pad[0..3]
  * back, which is how the reference uses SQProblem::hotstart (balance_controller.cpp:177-202).  Such batches take a

@@ -8,6 +8,10 @@ from .records import (  # noqa: F401
     QPB_OK,
     STATE_DTYPE,
     SWING_DTYPE,
+    WIRE_OUT_DTYPE,
+    WIRE_STATE_DTYPE,
+    from_wire,
+    to_wire,
     JointGains,
     default_joint_gains,
     Params,

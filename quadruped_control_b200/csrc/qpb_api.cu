@@ -11,6 +11,7 @@
 #include <new>
 #include <string>
 #include <type_traits>
+#include <vector>
 
 #include "qpb_internal.h"
 #include "qpb_kernel.cuh"
@@ -18,6 +19,7 @@
 #include "qpb_plan.cuh"
 #include "qpb_swing.cuh"
 #include "qpb_tpq.cuh"
+#include "qpb_wire.cuh"
 
 namespace {
 
@@ -87,12 +89,22 @@ struct qpb_handle {
   int warm_batches = 0;         // device-resident calls: the records carry warm-start words (qpb_set_warm_batches)
   int64_t tpq_warm_one_max = (int64_t)1 << 40;  // warm batches up to this size take tpq_one_kernel (QPB_TPQ_WARM_ONE_MAX)
   qpb::tpq::FastParams fast;
+  qpb::tpq::EdgeParams edge;  // the slice of params the set-up / finishing passes take by value
   qpb_params params;
   qpb_params* d_params = nullptr;
   cudaStream_t streams[kHostSlots] = {};
   qpb_state_rec* d_in[kHostSlots] = {};
   qpb_out_rec* d_out[kHostSlots] = {};
   qpb_swing_rec* d_sw[kHostSlots] = {};
+  qpb_wire_state* d_win[kHostSlots] = {};  // wire records of a stage as they arrive / leave (qpb_control_batch_wire_host)
+  qpb_wire_out* d_wout[kHostSlots] = {};
+  double* d_scratch[kHostSlots] = {};  // scratch of the three-pass path for one pipeline stage (instead of cudaMallocAsync)
+  // QPB_HOST_TRACE=1: every stage of the host pipeline is bracketed by events (stream reached the stage, upload done,
+  // kernels done, download done); the next synchronisation prints the timeline to stderr.  A debugging aid.
+  int trace = 0;
+  struct TraceStage { cudaEvent_t ev[4]; int slot; int64_t m; };
+  std::vector<TraceStage> trace_stages;
+  int host_stages = 8;                 // stages a host batch is cut into on the three-pass path (QPB_HOST_STAGES)
   qpb_joint_gains* d_gains = nullptr;  // JointController gains for the swing-leg half of the tick
   qpb_plan_params* d_plan = nullptr;   // FootPlanner / FootTrajectoryManager constants
   std::atomic<int64_t> launches{ 0 };
@@ -134,7 +146,7 @@ inline qpb::SplitIO offset_io(const qpb::SplitIO& io, int64_t lo) {
 
 template <class IO>
 int launch_balance(qpb_handle* h, const IO& io, int64_t n, int ctas_per_sm, cudaStream_t stream, int force_path = 0,
-                   uint32_t* flags = nullptr, uint32_t seq = 0, int64_t whole_n = 0) {
+                   uint32_t* flags = nullptr, uint32_t seq = 0, int64_t whole_n = 0, double* scratch = nullptr) {
   if (n == 0) return QPB_SUCCESS;
   if (n > kMaxRecordsPerLaunch) return fail(QPB_ERR_INVALID_ARG, "more than 2^31 records in one call: split the batch");
   // 1: one warp per QP; 2: two QPs per warp (half-warp kernel); 32: range-space path.  force_path: a caller that cuts a
@@ -156,15 +168,16 @@ int launch_balance(qpb_handle* h, const IO& io, int64_t n, int ctas_per_sm, cuda
     for (int64_t lo = 0; lo < n; lo += kTpqChunk) {
       const int64_t m = n - lo < kTpqChunk ? n - lo : kTpqChunk;
       const IO part = offset_io(io, lo);
-      double* prep = nullptr;  // m prepared records, m result words, the worklist of the loop pass (m record indices)
+      double* prep = scratch;  // m prepared records, m result words, the worklist of the loop pass (m record indices)
       const size_t prep_bytes = (size_t)m * qpb::tpq::kPrepSize * sizeof(double);
-      QPB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&prep), prep_bytes + (size_t)m * (sizeof(double) + sizeof(uint32_t)), stream));
+      if (!scratch)  // (the host pipeline brings its own: one block per stage slot, n <= kHostChunkMax)
+        QPB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&prep), prep_bytes + (size_t)m * (sizeof(double) + sizeof(uint32_t)), stream));
       double* res = prep + (size_t)m * qpb::tpq::kPrepSize;
       uint32_t* work = reinterpret_cast<uint32_t*>(res + m);
       const uint32_t slot2 = lo == 0 ? slot : h->ticket_slot.fetch_add(1, std::memory_order_relaxed) % kTicketSlots;
       unsigned long long* tk = h->d_tickets + 4 * (size_t)slot2;
       const unsigned edge = (unsigned)((m + qpb::tpq::kEdgeThreads - 1) / qpb::tpq::kEdgeThreads);
-      qpb::tpq::tpq_setup_kernel<IO><<<edge, qpb::tpq::kEdgeThreads, 0, stream>>>(h->params, h->fast, part, m, prep, res, work, tk);
+      qpb::tpq::tpq_setup_kernel<IO><<<edge, qpb::tpq::kEdgeThreads, 0, stream>>>(h->edge, h->fast, part, m, prep, res, work, tk);
       const int lthreads = lpq == 1 ? qpb::tpq::LoopShape<1>::THREADS : (lpq == 2 ? qpb::tpq::LoopShape<2>::THREADS : qpb::tpq::LoopShape<4>::THREADS);
       const int64_t want = (m * lpq + lthreads - 1) / lthreads;
       const int64_t cap = (int64_t)h->num_sms * h->ctas_per_sm_tpq[lpq];
@@ -175,10 +188,10 @@ int launch_balance(qpb_handle* h, const IO& io, int64_t n, int ctas_per_sm, cuda
         qpb::tpq::tpq_loop_kernel<2><<<grid, lthreads, 0, stream>>>(h->fast, prep, res, work, tk);
       else
         qpb::tpq::tpq_loop_kernel<4><<<grid, lthreads, 0, stream>>>(h->fast, prep, res, work, tk);
-      qpb::tpq::tpq_finish_kernel<IO><<<edge, qpb::tpq::kEdgeThreads, 0, stream>>>(h->params, h->fast, part, m, prep, res);
+      qpb::tpq::tpq_finish_kernel<IO><<<edge, qpb::tpq::kEdgeThreads, 0, stream>>>(h->edge, h->fast, part, m, prep, res);
       h->launches.fetch_add(3, std::memory_order_relaxed);
       QPB_CUDA(cudaGetLastError());
-      QPB_CUDA(cudaFreeAsync(prep, stream));
+      if (!scratch) QPB_CUDA(cudaFreeAsync(prep, stream));
     }
     return QPB_SUCCESS;
   }
@@ -190,9 +203,9 @@ int launch_balance(qpb_handle* h, const IO& io, int64_t n, int ctas_per_sm, cuda
     // a warp per record: the epilogue is shared out over its lanes (decided on the batch a shard is cut from: the two
     // epilogues round differently in the last bit)
     if (per_cta == 1 && (whole_n > n ? whole_n : n) <= (int64_t)h->num_sms * 8)
-      qpb::tpq::tpq_one_kernel<IO, true><<<grid, qpb::tpq::kOneThreads, 0, stream>>>(h->params, h->fast, io, n, 1, flags, seq);
+      qpb::tpq::tpq_one_kernel<IO, true><<<grid, qpb::tpq::kOneThreads, 0, stream>>>(h->edge, h->fast, io, n, 1, flags, seq);
     else
-      qpb::tpq::tpq_one_kernel<IO, false><<<grid, qpb::tpq::kOneThreads, 0, stream>>>(h->params, h->fast, io, n, (int)per_cta, nullptr, 0u);
+      qpb::tpq::tpq_one_kernel<IO, false><<<grid, qpb::tpq::kOneThreads, 0, stream>>>(h->edge, h->fast, io, n, (int)per_cta, nullptr, 0u);
     h->launches.fetch_add(1, std::memory_order_relaxed);
     QPB_CUDA(cudaGetLastError());
     return QPB_SUCCESS;
@@ -253,20 +266,37 @@ int sync_pipeline(qpb_handle* h) {
       if (e != cudaSuccess && first == cudaSuccess) first = e;
     }
   if (first != cudaSuccess) return fail(QPB_ERR_CUDA, std::string("cudaStreamSynchronize: ") + cudaGetErrorString(first));
+  if (h->trace && !h->trace_stages.empty()) {
+    std::fprintf(stderr, "qpb host pipeline: %zu stages (us since the first one was reached)\n  #  slot records   reached  uploaded    solved downloaded\n",
+                 h->trace_stages.size());
+    for (size_t i = 0; i < h->trace_stages.size(); i++) {
+      float t[4] = { 0.f, 0.f, 0.f, 0.f };
+      for (int k = 0; k < 4; k++) cudaEventElapsedTime(&t[k], h->trace_stages[0].ev[0], h->trace_stages[i].ev[k]);
+      std::fprintf(stderr, "%3zu  %4d %7lld %9.1f %9.1f %9.1f %9.1f\n", i, h->trace_stages[i].slot, (long long)h->trace_stages[i].m,
+                   t[0] * 1e3, t[1] * 1e3, t[2] * 1e3, t[3] * 1e3);
+    }
+    for (auto& ts : h->trace_stages)
+      for (int k = 0; k < 4; k++) cudaEventDestroy(ts.ev[k]);
+    (void)cudaGetLastError();
+    h->trace_stages.clear();
+  }
   return QPB_SUCCESS;
 }
 
 // whole_n / whole_warm: when the n records are one shard of a larger batch (qpb_multi_*), the size of that batch and
 // whether ITS first record carries a warm-start word -- the kernels are chosen for the batch, not for the shard.
+// w_in / w_out (instead of h_states / h_out): the batch travels as wire records and is widened / narrowed on the device.
 int host_pipeline(qpb_handle* h, int64_t n, const qpb_state_rec* h_states, const qpb_swing_rec* h_swing, qpb_out_rec* h_out,
-                  bool async = false, int64_t whole_n = -1, int whole_warm = -1) {
+                  bool async = false, int64_t whole_n = -1, int whole_warm = -1, const qpb_wire_state* w_in = nullptr,
+                  qpb_wire_out* w_out = nullptr) {
   if (n == 0) return QPB_SUCCESS;
+  const bool wire = w_in != nullptr;
   DeviceGuard guard(h->device);
   if (!guard.ok) return fail(QPB_ERR_CUDA, "cudaSetDevice failed");
   // one path for the whole batch, whatever the pieces it is cut into
   // (host records can be looked at: a batch whose first record carries a warm-start word is taken to be a warm batch)
   const int64_t dn = whole_n >= 0 ? whole_n : n;
-  const bool hinted = whole_warm >= 0 ? whole_warm != 0 : (h_states[0].pad[3] & 0x80u) != 0;
+  const bool hinted = whole_warm >= 0 ? whole_warm != 0 : (wire ? (w_in[0].warm >> 31) != 0u : (h_states[0].pad[3] & 0x80u) != 0);
   const bool warm = h->qps_per_warp == 32 && (h->warm_batches || hinted);
   const bool range_space = h->qps_per_warp == 32 && (warm ? dn > h->tpq_warm_one_max : dn >= h->tpq_min_n);
   const int path = range_space ? 32 : (h->qps_per_warp == 32 ? ((warm || dn <= h->tpq_one_max) ? 33 : 2) : h->qps_per_warp);
@@ -275,7 +305,12 @@ int host_pipeline(qpb_handle* h, int64_t n, const qpb_state_rec* h_states, const
     const int rc0 = ensure_small(h);
     if (rc0 != QPB_SUCCESS) return rc0;
     const size_t off_out = (size_t)kSmallCall * sizeof(qpb_state_rec), off_sw = off_out + (size_t)kSmallCall * sizeof(qpb_out_rec);
-    std::memcpy(h->h_small, h_states, (size_t)n * sizeof(qpb_state_rec));
+    if (wire) {  // a handful of records: widen them on the way into the pinned block
+      std::memset(h->h_small, 0, (size_t)n * sizeof(qpb_state_rec));
+      for (int64_t i = 0; i < n; i++) std::memcpy(h->h_small + (size_t)i * sizeof(qpb_state_rec), w_in + i, sizeof(qpb_wire_state));
+    } else {
+      std::memcpy(h->h_small, h_states, (size_t)n * sizeof(qpb_state_rec));
+    }
     if (h_swing) std::memcpy(h->h_small + off_sw, h_swing, (size_t)n * sizeof(qpb_swing_rec));
     const qpb_state_rec* ds = reinterpret_cast<const qpb_state_rec*>(h->d_small);
     qpb_out_rec* dout = reinterpret_cast<qpb_out_rec*>(h->d_small + off_out);
@@ -309,10 +344,20 @@ int host_pipeline(qpb_handle* h, int64_t n, const qpb_state_rec* h_states, const
       std::atomic_thread_fence(std::memory_order_acquire);
     }
     if (!stamped) QPB_CUDA(cudaStreamSynchronize(h->streams[0]));
-    std::memcpy(h_out, h->h_small + off_out, (size_t)n * sizeof(qpb_out_rec));
+    if (wire) {
+      for (int64_t i = 0; i < n; i++) {
+        const qpb_out_rec* o = reinterpret_cast<const qpb_out_rec*>(h->h_small + off_out) + i;
+        std::memcpy(w_out + i, o, 24 * sizeof(double));
+        w_out[i].status = (int16_t)o->status;
+        w_out[i].iters = (int16_t)(o->iters < 0 ? 0 : (o->iters > 32767 ? 32767 : o->iters));
+        std::memcpy(&w_out[i].wset, o->pad, sizeof(uint32_t));
+      }
+    } else {
+      std::memcpy(h_out, h->h_small + off_out, (size_t)n * sizeof(qpb_out_rec));
+    }
     return QPB_SUCCESS;
   }
-  if (!async && h->zero_copy && !h_swing && !range_space) {
+  if (!async && h->zero_copy && !h_swing && !range_space && !wire) {
     // Pinned (hence mapped) buffers and the one-launch kernels: the launch reads the records and writes the results
     // straight over PCIe, one coalesced 512-B request per record.  No staging copies, no pipeline fill/drain.  (The
     // range-space path makes three passes over its records, so it always stages them in device memory.)
@@ -334,12 +379,16 @@ int host_pipeline(qpb_handle* h, int64_t n, const qpb_state_rec* h_states, const
     if (!h->d_in[s]) QPB_CUDA(cudaMalloc(&h->d_in[s], kHostChunkMax * sizeof(qpb_state_rec)));
     if (!h->d_out[s]) QPB_CUDA(cudaMalloc(&h->d_out[s], kHostChunkMax * sizeof(qpb_out_rec)));
     if (h_swing && !h->d_sw[s]) QPB_CUDA(cudaMalloc(&h->d_sw[s], kHostChunkMax * sizeof(qpb_swing_rec)));
+    if (wire && !h->d_win[s]) QPB_CUDA(cudaMalloc(&h->d_win[s], kHostChunkMax * sizeof(qpb_wire_state)));
+    if (wire && !h->d_wout[s]) QPB_CUDA(cudaMalloc(&h->d_wout[s], kHostChunkMax * sizeof(qpb_wire_out)));
+    if (range_space && !h->d_scratch[s])
+      QPB_CUDA(cudaMalloc(&h->d_scratch[s], kHostChunkMax * (qpb::tpq::kPrepSize * sizeof(double) + sizeof(double) + sizeof(uint32_t))));
   }
   // Stages of records are uploaded, solved and downloaded on a ring of streams, so the copy engines and the SMs overlap.
   // One-launch kernels: stage sizes halve towards the end of the batch so the last kernel + download (the part that
   // cannot overlap an upload) is short.  Range-space path (three launches per stage): about eight equal stages.
   const int64_t chunk = h->host_chunk, min_chunk = 1024;
-  int64_t even = ((n + 7) / 8 + 1023) / 1024 * 1024;
+  int64_t even = ((n + h->host_stages - 1) / h->host_stages + 1023) / 1024 * 1024;
   if (even < 4096) even = 4096;
   if (even > kHostChunkMax) even = kHostChunkMax;
   int rc = QPB_SUCCESS;
@@ -354,15 +403,44 @@ int host_pipeline(qpb_handle* h, int64_t n, const qpb_state_rec* h_states, const
     }
     const int slot = (int)(h->host_slot++ % kHostSlots);
     cudaStream_t st = h->streams[slot];
-    ce = cudaMemcpyAsync(h->d_in[slot], h_states + lo, m * sizeof(qpb_state_rec), cudaMemcpyHostToDevice, st);
+    qpb_handle::TraceStage tr{ {}, slot, m };
+    if (h->trace) {
+      for (int k = 0; k < 4; k++) cudaEventCreate(&tr.ev[k]);
+      cudaEventRecord(tr.ev[0], st);
+    }
+    if (wire) {
+      ce = cudaMemcpyAsync(h->d_win[slot], w_in + lo, m * sizeof(qpb_wire_state), cudaMemcpyHostToDevice, st);
+      if (ce == cudaSuccess) {
+        qpb::wire_unpack_kernel<<<(unsigned)((m * 64 + 255) / 256), 256, 0, st>>>(
+            reinterpret_cast<const uint64_t*>(h->d_win[slot]), reinterpret_cast<uint64_t*>(h->d_in[slot]), m);
+        h->launches.fetch_add(1, std::memory_order_relaxed);
+        ce = cudaGetLastError();
+      }
+    } else {
+      ce = cudaMemcpyAsync(h->d_in[slot], h_states + lo, m * sizeof(qpb_state_rec), cudaMemcpyHostToDevice, st);
+    }
     if (ce == cudaSuccess && h_swing)
       ce = cudaMemcpyAsync(h->d_sw[slot], h_swing + lo, m * sizeof(qpb_swing_rec), cudaMemcpyHostToDevice, st);
     if (ce != cudaSuccess) break;
+    if (h->trace) cudaEventRecord(tr.ev[1], st);
     qpb::PackedIO io{ h->d_in[slot], h->d_out[slot] };
-    rc = launch_balance(h, io, m, h->ctas_per_sm_packed, st, path, nullptr, 0u, dn);
+    rc = launch_balance(h, io, m, h->ctas_per_sm_packed, st, path, nullptr, 0u, dn, range_space ? h->d_scratch[slot] : nullptr);
     if (rc == QPB_SUCCESS && h_swing) rc = launch_swing(h, m, h->d_in[slot], h->d_sw[slot], h->d_out[slot], st);
     if (rc != QPB_SUCCESS) break;
-    ce = cudaMemcpyAsync(h_out + lo, h->d_out[slot], m * sizeof(qpb_out_rec), cudaMemcpyDeviceToHost, st);
+    if (h->trace) cudaEventRecord(tr.ev[2], st);
+    if (wire) {
+      qpb::wire_pack_kernel<<<(unsigned)((m * qpb::kWireOutWords + 255) / 256), 256, 0, st>>>(
+          reinterpret_cast<const uint64_t*>(h->d_out[slot]), reinterpret_cast<uint64_t*>(h->d_wout[slot]), m);
+      h->launches.fetch_add(1, std::memory_order_relaxed);
+      ce = cudaGetLastError();
+      if (ce == cudaSuccess) ce = cudaMemcpyAsync(w_out + lo, h->d_wout[slot], m * sizeof(qpb_wire_out), cudaMemcpyDeviceToHost, st);
+    } else {
+      ce = cudaMemcpyAsync(h_out + lo, h->d_out[slot], m * sizeof(qpb_out_rec), cudaMemcpyDeviceToHost, st);
+    }
+    if (h->trace) {
+      cudaEventRecord(tr.ev[3], st);
+      h->trace_stages.push_back(tr);
+    }
   }
   if (rc != QPB_SUCCESS || ce != cudaSuccess) {
     // earlier stages may still be copying into the caller's buffers: never return while they are in flight
@@ -497,6 +575,7 @@ int qpb_create(const qpb_params* params, int device, qpb_handle** out) {
   // The thread-per-QP kernel needs W = w I (range-space form) and fzmin >= 0 (its working sets stay within the faces
   // of the truncated pyramid, qpb_tpq_core.h); everything else takes the general half-warp kernel.
   const bool fast_ok = qpb::tpq::make_fast_params(*params, h->fast) && params->fzmin >= 0.0;
+  h->edge = qpb::tpq::make_edge_params(*params);
   h->qps_per_warp = fast_ok ? 32 : 2;
   if (const char* env = std::getenv("QPB_QPS_PER_WARP")) {
     const int v = std::atoi(env);
@@ -520,6 +599,11 @@ int qpb_create(const qpb_params* params, int device, qpb_handle** out) {
   }
   if (const char* env = std::getenv("QPB_ZEROCOPY")) h->zero_copy = std::atoi(env);
   if (const char* env = std::getenv("QPB_SMALL_POLL")) h->small_poll = std::atoi(env);
+  if (const char* env = std::getenv("QPB_HOST_TRACE")) h->trace = std::atoi(env);
+  if (const char* env = std::getenv("QPB_HOST_STAGES")) {
+    const int v = std::atoi(env);
+    if (v >= 1 && v <= 64) h->host_stages = v;
+  }
   if (const char* env = std::getenv("QPB_HOST_CHUNK")) {
     const long long v = std::atoll(env);
     if (v >= 256 && v <= kHostChunkMax) h->host_chunk = v;
@@ -536,6 +620,9 @@ int qpb_destroy(qpb_handle* h) {
     if (h->d_in[s]) cudaFree(h->d_in[s]);
     if (h->d_out[s]) cudaFree(h->d_out[s]);
     if (h->d_sw[s]) cudaFree(h->d_sw[s]);
+    if (h->d_scratch[s]) cudaFree(h->d_scratch[s]);
+    if (h->d_win[s]) cudaFree(h->d_win[s]);
+    if (h->d_wout[s]) cudaFree(h->d_wout[s]);
   }
   if (h->d_params) cudaFree(h->d_params);
   if (h->d_tickets) cudaFree(h->d_tickets);
@@ -588,6 +675,18 @@ int qpb_control_batch_host_async(qpb_handle* h, int64_t n, const qpb_state_rec* 
   if (!h || n < 0 || (n > 0 && (!h_states || !h_out)))
     return fail(QPB_ERR_INVALID_ARG, "qpb_control_batch_host_async: bad argument");
   return host_pipeline(h, n, h_states, nullptr, h_out, true);
+}
+
+int qpb_control_batch_wire_host(qpb_handle* h, int64_t n, const qpb_wire_state* h_states, qpb_wire_out* h_out) {
+  if (!h || n < 0 || (n > 0 && (!h_states || !h_out)))
+    return fail(QPB_ERR_INVALID_ARG, "qpb_control_batch_wire_host: bad argument");
+  return host_pipeline(h, n, nullptr, nullptr, nullptr, false, -1, -1, h_states, h_out);
+}
+
+int qpb_control_batch_wire_host_async(qpb_handle* h, int64_t n, const qpb_wire_state* h_states, qpb_wire_out* h_out) {
+  if (!h || n < 0 || (n > 0 && (!h_states || !h_out)))
+    return fail(QPB_ERR_INVALID_ARG, "qpb_control_batch_wire_host_async: bad argument");
+  return host_pipeline(h, n, nullptr, nullptr, nullptr, true, -1, -1, h_states, h_out);
 }
 
 int qpb_host_sync(qpb_handle* h) {

@@ -200,7 +200,7 @@ struct PrepCommit {
 
 template <class IO>
 __global__ void __launch_bounds__(kEdgeThreads, QPB_TPQ_EDGE_MINCTAS)
-tpq_setup_kernel(const __grid_constant__ qpb_params P, const __grid_constant__ FastParams K, IO io, int64_t n, double* __restrict__ prep,
+tpq_setup_kernel(const __grid_constant__ EdgeParams P, const __grid_constant__ FastParams K, IO io, int64_t n, double* __restrict__ prep,
                  double* __restrict__ res, uint32_t* __restrict__ work, unsigned long long* __restrict__ ticket) {
   const int64_t rec = (int64_t)blockIdx.x * kEdgeThreads + threadIdx.x;
   bool need = false;  // this record goes through the active-set loop (its starting pair is not optimal yet)
@@ -371,7 +371,7 @@ tpq_loop_kernel(const __grid_constant__ FastParams K, const double* __restrict__
 // ---- pass 3: polish + epilogue, one thread per record -------------------------------------------------------------------
 template <class IO>
 __global__ void __launch_bounds__(kEdgeThreads, QPB_TPQ_FINISH_MINCTAS)
-tpq_finish_kernel(const __grid_constant__ qpb_params P, const __grid_constant__ FastParams K, IO io, int64_t n,
+tpq_finish_kernel(const __grid_constant__ EdgeParams P, const __grid_constant__ FastParams K, IO io, int64_t n,
                   const double* __restrict__ prep, const double* __restrict__ res) {
   const int64_t rec = (int64_t)blockIdx.x * kEdgeThreads + threadIdx.x;
   if (rec >= n) return;
@@ -446,7 +446,7 @@ struct KeepCommit {
 // executes once: profiles/r02_ncu_one_n1_digest.txt).
 template <class IO, bool COOP>
 __global__ void __launch_bounds__(kOneThreads)
-tpq_one_kernel(const __grid_constant__ qpb_params P, const __grid_constant__ FastParams K, IO io, int64_t n, int records_per_cta,
+tpq_one_kernel(const __grid_constant__ EdgeParams P, const __grid_constant__ FastParams K, IO io, int64_t n, int records_per_cta,
                uint32_t* __restrict__ flags, uint32_t seq) {
   __shared__ double side_all[kOneThreads * kSideSize];
   __shared__ double keep_all[kOneThreads * kKeepSize];

@@ -784,6 +784,35 @@ QPB_HD void finish(const Params& P, const double* R, const double* q, const Stat
   }
 }
 
+// What the set-up and finishing passes read of qpb_params (344 of its 1 904 bytes: no S, no W -- FastParams carries what the
+// solver needs of those).  Kernel arguments travel with every launch; with the whole qpb_params by value (2.2 KB per
+// launch, two launches per pipeline stage) the host pipeline stalled with four stages in flight.
+struct EdgeParams {
+  double mass;
+  double Ib[9];
+  double kff[6], kp_p[3], kd_p[3], kp_w[3], kd_w[3];
+  double link[12];
+  double tau_min, tau_max;
+  int32_t clamp_tau;
+};
+inline EdgeParams make_edge_params(const qpb_params& P) {
+  EdgeParams E;
+  E.mass = P.mass;
+  for (int i = 0; i < 9; i++) E.Ib[i] = P.Ib[i];
+  for (int i = 0; i < 6; i++) E.kff[i] = P.kff[i];
+  for (int i = 0; i < 3; i++) {
+    E.kp_p[i] = P.kp_p[i];
+    E.kd_p[i] = P.kd_p[i];
+    E.kp_w[i] = P.kp_w[i];
+    E.kd_w[i] = P.kd_w[i];
+  }
+  for (int i = 0; i < 12; i++) E.link[i] = P.link[i];
+  E.tau_min = P.tau_min;
+  E.tau_max = P.tau_max;
+  E.clamp_tau = P.clamp_tau;
+  return E;
+}
+
 // Host-side derivation of FastParams.  Returns false when W is not a multiple of the identity (the general kernel
 // must be used) or S cannot be inverted.
 inline bool make_fast_params(const qpb_params& P, FastParams& K) {

@@ -9,7 +9,7 @@ import os
 
 import numpy as np
 
-from .records import (MPC_OUT_DTYPE, MPC_REC_DTYPE, OUT_DTYPE, STATE_DTYPE, SWING_DTYPE, JointGains, MpcParams, Params,
+from .records import (MPC_OUT_DTYPE, MPC_REC_DTYPE, OUT_DTYPE, STATE_DTYPE, SWING_DTYPE, WIRE_OUT_DTYPE, WIRE_STATE_DTYPE, JointGains, MpcParams, Params,
                       PlanParams)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -26,6 +26,8 @@ EXPORTS = (
     "qpb_control_batch_host",
     "qpb_control_batch_host_async",
     "qpb_host_sync",
+    "qpb_control_batch_wire_host",
+    "qpb_control_batch_wire_host_async",
     "qpb_jt_batch",
     "qpb_fk_batch",
     "qpb_jt_batch_host",
@@ -85,6 +87,8 @@ def load():
     L.qpb_control_batch_host.argtypes = [vp, i64, vp, vp]
     L.qpb_control_batch_host_async.argtypes = [vp, i64, vp, vp]
     L.qpb_host_sync.argtypes = [vp]
+    L.qpb_control_batch_wire_host.argtypes = [vp, i64, vp, vp]
+    L.qpb_control_batch_wire_host_async.argtypes = [vp, i64, vp, vp]
     L.qpb_jt_batch.argtypes = [vp, i64, dp, dp, dp, dp, vp]
     L.qpb_fk_batch.argtypes = [vp, i64, dp, dp, vp]
     L.qpb_jt_batch_host.argtypes = [vp, i64, dp, dp, dp, dp]
@@ -286,6 +290,23 @@ class BalanceSolver:
         assert out.dtype == OUT_DTYPE and out.shape[0] == states.shape[0] and out.flags.c_contiguous
         _check(load().qpb_control_batch_host_async(self._h, states.shape[0], states.ctypes.data, out.ctypes.data),
                "qpb_control_batch_host_async")
+
+    def control_wire_host(self, states: np.ndarray, out: np.ndarray = None):
+        """Host buffers in the wire format (488 B up, 200 B down per robot; records.to_wire / from_wire convert)."""
+        states = np.ascontiguousarray(states)
+        assert states.dtype == WIRE_STATE_DTYPE
+        if out is None:
+            out = np.empty(states.shape[0], dtype=WIRE_OUT_DTYPE)
+        assert out.dtype == WIRE_OUT_DTYPE and out.shape[0] == states.shape[0] and out.flags.c_contiguous
+        _check(load().qpb_control_batch_wire_host(self._h, states.shape[0], states.ctypes.data, out.ctypes.data),
+               "qpb_control_batch_wire_host")
+        return out
+
+    def control_wire_host_async(self, states: np.ndarray, out: np.ndarray):
+        assert states.dtype == WIRE_STATE_DTYPE and states.flags.c_contiguous
+        assert out.dtype == WIRE_OUT_DTYPE and out.shape[0] == states.shape[0] and out.flags.c_contiguous
+        _check(load().qpb_control_batch_wire_host_async(self._h, states.shape[0], states.ctypes.data, out.ctypes.data),
+               "qpb_control_batch_wire_host_async")
 
     def host_sync(self):
         _check(load().qpb_host_sync(self._h), "qpb_host_sync")

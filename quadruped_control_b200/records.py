@@ -41,6 +41,30 @@ OUT_DTYPE = np.dtype(
 )
 assert OUT_DTYPE.itemsize == 256
 
+# wire records of the host-buffer calls (qpb_wire_state / qpb_wire_out): the same fields without the padding
+WIRE_STATE_DTYPE = np.dtype(STATE_DTYPE.descr[:-1] + [("warm", "<u4")])
+assert WIRE_STATE_DTYPE.itemsize == 488
+WIRE_OUT_DTYPE = np.dtype([("grf_body", "<f8", (12,)), ("tau", "<f8", (12,)), ("status", "<i2"), ("iters", "<i2"), ("wset", "<u4")])
+assert WIRE_OUT_DTYPE.itemsize == 200
+
+
+def to_wire(states: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:
+    """qpb_state_rec array -> qpb_wire_state array (pad[0:4], the warm-start word, becomes ``warm``)."""
+    w = np.empty(states.shape[0], dtype=WIRE_STATE_DTYPE) if out is None else out
+    for name in STATE_DTYPE.names[:-1]:
+        w[name] = states[name]
+    w["warm"] = np.ascontiguousarray(states["pad"][:, :4]).view("<u4")[:, 0]
+    return w
+
+
+def from_wire(wout: np.ndarray) -> np.ndarray:
+    """qpb_wire_out array -> qpb_out_rec array (for comparisons with the device-record entry points)."""
+    o = np.zeros(wout.shape[0], dtype=OUT_DTYPE)
+    o["grf_body"], o["tau"], o["status"], o["iters"] = wout["grf_body"], wout["tau"], wout["status"], wout["iters"]
+    o["pad"][:, :4] = np.ascontiguousarray(wout["wset"]).view("u1").reshape(-1, 4)
+    return o
+
+
 # per-QP status (qpb200.h)
 QPB_OK, QPB_MAX_ITER, QPB_BAD_INPUT = 0, 1, 2
 

@@ -11,7 +11,8 @@ import pytest
 import oracle
 from conftest import rel_err
 from oracle.kkt import certificate
-from quadruped_control_b200 import OUT_DTYPE, STATE_DTYPE, default_params, lib, states
+from quadruped_control_b200 import (OUT_DTYPE, STATE_DTYPE, WIRE_OUT_DTYPE, WIRE_STATE_DTYPE, default_params, from_wire, lib, states,
+                                    to_wire)
 
 pytestmark = pytest.mark.gpu
 
@@ -170,6 +171,36 @@ def test_warm_batches_flag_on_device_calls(built, params06):
     assert np.array_equal(again["status"], cold["status"]) and np.array_equal(again["iters"], cold["iters"])
     assert rel_err(again["grf_body"], cold["grf_body"]) <= 1e-9
     solver.set_warm_batches(False)
+    solver.close()
+
+
+def test_wire_records_give_the_same_results(built, params06):
+    """qpb_control_batch_wire_host(+_async): 488-B / 200-B wire records widened and narrowed on the device must give,
+    field for field, what the 512-B / 256-B records give -- every dispatch size, warm-start words, bad input."""
+    S = states.generate_states(70000, 123, masks="mixed")
+    S["x"][5, 0] = np.nan
+    S["q"][7, 3] = np.inf
+    solver = lib.BalanceSolver(params06)
+    for n in (1, 100, 5000, 70000):
+        ref = solver.control_host(S[:n])
+        got = solver.control_wire_host(to_wire(S[:n]))
+        assert from_wire(got).tobytes() == ref.tobytes()
+    ref = solver.control_host(S)
+    W = S.copy()
+    W["pad"][:, :4] = ref["pad"][:, :4]
+    warm = solver.control_wire_host(to_wire(W))
+    assert from_wire(warm).tobytes() == solver.control_host(W).tobytes()
+    assert warm["iters"].mean() <= 0.02 and np.array_equal(warm["status"], ref["status"])
+    pin_in, pin_out = lib.PinnedBuffer(len(S), WIRE_STATE_DTYPE), [lib.PinnedBuffer(len(S), WIRE_OUT_DTYPE) for _ in range(2)]
+    to_wire(S, pin_in.array)
+    for k in range(2):
+        solver.control_wire_host_async(pin_in.array, pin_out[k].array)
+    solver.host_sync()
+    for k in range(2):
+        assert from_wire(pin_out[k].array).tobytes() == ref.tobytes()
+    pin_in.free()
+    for b in pin_out:
+        b.free()
     solver.close()
 
 

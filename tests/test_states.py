@@ -41,3 +41,21 @@ def test_distributions_match_survey_8d():
     counts = np.bincount(codes, minlength=16)
     assert (counts[[m for m in range(16) if bin(m).count("1") < 2]] == 0).all()
     assert counts[states.MIXED_MASKS].min() > 1700  # uniform over the 11 masks
+
+
+def test_wire_records_round_trip():
+    """to_wire / from_wire (qpb_wire_state 488 B, qpb_wire_out 200 B): the device records without their padding."""
+    from quadruped_control_b200 import OUT_DTYPE, WIRE_OUT_DTYPE, WIRE_STATE_DTYPE, from_wire, to_wire
+
+    S = states.generate_states(37, 5, masks="mixed")
+    S["pad"][:, :4] = np.arange(37 * 4, dtype=np.uint8).reshape(37, 4)
+    W = to_wire(S)
+    assert W.dtype == WIRE_STATE_DTYPE and W.itemsize == 488
+    # the wire record IS the first 488 bytes of the device record
+    assert W.tobytes() == b"".join(S[i].tobytes()[:488] for i in range(37))
+    o = np.zeros(5, dtype=WIRE_OUT_DTYPE)
+    o["grf_body"] = np.arange(60).reshape(5, 12)
+    o["status"], o["iters"], o["wset"] = [0, 1, 2, 0, 0], [3, 200, 0, 7, 32767], [0x80000001, 0x80ffffff, 0, 5, 6]
+    back = from_wire(o)
+    assert back.dtype == OUT_DTYPE and np.array_equal(back["iters"], o["iters"]) and np.array_equal(back["status"], o["status"])
+    assert np.array_equal(back["pad"][:, :4].copy().view("<u4")[:, 0], o["wset"]) and not back["pad"][:, 4:].any()
