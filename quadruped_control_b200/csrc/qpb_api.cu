@@ -92,7 +92,12 @@ struct qpb_handle {
   qpb::tpq::EdgeParams edge;  // the slice of params the set-up / finishing passes take by value
   qpb_params params;
   qpb_params* d_params = nullptr;
-  cudaStream_t streams[kHostSlots] = {};
+  cudaStream_t streams[kHostSlots] = {};  // per-slot compute streams of the host pipeline ([0] also serves the small calls)
+  // All uploads of the pipeline go down ONE stream and all downloads down another, so the copy engines get their work
+  // back to back (copies issued from six different streams left a 5-us gap between consecutive uploads); events carry
+  // the dependencies: upload -> kernels -> download, and a slot's buffers are refilled only after their last reader.
+  cudaStream_t up_stream = nullptr, down_stream = nullptr;
+  cudaEvent_t ev_up[kHostSlots] = {}, ev_in_free[kHostSlots] = {}, ev_solved[kHostSlots] = {}, ev_down[kHostSlots] = {};
   qpb_state_rec* d_in[kHostSlots] = {};
   qpb_out_rec* d_out[kHostSlots] = {};
   qpb_swing_rec* d_sw[kHostSlots] = {};
@@ -104,6 +109,8 @@ struct qpb_handle {
   int trace = 0;
   struct TraceStage { cudaEvent_t ev[4]; int slot; int64_t m; };
   std::vector<TraceStage> trace_stages;
+  int host_cstreams = 2;               // compute streams the stages rotate over: 2 measured best, 3 worst (QPB_HOST_CSTREAMS,
+                                       // profiles/r02_host_pipeline_streams.txt)
   int host_stages = 8;                 // stages a host batch is cut into on the three-pass path (QPB_HOST_STAGES)
   qpb_joint_gains* d_gains = nullptr;  // JointController gains for the swing-leg half of the tick
   qpb_plan_params* d_plan = nullptr;   // FootPlanner / FootTrajectoryManager constants
@@ -260,11 +267,13 @@ int ensure_small(qpb_handle* h) {
 // streams so the three overlap (the tick always stages: its second kernel would re-read the records over PCIe).
 int sync_pipeline(qpb_handle* h) {
   cudaError_t first = cudaSuccess;
-  for (int s = 0; s < kHostSlots; s++)
-    if (h->streams[s]) {
-      const cudaError_t e = cudaStreamSynchronize(h->streams[s]);
+  for (int s = 0; s < kHostSlots + 2; s++) {
+    cudaStream_t st = s < kHostSlots ? h->streams[s] : (s == kHostSlots ? h->up_stream : h->down_stream);
+    if (st) {
+      const cudaError_t e = cudaStreamSynchronize(st);
       if (e != cudaSuccess && first == cudaSuccess) first = e;
     }
+  }
   if (first != cudaSuccess) return fail(QPB_ERR_CUDA, std::string("cudaStreamSynchronize: ") + cudaGetErrorString(first));
   if (h->trace && !h->trace_stages.empty()) {
     std::fprintf(stderr, "qpb host pipeline: %zu stages (us since the first one was reached)\n  #  slot records   reached  uploaded    solved downloaded\n",
@@ -374,8 +383,12 @@ int host_pipeline(qpb_handle* h, int64_t n, const qpb_state_rec* h_states, const
       (void)cudaGetLastError();
     }
   }
+  if (!h->up_stream) QPB_CUDA(cudaStreamCreateWithFlags(&h->up_stream, cudaStreamNonBlocking));
+  if (!h->down_stream) QPB_CUDA(cudaStreamCreateWithFlags(&h->down_stream, cudaStreamNonBlocking));
   for (int s = 0; s < kHostSlots; s++) {  // lazily create the pipeline
     if (!h->streams[s]) QPB_CUDA(cudaStreamCreateWithFlags(&h->streams[s], cudaStreamNonBlocking));
+    for (cudaEvent_t* e : { &h->ev_up[s], &h->ev_in_free[s], &h->ev_solved[s], &h->ev_down[s] })
+      if (!*e) QPB_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     if (!h->d_in[s]) QPB_CUDA(cudaMalloc(&h->d_in[s], kHostChunkMax * sizeof(qpb_state_rec)));
     if (!h->d_out[s]) QPB_CUDA(cudaMalloc(&h->d_out[s], kHostChunkMax * sizeof(qpb_out_rec)));
     if (h_swing && !h->d_sw[s]) QPB_CUDA(cudaMalloc(&h->d_sw[s], kHostChunkMax * sizeof(qpb_swing_rec)));
@@ -402,43 +415,64 @@ int host_pipeline(qpb_handle* h, int64_t n, const qpb_state_rec* h_states, const
       if (m > chunk) m = chunk;
     }
     const int slot = (int)(h->host_slot++ % kHostSlots);
-    cudaStream_t st = h->streams[slot];
+    cudaStream_t st = h->streams[slot % h->host_cstreams], up = h->up_stream, down = h->down_stream;
     qpb_handle::TraceStage tr{ {}, slot, m };
     if (h->trace) {
       for (int k = 0; k < 4; k++) cudaEventCreate(&tr.ev[k]);
-      cudaEventRecord(tr.ev[0], st);
+      cudaEventRecord(tr.ev[0], up);
     }
-    if (wire) {
-      ce = cudaMemcpyAsync(h->d_win[slot], w_in + lo, m * sizeof(qpb_wire_state), cudaMemcpyHostToDevice, st);
-      if (ce == cudaSuccess) {
-        qpb::wire_unpack_kernel<<<(unsigned)((m * 64 + 255) / 256), 256, 0, st>>>(
-            reinterpret_cast<const uint64_t*>(h->d_win[slot]), reinterpret_cast<uint64_t*>(h->d_in[slot]), m);
-        h->launches.fetch_add(1, std::memory_order_relaxed);
-        ce = cudaGetLastError();
-      }
-    } else {
-      ce = cudaMemcpyAsync(h->d_in[slot], h_states + lo, m * sizeof(qpb_state_rec), cudaMemcpyHostToDevice, st);
-    }
-    if (ce == cudaSuccess && h_swing)
-      ce = cudaMemcpyAsync(h->d_sw[slot], h_swing + lo, m * sizeof(qpb_swing_rec), cudaMemcpyHostToDevice, st);
+    // upload, once the slot's input buffers have been read by their last user (a wait on an event that was never
+    // recorded returns at once)
+    ce = cudaStreamWaitEvent(up, h->ev_in_free[slot], 0);
+    if (ce == cudaSuccess && !wire) ce = cudaStreamWaitEvent(up, h->ev_solved[slot], 0);  // d_in is what the kernels read
     if (ce != cudaSuccess) break;
-    if (h->trace) cudaEventRecord(tr.ev[1], st);
+    if (wire)
+      ce = cudaMemcpyAsync(h->d_win[slot], w_in + lo, m * sizeof(qpb_wire_state), cudaMemcpyHostToDevice, up);
+    else
+      ce = cudaMemcpyAsync(h->d_in[slot], h_states + lo, m * sizeof(qpb_state_rec), cudaMemcpyHostToDevice, up);
+    if (ce == cudaSuccess && h_swing)
+      ce = cudaMemcpyAsync(h->d_sw[slot], h_swing + lo, m * sizeof(qpb_swing_rec), cudaMemcpyHostToDevice, up);
+    if (ce == cudaSuccess) ce = cudaEventRecord(h->ev_up[slot], up);
+    if (ce != cudaSuccess) break;
+    if (h->trace) cudaEventRecord(tr.ev[1], up);
+    // kernels, once the records are there and the slot's previous results have left
+    ce = cudaStreamWaitEvent(st, h->ev_up[slot], 0);
+    if (ce == cudaSuccess) ce = cudaStreamWaitEvent(st, h->ev_down[slot], 0);
+    if (ce != cudaSuccess) break;
+    if (wire) {
+      qpb::wire_unpack_kernel<<<(unsigned)((m * 64 + 255) / 256), 256, 0, st>>>(
+          reinterpret_cast<const uint64_t*>(h->d_win[slot]), reinterpret_cast<uint64_t*>(h->d_in[slot]), m);
+      h->launches.fetch_add(1, std::memory_order_relaxed);
+      ce = cudaGetLastError();
+      if (ce == cudaSuccess && !h_swing) ce = cudaEventRecord(h->ev_in_free[slot], st);  // the wire records have been read
+      if (ce != cudaSuccess) break;
+    }
     qpb::PackedIO io{ h->d_in[slot], h->d_out[slot] };
     rc = launch_balance(h, io, m, h->ctas_per_sm_packed, st, path, nullptr, 0u, dn, range_space ? h->d_scratch[slot] : nullptr);
     if (rc == QPB_SUCCESS && h_swing) rc = launch_swing(h, m, h->d_in[slot], h->d_sw[slot], h->d_out[slot], st);
     if (rc != QPB_SUCCESS) break;
-    if (h->trace) cudaEventRecord(tr.ev[2], st);
+    if (!wire || h_swing) ce = cudaEventRecord(h->ev_in_free[slot], st);
+    if (ce != cudaSuccess) break;
     if (wire) {
       qpb::wire_pack_kernel<<<(unsigned)((m * qpb::kWireOutWords + 255) / 256), 256, 0, st>>>(
           reinterpret_cast<const uint64_t*>(h->d_out[slot]), reinterpret_cast<uint64_t*>(h->d_wout[slot]), m);
       h->launches.fetch_add(1, std::memory_order_relaxed);
       ce = cudaGetLastError();
-      if (ce == cudaSuccess) ce = cudaMemcpyAsync(w_out + lo, h->d_wout[slot], m * sizeof(qpb_wire_out), cudaMemcpyDeviceToHost, st);
-    } else {
-      ce = cudaMemcpyAsync(h_out + lo, h->d_out[slot], m * sizeof(qpb_out_rec), cudaMemcpyDeviceToHost, st);
+      if (ce != cudaSuccess) break;
     }
+    ce = cudaEventRecord(h->ev_solved[slot], st);
+    if (ce != cudaSuccess) break;
+    if (h->trace) cudaEventRecord(tr.ev[2], st);
+    // download
+    ce = cudaStreamWaitEvent(down, h->ev_solved[slot], 0);
+    if (ce != cudaSuccess) break;
+    if (wire)
+      ce = cudaMemcpyAsync(w_out + lo, h->d_wout[slot], m * sizeof(qpb_wire_out), cudaMemcpyDeviceToHost, down);
+    else
+      ce = cudaMemcpyAsync(h_out + lo, h->d_out[slot], m * sizeof(qpb_out_rec), cudaMemcpyDeviceToHost, down);
+    if (ce == cudaSuccess) ce = cudaEventRecord(h->ev_down[slot], down);
     if (h->trace) {
-      cudaEventRecord(tr.ev[3], st);
+      cudaEventRecord(tr.ev[3], down);
       h->trace_stages.push_back(tr);
     }
   }
@@ -600,6 +634,10 @@ int qpb_create(const qpb_params* params, int device, qpb_handle** out) {
   if (const char* env = std::getenv("QPB_ZEROCOPY")) h->zero_copy = std::atoi(env);
   if (const char* env = std::getenv("QPB_SMALL_POLL")) h->small_poll = std::atoi(env);
   if (const char* env = std::getenv("QPB_HOST_TRACE")) h->trace = std::atoi(env);
+  if (const char* env = std::getenv("QPB_HOST_CSTREAMS")) {
+    const int v = std::atoi(env);
+    if (v >= 1 && v <= kHostSlots) h->host_cstreams = v;
+  }
   if (const char* env = std::getenv("QPB_HOST_STAGES")) {
     const int v = std::atoi(env);
     if (v >= 1 && v <= 64) h->host_stages = v;
@@ -617,6 +655,8 @@ int qpb_destroy(qpb_handle* h) {
   DeviceGuard guard(h->device);
   for (int s = 0; s < kHostSlots; s++) {
     if (h->streams[s]) cudaStreamDestroy(h->streams[s]);
+    for (cudaEvent_t e : { h->ev_up[s], h->ev_in_free[s], h->ev_solved[s], h->ev_down[s] })
+      if (e) cudaEventDestroy(e);
     if (h->d_in[s]) cudaFree(h->d_in[s]);
     if (h->d_out[s]) cudaFree(h->d_out[s]);
     if (h->d_sw[s]) cudaFree(h->d_sw[s]);
@@ -624,6 +664,8 @@ int qpb_destroy(qpb_handle* h) {
     if (h->d_win[s]) cudaFree(h->d_win[s]);
     if (h->d_wout[s]) cudaFree(h->d_wout[s]);
   }
+  if (h->up_stream) cudaStreamDestroy(h->up_stream);
+  if (h->down_stream) cudaStreamDestroy(h->down_stream);
   if (h->d_params) cudaFree(h->d_params);
   if (h->d_tickets) cudaFree(h->d_tickets);
   if (h->d_gains) cudaFree(h->d_gains);
