@@ -172,35 +172,43 @@ int launch_balance(qpb_handle* h, const IO& io, int64_t n, int ctas_per_sm, cuda
     // Three passes over scratch memory (qpb_tpq.cuh): set-up -> prepared records, the active-set loop, polish + epilogue.
     // The scratch comes from the stream-ordered allocator, so concurrent calls on different streams never share it.
     const int lpq = h->tpq_lpq;
-    for (int64_t lo = 0; lo < n; lo += kTpqChunk) {
-      const int64_t m = n - lo < kTpqChunk ? n - lo : kTpqChunk;
-      const IO part = offset_io(io, lo);
-      double* prep = scratch;  // m prepared records, m result words, the worklist of the loop pass (m record indices)
-      const size_t prep_bytes = (size_t)m * qpb::tpq::kPrepSize * sizeof(double);
-      if (!scratch)  // (the host pipeline brings its own: one block per stage slot, n <= kHostChunkMax)
-        QPB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&prep), prep_bytes + (size_t)m * (sizeof(double) + sizeof(uint32_t)), stream));
-      double* res = prep + (size_t)m * qpb::tpq::kPrepSize;
-      uint32_t* work = reinterpret_cast<uint32_t*>(res + m);
-      const uint32_t slot2 = lo == 0 ? slot : h->ticket_slot.fetch_add(1, std::memory_order_relaxed) % kTicketSlots;
-      unsigned long long* tk = h->d_tickets + 4 * (size_t)slot2;
-      const unsigned edge = (unsigned)((m + qpb::tpq::kEdgeThreads - 1) / qpb::tpq::kEdgeThreads);
-      qpb::tpq::tpq_setup_kernel<IO><<<edge, qpb::tpq::kEdgeThreads, 0, stream>>>(h->edge, h->fast, part, m, prep, res, work, tk);
-      const int lthreads = lpq == 1 ? qpb::tpq::LoopShape<1>::THREADS : (lpq == 2 ? qpb::tpq::LoopShape<2>::THREADS : qpb::tpq::LoopShape<4>::THREADS);
-      const int64_t want = (m * lpq + lthreads - 1) / lthreads;
-      const int64_t cap = (int64_t)h->num_sms * h->ctas_per_sm_tpq[lpq];
-      const int grid = (int)(want < cap ? want : cap);
-      if (lpq == 1)
-        qpb::tpq::tpq_loop_kernel<1><<<grid, lthreads, 0, stream>>>(h->fast, prep, res, work, tk);
-      else if (lpq == 2)
-        qpb::tpq::tpq_loop_kernel<2><<<grid, lthreads, 0, stream>>>(h->fast, prep, res, work, tk);
-      else
-        qpb::tpq::tpq_loop_kernel<4><<<grid, lthreads, 0, stream>>>(h->fast, prep, res, work, tk);
-      qpb::tpq::tpq_finish_kernel<IO><<<edge, qpb::tpq::kEdgeThreads, 0, stream>>>(h->edge, h->fast, part, m, prep, res);
-      h->launches.fetch_add(3, std::memory_order_relaxed);
-      QPB_CUDA(cudaGetLastError());
-      if (!scratch) QPB_CUDA(cudaFreeAsync(prep, stream));
-    }
-    return QPB_SUCCESS;
+    bool first_chain = true;
+    // one chain of three launches per at most 2^20 records of [lo0, lo0 + n0), on stream s
+    auto run_chain = [&](int64_t lo0, int64_t n0, cudaStream_t s) -> int {
+      for (int64_t lo = lo0; lo < lo0 + n0; lo += kTpqChunk) {
+        const int64_t m = lo0 + n0 - lo < kTpqChunk ? lo0 + n0 - lo : kTpqChunk;
+        const IO part = offset_io(io, lo);
+        double* prep = scratch;  // m prepared records, m result words, the worklist of the loop pass (m record indices)
+        const size_t prep_bytes = (size_t)m * qpb::tpq::kPrepSize * sizeof(double);
+        if (!scratch)  // (the host pipeline brings its own: one block per stage slot, n <= kHostChunkMax)
+          QPB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&prep), prep_bytes + (size_t)m * (sizeof(double) + sizeof(uint32_t)), s));
+        double* res = prep + (size_t)m * qpb::tpq::kPrepSize;
+        uint32_t* work = reinterpret_cast<uint32_t*>(res + m);
+        const uint32_t slot2 = first_chain ? slot : h->ticket_slot.fetch_add(1, std::memory_order_relaxed) % kTicketSlots;
+        first_chain = false;
+        unsigned long long* tk = h->d_tickets + 4 * (size_t)slot2;
+        const unsigned edge = (unsigned)((m + qpb::tpq::kEdgeThreads - 1) / qpb::tpq::kEdgeThreads);
+        qpb::tpq::tpq_setup_kernel<IO><<<edge, qpb::tpq::kEdgeThreads, 0, s>>>(h->edge, h->fast, part, m, prep, res, work, tk);
+        const int lthreads = lpq == 1 ? qpb::tpq::LoopShape<1>::THREADS : (lpq == 2 ? qpb::tpq::LoopShape<2>::THREADS : qpb::tpq::LoopShape<4>::THREADS);
+        const int64_t want = (m * lpq + lthreads - 1) / lthreads;
+        const int64_t cap = (int64_t)h->num_sms * h->ctas_per_sm_tpq[lpq];
+        const int grid = (int)(want < cap ? want : cap);
+        if (lpq == 1)
+          qpb::tpq::tpq_loop_kernel<1><<<grid, lthreads, 0, s>>>(h->fast, prep, res, work, tk);
+        else if (lpq == 2)
+          qpb::tpq::tpq_loop_kernel<2><<<grid, lthreads, 0, s>>>(h->fast, prep, res, work, tk);
+        else
+          qpb::tpq::tpq_loop_kernel<4><<<grid, lthreads, 0, s>>>(h->fast, prep, res, work, tk);
+        qpb::tpq::tpq_finish_kernel<IO><<<edge, qpb::tpq::kEdgeThreads, 0, s>>>(h->edge, h->fast, part, m, prep, res);
+        h->launches.fetch_add(3, std::memory_order_relaxed);
+        QPB_CUDA(cudaGetLastError());
+        if (!scratch) QPB_CUDA(cudaFreeAsync(prep, s));
+      }
+      return QPB_SUCCESS;
+    };
+    // (Cutting a large batch into parts whose chains run side by side on helper streams was measured and dropped: +1 % with
+    // two parts on config 2, a loss everywhere else -- profiles/r02_split_ab.txt.)
+    return run_chain(0, n, stream);
   }
   if (per_warp == 32 && (force_path ? force_path == 33 : n <= h->tpq_one_max)) {
     // small batches: set-up, loop and finish in one launch, a warp per record while there are warps to go round

@@ -204,6 +204,37 @@ def test_wire_records_give_the_same_results(built, params06):
     solver.close()
 
 
+def test_cuda_graph_replay(built, params06):
+    """qpb_control_batch_packed is capturable: the work tickets re-arm themselves and the scratch comes from the
+    stream-ordered allocator.  One captured call, replayed on fresh inputs, must give what direct calls give -- for the
+    one-launch kernels and for the three-pass path."""
+    torch = _torch()
+    for n in (3000, 70000):
+        S = [states.generate_states(n, 500 + k, masks="mixed") for k in range(3)]
+        solver = lib.BalanceSolver(params06)
+        d_in = torch.from_numpy(S[0].view(np.uint8).reshape(-1).copy()).cuda()
+        d_out = torch.zeros(n * 256, dtype=torch.uint8, device="cuda")
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            solver.control_packed(d_in, d_out, n, side.cuda_stream)  # warm-up outside the capture
+        side.synchronize()
+        want = [solver.control_host(s) for s in S]
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            solver.control_packed(d_in, d_out, n, side.cuda_stream)
+        for rep in range(2):
+            for k in range(3):
+                d_in.copy_(torch.from_numpy(S[k].view(np.uint8).reshape(-1).copy()).cuda())
+                d_out.zero_()
+                graph.replay()
+                torch.cuda.synchronize()
+                got = d_out.cpu().numpy().view(OUT_DTYPE)
+                assert got.tobytes() == want[k].tobytes(), (n, rep, k)
+        del graph
+        solver.close()
+
+
 def test_three_entry_points_agree(solver06, params06):
     torch = _torch()
     S = states.generate_states(5001, 4, masks="mixed")  # not a multiple of the CTA size
