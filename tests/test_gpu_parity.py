@@ -600,6 +600,60 @@ def test_warm_start_across_ticks(built, params06):
     solver.close()
 
 
+def test_thousand_tick_trajectory_warm_equals_cold(built, params06, monkeypatch):
+    """A batch of robots followed over 1 000 ticks of a 1 kHz loop, every tick warm-started from the previous one's working
+    set: a slow sway of the commanded pose, velocity noise, a push every 250 ticks and a foot lifted for 100 ticks out of 300
+    (so working sets do go stale).  Every tick must equal the cold solve of the same records to 1e-8 (measured worst
+    2.2e-9: two fresh 6x6 solves on faces that differ by a degenerate row, cond(G) up to 1e6), the worst tick is also
+    checked against the oracle, and the mean number of working-set changes per tick must stay below 2 (cold: about 7)."""
+    rng = np.random.default_rng(5)
+    n = 512
+    S = states.generate_states(n, 4242)
+    base = S.copy()
+    warm_solver = lib.BalanceSolver(params06)
+    monkeypatch.setenv("QPB_TPQ_ONE_MAX", str(1 << 30))  # the cold solves through the same range-space kernel
+    cold_solver = lib.BalanceSolver(params06)
+    monkeypatch.delenv("QPB_TPQ_ONE_MAX")
+    word = np.zeros((n, 4), dtype=np.uint8)
+    warm_iters, cold_iters, worst, worst_case = [], [], -1.0, None
+    for tick in range(1000):
+        t = tick * 1e-3
+        S["x_d"] = base["x_d"] + 0.02 * np.sin(2 * np.pi * 1.5 * t + np.arange(n)[:, None] * 0.01)
+        S["xdot"] = base["xdot"] + rng.normal(0, 2e-3, (n, 3))
+        S["w"] = base["w"] + rng.normal(0, 2e-3, (n, 3))
+        if tick % 250 == 249:  # a push
+            base["xdot"] += rng.normal(0, 0.2, (n, 3))
+        lifted = (np.arange(n) + tick // 300) % 4  # which foot this robot lifts during the swing window
+        S["contact"][:] = 1
+        if tick % 300 >= 200:
+            S["contact"][np.arange(n), lifted] = 0
+        S["pad"][:, :4] = word
+        warm = warm_solver.control_host(S)
+        C = S.copy()
+        C["pad"][:] = 0
+        cold = cold_solver.control_host(C)
+        assert np.array_equal(warm["status"], cold["status"]), tick
+        e = max(rel_err(warm["grf_body"], cold["grf_body"]), rel_err(warm["tau"], cold["tau"]))
+        if e > worst:
+            worst, worst_case = e, (tick, C.copy(), warm.copy(), cold.copy())
+        ok = cold["status"] == 0
+        warm_iters.append(warm["iters"][ok].mean())
+        cold_iters.append(cold["iters"][ok].mean())
+        word = warm["pad"][:, :4].copy()
+    tick_w, C_w, warm_w, cold_w = worst_case
+    ref_w = oracle.control_batch(params06, C_w, NCPU)
+    print(f"1000 ticks x {n} robots: working-set changes per tick warm {np.mean(warm_iters):.2f} cold {np.mean(cold_iters):.2f}, "
+          f"worst warm-vs-cold {worst:.1e} at tick {tick_w}: warm vs oracle {rel_err(warm_w['grf_body'], ref_w['grf_body']):.1e}, "
+          f"cold vs oracle {rel_err(cold_w['grf_body'], ref_w['grf_body']):.1e}")
+    assert worst <= 1e-8, worst
+    _compare(warm_w, ref_w)
+    assert np.mean(warm_iters) <= 2.0 and np.mean(cold_iters) >= 4.0, (np.mean(warm_iters), np.mean(cold_iters))
+    ref = oracle.control_batch(params06, C, NCPU)  # the last tick against the oracle
+    _compare(warm, ref)
+    warm_solver.close()
+    cold_solver.close()
+
+
 def test_cuda_path_against_the_reference_sources_directly(built, params06):
     """The CUDA results compared with oracle/_ref -- the reference's OWN balance_controller.cpp + kinematics.cpp compiled
     from /root/reference against stand-in third-party headers -- without the plain-C port in between: the whole of

@@ -6,7 +6,7 @@ from quadruped_control_b200 import default_params, states, lib
 trials = int(sys.argv[1]) if len(sys.argv) > 1 else 40
 nper = int(sys.argv[2]) if len(sys.argv) > 2 else 2048
 rng = np.random.default_rng(int(sys.argv[3]) if len(sys.argv) > 3 else 2026)
-worst = 0.0; fails = 0; ncpu = os.cpu_count() or 1
+worst = 0.0; worst_desc = ''; fails = 0; ncpu = os.cpu_count() or 1
 for t in range(trials):
     p = default_params(float(np.exp(rng.uniform(np.log(0.02), np.log(3.0)))))
     p.mass = float(rng.uniform(2.0, 80.0))
@@ -30,19 +30,34 @@ for t in range(trials):
     if rng.random() < 0.3:
         Sin["x_d"][:, 2] -= rng.uniform(0, 0.5, nper)
     ref = oracle.control_batch(p, Sin, ncpu)
-    for mode in ("auto", "2", "1"):  # auto: thread-per-QP kernel when W = w I and fzmin >= 0, else the half-warp kernel
-        if mode == "auto":
-            os.environ.pop("QPB_QPS_PER_WARP", None)
-        else:
+    # auto: the dispatch as shipped; three / one: the three-pass and the one-launch range-space paths forced at this size
+    # (they apply when W = w I and fzmin >= 0, else the half-warp kernel runs); warm: the same records carrying the
+    # working sets the previous mode returned; 2 / 1: half-warp and one-warp kernels
+    prev = None
+    for mode in ("auto", "three", "one", "warm", "2", "1"):
+        for k in ("QPB_QPS_PER_WARP", "QPB_TPQ_MIN_N", "QPB_TPQ_ONE_MAX"):
+            os.environ.pop(k, None)
+        if mode in ("2", "1"):
             os.environ["QPB_QPS_PER_WARP"] = mode
-        sol = lib.BalanceSolver(p); out = sol.control_host(Sin); sol.close()
+        elif mode == "three":
+            os.environ["QPB_TPQ_MIN_N"] = "0"
+        elif mode == "one":
+            os.environ["QPB_TPQ_MIN_N"] = str(1 << 31); os.environ["QPB_TPQ_ONE_MAX"] = str(1 << 30)
+        X = Sin
+        if mode == "warm":
+            X = Sin.copy(); X["pad"][:, :4] = prev["pad"][:, :4]
+        sol = lib.BalanceSolver(p); out = sol.control_host(X); sol.close()
+        prev = out
         mism = int((out["status"] != ref["status"]).sum())
         ok = (out["status"] == 0) & (ref["status"] == 0)
         err = float((np.abs(out["grf_body"][ok] - ref["grf_body"][ok]).max(axis=1) / np.maximum(np.abs(ref["grf_body"][ok]).max(axis=1), 1)).max()) if ok.any() else 0.0
         errt = float((np.abs(out["tau"][ok] - ref["tau"][ok]).max(axis=1) / np.maximum(np.abs(ref["tau"][ok]).max(axis=1), 1)).max()) if ok.any() else 0.0
-        worst = max(worst, err, errt)
+        if max(err, errt) > worst:
+            worst = max(err, errt)
+            worst_desc = f"trial {t} mode {mode}: mu={p.mu:.3g} mass={p.mass:.3g} fz=[{p.fzmin:.3g},{p.fzmax:.3g}] w={w:.2e} sS={sS} sW={sW} {prof}/{masks} err {err:.2e} {errt:.2e}"
         if mism or err > 1e-5 or errt > 1e-5:
             fails += 1
             print(f"FAIL trial {t} mode {mode}: mu={p.mu:.3g} mass={p.mass:.3g} fz=[{p.fzmin:.3g},{p.fzmax:.3g}] w={w:.2e} sS={sS} sW={sW} {prof}/{masks} "
                   f"status mism {mism} (gpu {np.bincount(out['status'], minlength=3)}, ref {np.bincount(ref['status'], minlength=3)}) err {err:.2e} {errt:.2e} iters max {out['iters'].max()}")
-print(f"fuzz: {trials} parameter sets x {nper} states x 3 kernel choices, failures {fails}, worst rel err {worst:.2e}")
+print("worst case:", worst_desc)
+print(f"fuzz: {trials} parameter sets x {nper} states x 6 kernel choices, failures {fails}, worst rel err {worst:.2e}")
