@@ -358,7 +358,7 @@ def secondary_block(solver, params, rank, world, local_rank, dev, dist, barrier)
         out[name] = entry
         del d_in, d_out, S
     # cfg2 as a controller sees it in its loop: every record carries the working set its previous tick ended on (the
-    # reference's hotstart), the states have moved by 1 ms of a 1 kHz loop since.  One launch (tpq_one_kernel).
+    # reference's hotstart), the states have moved by 1 ms of a 1 kHz loop since.  One launch (tpq_one_kernel) at this size.
     n, seed, masks, profile, desc = WORKLOADS["cfg2"]
     S = states.generate_states(n, seed, lo=rank * n, profile=profile, masks=masks)
     d_in = torch.from_numpy(S.view(np.uint8).reshape(-1)).to(dev)

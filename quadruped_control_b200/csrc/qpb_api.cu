@@ -87,7 +87,8 @@ struct qpb_handle {
   int64_t tpq_min_n = 12288;    // smaller batches take a one-launch kernel: lower latency (QPB_TPQ_MIN_N)
   int64_t tpq_one_max = 1;      // ... up to here the range-space one (tpq_one_kernel), above it the half-warp kernel (QPB_TPQ_ONE_MAX)
   int warm_batches = 0;         // device-resident calls: the records carry warm-start words (qpb_set_warm_batches)
-  int64_t tpq_warm_one_max = (int64_t)1 << 40;  // warm batches up to this size take tpq_one_kernel (QPB_TPQ_WARM_ONE_MAX)
+  int64_t tpq_warm_defer_min = 196608;  // warm batches below this size take tpq_one_kernel, larger ones the three passes
+                                        // with early finish (QPB_TPQ_WARM_DEFER_MIN; profiles/r02_warm_sizes.txt)
   qpb::tpq::FastParams fast;
   qpb::tpq::EdgeParams edge;  // the slice of params the set-up / finishing passes take by value
   qpb_params params;
@@ -166,14 +167,19 @@ int launch_balance(qpb_handle* h, const IO& io, int64_t n, int ctas_per_sm, cuda
   unsigned long long* t0 = h->d_tickets + 4 * (size_t)slot;  // {work ticket, CTAs finished, worklist entries, -}
   // A warm batch (records carrying last tick's working sets) is at its optimum after the set-up's first solve almost
   // always, so the one-launch kernel wins at every size: no scratch, no second and third pass.
+  // Warm batches: one launch (33) up to ~200 000 records.  Larger ones: three passes in which the set-up finishes the
+  // records that are optimal at once and the loop and finishing passes only see the rest (34) -- in one launch nearly
+  // every warp holds at least one record that needs the loop and waits for it, which costs more than two extra
+  // launches once the batch is large (1 048 576 records one tick later: 438 us against 520 us; 65 536: 65 against 52).
   if (per_warp == 32 && !force_path && h->warm_batches && std::is_same<IO, qpb::PackedIO>::value)
-    force_path = n <= h->tpq_warm_one_max ? 33 : 32;
-  if (per_warp == 32 && (force_path ? force_path == 32 : n >= h->tpq_min_n)) {
+    force_path = n < h->tpq_warm_defer_min ? 33 : 34;
+  if (per_warp == 32 && (force_path ? (force_path == 32 || force_path == 34) : n >= h->tpq_min_n)) {
     // Three passes over scratch memory (qpb_tpq.cuh): set-up -> prepared records, the active-set loop, polish + epilogue.
     // The scratch comes from the stream-ordered allocator, so concurrent calls on different streams never share it.
     const int lpq = h->tpq_lpq;
     bool first_chain = true;
     // one chain of three launches per at most 2^20 records of [lo0, lo0 + n0), on stream s
+    const bool early = force_path == 34;  // warm batch: records optimal after the set-up are finished there
     auto run_chain = [&](int64_t lo0, int64_t n0, cudaStream_t s) -> int {
       for (int64_t lo = lo0; lo < lo0 + n0; lo += kTpqChunk) {
         const int64_t m = lo0 + n0 - lo < kTpqChunk ? lo0 + n0 - lo : kTpqChunk;
@@ -188,7 +194,10 @@ int launch_balance(qpb_handle* h, const IO& io, int64_t n, int ctas_per_sm, cuda
         first_chain = false;
         unsigned long long* tk = h->d_tickets + 4 * (size_t)slot2;
         const unsigned edge = (unsigned)((m + qpb::tpq::kEdgeThreads - 1) / qpb::tpq::kEdgeThreads);
-        qpb::tpq::tpq_setup_kernel<IO><<<edge, qpb::tpq::kEdgeThreads, 0, s>>>(h->edge, h->fast, part, m, prep, res, work, tk);
+        if (early)
+          qpb::tpq::tpq_setup_kernel<IO, true><<<edge, qpb::tpq::kEdgeThreads, 0, s>>>(h->edge, h->fast, part, m, prep, res, work, tk);
+        else
+          qpb::tpq::tpq_setup_kernel<IO, false><<<edge, qpb::tpq::kEdgeThreads, 0, s>>>(h->edge, h->fast, part, m, prep, res, work, tk);
         const int lthreads = lpq == 1 ? qpb::tpq::LoopShape<1>::THREADS : (lpq == 2 ? qpb::tpq::LoopShape<2>::THREADS : qpb::tpq::LoopShape<4>::THREADS);
         const int64_t want = (m * lpq + lthreads - 1) / lthreads;
         const int64_t cap = (int64_t)h->num_sms * h->ctas_per_sm_tpq[lpq];
@@ -199,7 +208,10 @@ int launch_balance(qpb_handle* h, const IO& io, int64_t n, int ctas_per_sm, cuda
           qpb::tpq::tpq_loop_kernel<2><<<grid, lthreads, 0, s>>>(h->fast, prep, res, work, tk);
         else
           qpb::tpq::tpq_loop_kernel<4><<<grid, lthreads, 0, s>>>(h->fast, prep, res, work, tk);
-        qpb::tpq::tpq_finish_kernel<IO><<<edge, qpb::tpq::kEdgeThreads, 0, s>>>(h->edge, h->fast, part, m, prep, res);
+        if (early)
+          qpb::tpq::tpq_finish_kernel<IO, true><<<edge, qpb::tpq::kEdgeThreads, 0, s>>>(h->edge, h->fast, part, m, prep, res, work, tk);
+        else
+          qpb::tpq::tpq_finish_kernel<IO, false><<<edge, qpb::tpq::kEdgeThreads, 0, s>>>(h->edge, h->fast, part, m, prep, res, work, tk);
         h->launches.fetch_add(3, std::memory_order_relaxed);
         QPB_CUDA(cudaGetLastError());
         if (!scratch) QPB_CUDA(cudaFreeAsync(prep, s));
@@ -315,8 +327,8 @@ int host_pipeline(qpb_handle* h, int64_t n, const qpb_state_rec* h_states, const
   const int64_t dn = whole_n >= 0 ? whole_n : n;
   const bool hinted = whole_warm >= 0 ? whole_warm != 0 : (wire ? (w_in[0].warm >> 31) != 0u : (h_states[0].pad[3] & 0x80u) != 0);
   const bool warm = h->qps_per_warp == 32 && (h->warm_batches || hinted);
-  const bool range_space = h->qps_per_warp == 32 && (warm ? dn > h->tpq_warm_one_max : dn >= h->tpq_min_n);
-  const int path = range_space ? 32 : (h->qps_per_warp == 32 ? ((warm || dn <= h->tpq_one_max) ? 33 : 2) : h->qps_per_warp);
+  const bool range_space = h->qps_per_warp == 32 && (warm ? dn >= h->tpq_warm_defer_min : dn >= h->tpq_min_n);
+  const int path = range_space ? (warm ? 34 : 32) : (h->qps_per_warp == 32 ? ((warm || dn <= h->tpq_one_max) ? 33 : 2) : h->qps_per_warp);
   if (!async && h->zero_copy && n <= kSmallCall) {
     // Latency path for per-tick callers: stage through the handle's pinned block, kernels work on its device alias.
     const int rc0 = ensure_small(h);
@@ -631,9 +643,9 @@ int qpb_create(const qpb_params* params, int device, qpb_handle** out) {
     const long long v = std::atoll(env);
     if (v >= 0) h->tpq_min_n = v;
   }
-  if (const char* env = std::getenv("QPB_TPQ_WARM_ONE_MAX")) {
+  if (const char* env = std::getenv("QPB_TPQ_WARM_DEFER_MIN")) {
     const long long v = std::atoll(env);
-    if (v >= 0) h->tpq_warm_one_max = v;
+    if (v >= 0) h->tpq_warm_defer_min = v;
   }
   if (const char* env = std::getenv("QPB_TPQ_ONE_MAX")) {
     const long long v = std::atoll(env);

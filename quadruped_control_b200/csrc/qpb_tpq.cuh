@@ -198,7 +198,11 @@ struct PrepCommit {
   }
 };
 
-template <class IO>
+// EARLY (warm batches): a record whose starting pair is already optimal -- nearly all of them when the records carry last
+// tick's working sets -- is finished right here (its forces ARE the minimiser on the final faces from one fresh solve):
+// epilogue, result record, no scratch traffic; only the others get a prepared record and a place in the worklist, and
+// the finishing pass then walks the worklist instead of the batch (tpq_finish_kernel<IO, true>).
+template <class IO, bool EARLY>
 __global__ void __launch_bounds__(kEdgeThreads, QPB_TPQ_EDGE_MINCTAS)
 tpq_setup_kernel(const __grid_constant__ EdgeParams P, const __grid_constant__ FastParams K, IO io, int64_t n, double* __restrict__ prep,
                  double* __restrict__ res, uint32_t* __restrict__ work, unsigned long long* __restrict__ ticket) {
@@ -212,14 +216,28 @@ tpq_setup_kernel(const __grid_constant__ EdgeParams P, const __grid_constant__ F
     double b6[6], G[21];
     PrepCommit commit{ prep + rec * kPrepSize, 0u, 0.0 };
     setup(P, K, v, cbytes, hint, st, b6, G, commit);
-    // what does not depend on the working set: lever arms and the right-hand side (after a non-finite input they are zero)
-    double2* o = reinterpret_cast<double2*>(commit.e);
-#pragma unroll
-    for (int i = 0; i < 6; i++) o[kPrepR / 2 + i] = make_double2(st.r[2 * i], st.r[2 * i + 1]);
-#pragma unroll
-    for (int i = 0; i < 3; i++) o[kPrepB / 2 + i] = make_double2(b6[2 * i], b6[2 * i + 1]);
-    res[rec] = commit.meta;  // the result word: final as it stands unless the loop pass takes the record
     need = commit.key != 0u;
+    if (EARLY && !need) {
+      // (the pair committed last is the one st holds: start() stops at the first optimal pair)
+      double q[12], grf[12], tau[12];
+      bool qfin = true;
+#pragma unroll
+      for (int i = 0; i < 12; i++) {
+        q[i] = tpq_q(io, rec, v, i);
+        qfin = qfin && (fabs(q[i]) <= 1.79769313486231570e308);
+      }
+      if (!qfin && st.status == QPB_OK) st.status = QPB_BAD_INPUT;
+      finish(P, v + kR, q, st, grf, tau);
+      tpq_store(io, rec, grf, tau, st.status, st.iters, st.word | 0x80000000u);
+    } else {
+      // what does not depend on the working set: lever arms and the right-hand side (after a non-finite input they are zero)
+      double2* o = reinterpret_cast<double2*>(commit.e);
+#pragma unroll
+      for (int i = 0; i < 6; i++) o[kPrepR / 2 + i] = make_double2(st.r[2 * i], st.r[2 * i + 1]);
+#pragma unroll
+      for (int i = 0; i < 3; i++) o[kPrepB / 2 + i] = make_double2(b6[2 * i], b6[2 * i + 1]);
+      res[rec] = commit.meta;  // the result word: final as it stands unless the loop pass takes the record
+    }
   }
   // worklist of the loop pass: one atomic per warp (ticket[2] counts the entries; the loop's last CTA re-arms it)
   const uint32_t m = __ballot_sync(FULL, need);
@@ -360,6 +378,7 @@ tpq_loop_kernel(const __grid_constant__ FastParams K, const double* __restrict__
   if (threadIdx.x == 0) {
     __threadfence();
     if (atomicAdd(ticket + 1, 1ULL) == (unsigned long long)gridDim.x - 1ULL) {
+      ticket[3] = (unsigned long long)n;  // for a finishing pass that walks the worklist
       ticket[0] = 0ULL;
       ticket[1] = 0ULL;
       ticket[2] = 0ULL;  // the worklist counter the set-up pass filled
@@ -369,12 +388,20 @@ tpq_loop_kernel(const __grid_constant__ FastParams K, const double* __restrict__
 }
 
 // ---- pass 3: polish + epilogue, one thread per record -------------------------------------------------------------------
-template <class IO>
+// LIST: only the records of the worklist (ticket[3] entries, published by the loop pass) -- the others were finished by
+// tpq_setup_kernel<IO, true>.
+template <class IO, bool LIST>
 __global__ void __launch_bounds__(kEdgeThreads, QPB_TPQ_FINISH_MINCTAS)
 tpq_finish_kernel(const __grid_constant__ EdgeParams P, const __grid_constant__ FastParams K, IO io, int64_t n,
-                  const double* __restrict__ prep, const double* __restrict__ res) {
-  const int64_t rec = (int64_t)blockIdx.x * kEdgeThreads + threadIdx.x;
-  if (rec >= n) return;
+                  const double* __restrict__ prep, const double* __restrict__ res, const uint32_t* __restrict__ work,
+                  const unsigned long long* __restrict__ ticket) {
+  int64_t rec = (int64_t)blockIdx.x * kEdgeThreads + threadIdx.x;
+  if (LIST) {
+    if (rec >= (int64_t)__ldg(ticket + 3)) return;
+    rec = (int64_t)__ldg(work + rec);
+  } else if (rec >= n) {
+    return;
+  }
   const double* e = prep + rec * kPrepSize;
   State st;
   double b6[6];

@@ -138,40 +138,48 @@ def test_one_launch_range_space_kernel(built, params06, monkeypatch):
     one.close()
 
 
-def test_warm_batches_flag_on_device_calls(built, params06):
-    """qpb_set_warm_batches: device-resident records that carry last tick's working sets take the one-launch kernel at any
-    size (the host entry points find out by looking at the first record; a device pointer cannot be looked at)."""
+def test_warm_batches_flag_on_device_calls(built, params06, monkeypatch):
+    """qpb_set_warm_batches: device-resident records that carry last tick's working sets take the warm path at any size
+    (the host entry points find out by looking at the first record; a device pointer cannot be looked at) -- one launch
+    for small batches, for large ones (196 608 records by default, 16 384 here) three passes in which the set-up finishes
+    the records that are optimal at once."""
     torch = _torch()
-    n = 40000
-    S = states.generate_states(n, 99, masks="mixed")
-    solver = lib.BalanceSolver(params06)
-    d_in = torch.from_numpy(S.view(np.uint8).reshape(-1).copy()).cuda()
-    d_out = torch.zeros(n * 256, dtype=torch.uint8, device="cuda")
-    l0 = solver.launches
-    solver.control_packed(d_in, d_out, n)
-    torch.cuda.synchronize()
-    assert solver.launches - l0 == 3  # cold: set-up, loop, finish
-    cold = d_out.cpu().numpy().view(OUT_DTYPE).copy()
-    W = S.copy()
-    W["pad"][:, :4] = cold["pad"][:, :4]
-    d_in = torch.from_numpy(W.view(np.uint8).reshape(-1).copy()).cuda()
-    solver.set_warm_batches(True)
-    l0 = solver.launches
-    solver.control_packed(d_in, d_out, n)
-    torch.cuda.synchronize()
-    assert solver.launches - l0 == 1
-    warm = d_out.cpu().numpy().view(OUT_DTYPE).copy()
-    assert np.array_equal(warm["status"], cold["status"]) and warm["iters"].mean() <= 0.02
-    assert rel_err(warm["grf_body"], cold["grf_body"]) <= 1e-9 and rel_err(warm["tau"], cold["tau"]) <= 1e-9
-    # records without a word are still solved, from a cold start
-    d_in = torch.from_numpy(S.view(np.uint8).reshape(-1).copy()).cuda()
-    solver.control_packed(d_in, d_out, n)
-    torch.cuda.synchronize()
-    again = d_out.cpu().numpy().view(OUT_DTYPE).copy()
-    assert np.array_equal(again["status"], cold["status"]) and np.array_equal(again["iters"], cold["iters"])
-    assert rel_err(again["grf_body"], cold["grf_body"]) <= 1e-9
-    solver.set_warm_batches(False)
-    solver.close()
+    monkeypatch.setenv("QPB_TPQ_WARM_DEFER_MIN", "16384")
+    for n, cold_launches, warm_launches in ((8000, 1, 1), (40000, 3, 3)):
+        S = states.generate_states(n, 99, masks="mixed")
+        S["x"][3, 1] = np.nan
+        solver = lib.BalanceSolver(params06)
+        d_in = torch.from_numpy(S.view(np.uint8).reshape(-1).copy()).cuda()
+        d_out = torch.zeros(n * 256, dtype=torch.uint8, device="cuda")
+        l0 = solver.launches
+        solver.control_packed(d_in, d_out, n)
+        torch.cuda.synchronize()
+        assert solver.launches - l0 == cold_launches
+        cold = d_out.cpu().numpy().view(OUT_DTYPE).copy()
+        W = S.copy()
+        W["pad"][:, :4] = cold["pad"][:, :4]
+        W["xdot"] += np.random.default_rng(1).normal(0, 2e-3, W["xdot"].shape)  # one tick later: some working sets are stale
+        ref = oracle.control_batch(params06, W, NCPU)
+        d_in = torch.from_numpy(W.view(np.uint8).reshape(-1).copy()).cuda()
+        solver.set_warm_batches(True)
+        l0 = solver.launches
+        d_out.zero_()
+        solver.control_packed(d_in, d_out, n)
+        torch.cuda.synchronize()
+        assert solver.launches - l0 == warm_launches
+        warm = d_out.cpu().numpy().view(OUT_DTYPE).copy()
+        _compare(warm, ref)
+        assert warm["status"][3] == 2 and 0 < warm["iters"].mean() <= 0.5
+        assert solver.control_host(W).tobytes() == warm.tobytes()  # the host call takes the same kernels
+        # records without a word are still solved, from a cold start
+        d_in = torch.from_numpy(S.view(np.uint8).reshape(-1).copy()).cuda()
+        solver.control_packed(d_in, d_out, n)
+        torch.cuda.synchronize()
+        again = d_out.cpu().numpy().view(OUT_DTYPE).copy()
+        assert np.array_equal(again["status"], cold["status"])
+        assert rel_err(again["grf_body"], cold["grf_body"]) <= 1e-7
+        solver.set_warm_batches(False)
+        solver.close()
 
 
 def test_wire_records_give_the_same_results(built, params06):

@@ -7,9 +7,9 @@ LIB=quadruped_control_b200/libqpb200.so
 OUT=profiles/r02_sass_balance.txt
 {
 echo "# ptxas resource usage (cuobjdump -res-usage $LIB), balance kernels"
-cuobjdump -res-usage $LIB 2>/dev/null | grep -A1 -E "tpq_|balance_qp" | grep -E "Function|REG" | sed 's/ Function \(.*\):/\1/' | paste - - | sed 's/^ *//' | cut -c1-260
+cuobjdump -res-usage $LIB 2>/dev/null | grep -A1 -E "tpq_|balance_qp|wire_" | grep -E "Function|REG" | sed 's/ Function \(.*\):/\1/' | paste - - | sed 's/^ *//' | cut -c1-260
 echo
-for K in tpq_setup_kernelINS_8PackedIO tpq_loop_kernelILi1 tpq_loop_kernelILi2 tpq_loop_kernelILi4 tpq_finish_kernelINS_8PackedIO balance_qp_kernel16INS_8PackedIO; do
+for K in tpq_setup_kernelINS_8PackedIOELb0 tpq_setup_kernelINS_8PackedIOELb1 tpq_one_kernelINS_8PackedIOELb1 tpq_one_kernelINS_8PackedIOELb0 wire_unpack_kernel wire_pack_kernel tpq_loop_kernelILi1 tpq_loop_kernelILi2 tpq_loop_kernelILi4 tpq_finish_kernelINS_8PackedIOELb0 balance_qp_kernel16INS_8PackedIO; do
   F=$(cuobjdump -sass $LIB 2>/dev/null | grep -o "Function : [_A-Za-z0-9]*${K}[_A-Za-z0-9]*" | head -1 | sed 's/Function : //')
   [ -z "$F" ] && continue
   echo "# SASS opcode histogram: $F"
