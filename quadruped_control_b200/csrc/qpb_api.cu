@@ -179,7 +179,9 @@ int launch_balance(qpb_handle* h, const IO& io, int64_t n, int ctas_per_sm, cuda
     const int lpq = h->tpq_lpq;
     bool first_chain = true;
     // one chain of three launches per at most 2^20 records of [lo0, lo0 + n0), on stream s
-    const bool early = force_path == 34;  // warm batch: records optimal after the set-up are finished there
+    // warm batch: records optimal after the set-up are finished there (for cold batches -- 18 % / 45 % such records on
+    // config 2 / 3 -- the same costs 7 %: every warp pays the epilogue twice; profiles/r02_early_cold_ab.txt)
+    const bool early = force_path == 34;
     auto run_chain = [&](int64_t lo0, int64_t n0, cudaStream_t s) -> int {
       for (int64_t lo = lo0; lo < lo0 + n0; lo += kTpqChunk) {
         const int64_t m = lo0 + n0 - lo < kTpqChunk ? lo0 + n0 - lo : kTpqChunk;
