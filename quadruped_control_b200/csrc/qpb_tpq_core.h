@@ -757,11 +757,15 @@ QPB_HD void setup(const Params& P, const FastParams& K, const double* rec, uint3
 
 // World-frame solution -> body-frame GRF (balance_controller.cpp:218-232) and tau = J^T f (kinematics.cpp:162-188,
 // 218-231, clamp commander_node.cpp:526).  R: Rwb (9), q: joint angles (12).
-template <class Params>
+// UNROLL = 1: one copy of the three sincos expansions instead of four and the per-leg arrays in local memory -- for the
+// one-launch kernel, whose active-set loop shares the instruction cache with this code (unrolled, its cold mid-size
+// batches lose 15-20 %) and for the early-finish set-up, which has no registers to spare.  UNROLL = 4: everything in
+// registers -- for the finishing pass (+7 % on config 3, +3 % on config 2; profiles/r02_finish_unroll_ab.txt).
+template <int UNROLL = 1, class Params>
 QPB_HD void finish(const Params& P, const double* R, const double* q, const State& st, double (&grf)[12], double (&tau)[12]) {
   const bool good = st.status == QPB_OK;
   const bool qok = st.status != QPB_BAD_INPUT;
-#pragma unroll 1  // one copy of the three sincos expansions instead of four: this runs once per QP, code size matters more
+#pragma unroll UNROLL
   for (int i = 0; i < 4; i++) {
     const bool on = good && ((st.stance >> i) & 1u);
     const double f0 = st.f[3 * i], f1 = st.f[3 * i + 1], f2 = st.f[3 * i + 2];
