@@ -175,6 +175,36 @@ __device__ __forceinline__ void tpq_store(const SplitIO& io, int64_t rec, const 
   if (io.status) io.status[rec] = status;
 }
 
+// finish() rolled over the legs (ONE copy of the sincos code) with its per-leg arrays in a column of shared memory
+// instead of local memory: element i of this thread's array X sits at col[(X + i) * stride].  In: forces at F, joint
+// angles at Q.  Out: body-frame forces at GRF (may alias F), torques at TAU.  Same arithmetic as finish().
+template <int F, int Q, int GRF, int TAU, class Params>
+__device__ __forceinline__ void finish_rolled_smem(const Params& P, const double* R, double* col, int stride, int status, uint32_t stance) {
+  const bool good = status == QPB_OK, qok = status != QPB_BAD_INPUT;
+#pragma unroll 1
+  for (int i = 0; i < 4; i++) {
+    const bool on = good && ((stance >> i) & 1u);
+    const double f0 = col[(F + 3 * i) * stride], f1 = col[(F + 3 * i + 1) * stride], f2 = col[(F + 3 * i + 2) * stride];
+    double fb[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) fb[k] = on ? -1.0 * (R[k] * f0 + R[3 + k] * f1 + R[6 + k] * f2) : 0.0;
+    const double q0 = col[(Q + 3 * i) * stride], q1 = col[(Q + 3 * i + 1) * stride], q2 = col[(Q + 3 * i + 2) * stride];
+    double s1, c1, s2, c2, s23, c23;
+    sincos(qok ? q0 : 0.0, &s1, &c1);
+    sincos(qok ? q1 : 0.0, &s2, &c2);
+    sincos(qok ? q1 + q2 : 0.0, &s23, &c23);
+    double tq[3];
+    leg_jt(P.link[3 * i], P.link[3 * i + 1], P.link[3 * i + 2], s1, c1, s2, c2, s23, c23, fb[0], fb[1], fb[2], tq);
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      double v = tq[k];
+      if (P.clamp_tau) v = fmin(fmax(v, P.tau_min), P.tau_max);
+      col[(GRF + 3 * i + k) * stride] = fb[k];
+      col[(TAU + 3 * i + k) * stride] = on ? v : 0.0;
+    }
+  }
+}
+
 // ---- pass 1: set-up, one thread per record ----------------------------------------------------------------------------
 // Writes a dual-feasible starting pair into the prepared record: f, u, G and the meta word (working set, contact mask,
 // status, block rounds spent).  Called for every pair the block rounds of start() accept; the last call wins.
@@ -219,15 +249,24 @@ tpq_setup_kernel(const __grid_constant__ EdgeParams P, const __grid_constant__ F
     need = commit.key != 0u;
     if (EARLY && !need) {
       // (the pair committed last is the one st holds: start() stops at the first optimal pair)
-      double q[12], grf[12], tau[12];
+      __shared__ double cols[EARLY ? kEdgeThreads * 36 : 1];  // per thread: f -> grf (12), q (12), tau (12)
+      double* col = cols + threadIdx.x;
       bool qfin = true;
 #pragma unroll
       for (int i = 0; i < 12; i++) {
-        q[i] = tpq_q(io, rec, v, i);
-        qfin = qfin && (fabs(q[i]) <= 1.79769313486231570e308);
+        const double qi = tpq_q(io, rec, v, i);
+        qfin = qfin && (fabs(qi) <= 1.79769313486231570e308);
+        col[(12 + i) * kEdgeThreads] = qi;
+        col[i * kEdgeThreads] = st.f[i];
       }
       if (!qfin && st.status == QPB_OK) st.status = QPB_BAD_INPUT;
-      finish<1>(P, v + kR, q, st, grf, tau);  // (rolled: the set-up's registers are all taken, unrolled measured 4 % slower)
+      finish_rolled_smem<0, 12, 0, 24>(P, v + kR, col, kEdgeThreads, st.status, st.stance);
+      double grf[12], tau[12];
+#pragma unroll
+      for (int i = 0; i < 12; i++) {
+        grf[i] = col[i * kEdgeThreads];
+        tau[i] = col[(24 + i) * kEdgeThreads];
+      }
       tpq_store(io, rec, grf, tau, st.status, st.iters, st.word | 0x80000000u);
     } else {
       // what does not depend on the working set: lever arms and the right-hand side (after a non-finite input they are zero)
@@ -583,12 +622,20 @@ tpq_one_kernel(const __grid_constant__ EdgeParams P, const __grid_constant__ Fas
     return;
   }
   if (!active) return;
-  double R[9], q[12], grf[12], tau[12];
+  // The epilogue of finish() rolled over the legs (one copy of the sincos code: the loop above shares the instruction
+  // cache with it), its per-leg arrays in this thread's column of shared memory -- as local-memory arrays they miss the
+  // L1 that 8 CTAs x 26 KB of shared memory leave (profiles/r02_finish_unroll_ab.txt).
+  double R[9], grf[12], tau[12];
 #pragma unroll
   for (int i = 0; i < 9; i++) R[i] = keep[(kKeepR + i) * kOneThreads];
 #pragma unroll
-  for (int i = 0; i < 12; i++) q[i] = keep[(kKeepQ + i) * kOneThreads];
-  finish(P, R, q, st, grf, tau);
+  for (int i = 0; i < 12; i++) keep[(kKeepF + i) * kOneThreads] = st.f[i];
+  finish_rolled_smem<kKeepF, kKeepQ, kKeepU, kKeepG>(P, R, keep, kOneThreads, st.status, st.stance);  // (U and G are free by now)
+#pragma unroll
+  for (int i = 0; i < 12; i++) {
+    grf[i] = keep[(kKeepU + i) * kOneThreads];
+    tau[i] = keep[(kKeepG + i) * kOneThreads];
+  }
   tpq_store(io, rec, grf, tau, st.status, st.iters, st.word | 0x80000000u);
 }
 
