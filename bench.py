@@ -247,7 +247,7 @@ def kernel_path():
         return "balance_qp_kernel<PackedIO>"
     if m == "2":
         return "balance_qp_kernel16<PackedIO>"
-    return f"tpq_setup_kernel<PackedIO> + tpq_loop_kernel<{os.environ.get('QPB_TPQ_LPQ', '1')}> + tpq_finish_kernel<PackedIO>"
+    return f"tpq_setup_kernel<PackedIO, false> + tpq_loop_kernel<{os.environ.get('QPB_TPQ_LPQ', '1')}> + tpq_finish_kernel<PackedIO, false>"
 
 
 def fp64_block(iters, n, step_ms):
