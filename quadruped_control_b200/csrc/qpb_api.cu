@@ -196,10 +196,11 @@ int launch_balance(qpb_handle* h, const IO& io, int64_t n, int ctas_per_sm, cuda
         first_chain = false;
         unsigned long long* tk = h->d_tickets + 4 * (size_t)slot2;
         const unsigned edge = (unsigned)((m + qpb::tpq::kEdgeThreads - 1) / qpb::tpq::kEdgeThreads);
+        const size_t stage_bytes = qpb::tpq::StageIn<IO>::on ? qpb::tpq::kSetupStageBytes : 0;
         if (early)
-          qpb::tpq::tpq_setup_kernel<IO, true><<<edge, qpb::tpq::kEdgeThreads, 0, s>>>(h->edge, h->fast, part, m, prep, res, work, tk);
+          qpb::tpq::tpq_setup_kernel<IO, true><<<edge, qpb::tpq::kEdgeThreads, stage_bytes, s>>>(h->edge, h->fast, part, m, prep, res, work, tk);
         else
-          qpb::tpq::tpq_setup_kernel<IO, false><<<edge, qpb::tpq::kEdgeThreads, 0, s>>>(h->edge, h->fast, part, m, prep, res, work, tk);
+          qpb::tpq::tpq_setup_kernel<IO, false><<<edge, qpb::tpq::kEdgeThreads, stage_bytes, s>>>(h->edge, h->fast, part, m, prep, res, work, tk);
         const int lthreads = lpq == 1 ? qpb::tpq::LoopShape<1>::THREADS : (lpq == 2 ? qpb::tpq::LoopShape<2>::THREADS : qpb::tpq::LoopShape<4>::THREADS);
         const int64_t want = (m * lpq + lthreads - 1) / lthreads;
         const int64_t cap = (int64_t)h->num_sms * h->ctas_per_sm_tpq[lpq];
@@ -609,6 +610,11 @@ int qpb_create(const qpb_params* params, int device, qpb_handle** out) {
   if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->ctas_per_sm_tpq[1], qpb::tpq::tpq_loop_kernel<1>, qpb::tpq::LoopShape<1>::THREADS, 0);
   if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->ctas_per_sm_tpq[2], qpb::tpq::tpq_loop_kernel<2>, qpb::tpq::LoopShape<2>::THREADS, 0);
   if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->ctas_per_sm_tpq[4], qpb::tpq::tpq_loop_kernel<4>, qpb::tpq::LoopShape<4>::THREADS, 0);
+  if (e == cudaSuccess && qpb::tpq::StageIn<qpb::PackedIO>::on) {
+    e = cudaFuncSetAttribute(qpb::tpq::tpq_setup_kernel<qpb::PackedIO, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qpb::tpq::kSetupStageBytes);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(qpb::tpq::tpq_setup_kernel<qpb::PackedIO, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qpb::tpq::kSetupStageBytes);
+  }
   if (e == cudaSuccess) {  // keep freed scratch in the stream-ordered pool instead of returning it to the OS after every call
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {

@@ -107,6 +107,12 @@ __device__ __forceinline__ double pack_meta(uint32_t word, uint32_t stance, int 
   return __hiloint2double((int)hi, (int)lo);
 }
 
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 // ---- record access: 48 doubles + contact bytes + warm-start word in, 256-B record out --------------------------
 __device__ __forceinline__ void tpq_load(const PackedIO& io, int64_t rec, double (&v)[48], uint32_t& cbytes, uint32_t& hint) {
   const double2* p = reinterpret_cast<const double2*>(io.in + rec);
@@ -146,6 +152,9 @@ __device__ __forceinline__ void tpq_load_Rq(const SplitIO& io, int64_t rec, doub
 #pragma unroll
   for (int j = 0; j < 12; j++) q[j] = __ldg(io.q + rec * 12 + j);
 }
+// start of a packed record as doubles (only meaningful for PackedIO; the other loader never stages)
+__device__ __forceinline__ const double* packed_base(const PackedIO& io, int64_t rec) { return reinterpret_cast<const double*>(io.in + rec); }
+__device__ __forceinline__ const double* packed_base(const SplitIO&, int64_t) { return nullptr; }
 // joint angle i of a record whose slots 0..47 are already in registers (packed records carry q in slots 48..59)
 __device__ __forceinline__ double tpq_q(const PackedIO& io, int64_t rec, const double (&)[48], int i) {
   return __ldg(reinterpret_cast<const double*>(io.in + rec) + kQ + i);
@@ -228,6 +237,22 @@ struct PrepCommit {
   }
 };
 
+// Staged records (packed records only; QPB_TPQ_STAGE_IN=0 turns it off): the 32 records of a warp are copied to shared
+// memory by 32 cp.async instructions, each moving one whole record (31 lanes x 16 B, coalesced), instead of 25 loads per
+// thread that each touch 32 different lines; the threads read their record with conflict-free 128-bit shared loads.
+// The same row then collects the prepared record -- every pair the block rounds commit lands in shared memory instead of
+// global memory -- and leaves in one coalesced copy per record.  Config 3 +10 %, config 2 +3 % (input alone: +2 % / 0;
+// profiles/r02_setup_staging_ab.txt): `lg_throttle` and most of `long_scoreboard` of the set-up pass were these accesses.
+#ifndef QPB_TPQ_STAGE_IN
+#define QPB_TPQ_STAGE_IN 1
+#endif
+constexpr int kStageStride = 66;  // doubles per staged record (62 used; 132 words: a quarter-warp of LDS.128 covers all banks)
+template <class IO> struct StageIn { static constexpr bool on = false; };
+#if QPB_TPQ_STAGE_IN
+template <> struct StageIn<PackedIO> { static constexpr bool on = true; };
+#endif
+constexpr size_t kSetupStageBytes = (size_t)kEdgeThreads * kStageStride * sizeof(double);
+
 // EARLY (warm batches): a record whose starting pair is already optimal -- nearly all of them when the records carry last
 // tick's working sets -- is finished right here (its forces ARE the minimiser on the final faces from one fresh solve):
 // epilogue, result record, no scratch traffic; only the others get a prepared record and a place in the worklist, and
@@ -238,25 +263,63 @@ tpq_setup_kernel(const __grid_constant__ EdgeParams P, const __grid_constant__ F
                  double* __restrict__ res, uint32_t* __restrict__ work, unsigned long long* __restrict__ ticket) {
   const int64_t rec = (int64_t)blockIdx.x * kEdgeThreads + threadIdx.x;
   bool need = false;  // this record goes through the active-set loop (its starting pair is not optimal yet)
+  extern __shared__ __align__(16) double stage_dyn[];
+  const double* mine = nullptr;  // this thread's staged record
+  if (StageIn<IO>::on) {
+    const int lane = threadIdx.x & 31;
+    double* stage = stage_dyn + (threadIdx.x >> 5) * 32 * kStageStride;
+    const int64_t base = (int64_t)blockIdx.x * kEdgeThreads + (threadIdx.x & ~31);
+    const int cnt = n - base >= 32 ? 32 : (n > base ? (int)(n - base) : 0);
+    if (lane < 31)
+      for (int e = 0; e < cnt; e++) cp_async16(stage + e * kStageStride + 2 * lane, packed_base(io, base + e) + 2 * lane);
+    cp_async_commit();
+    cp_async_wait_all();
+    __syncwarp();
+    mine = stage + lane * kStageStride;
+  }
   if (rec < n) {
     double v[48];
     uint32_t cbytes, hint;
-    tpq_load(io, rec, v, cbytes, hint);
+    if (StageIn<IO>::on) {
+#pragma unroll
+      for (int j = 0; j < 24; j++) {
+        const double2 t = reinterpret_cast<const double2*>(mine)[j];
+        v[2 * j] = t.x;
+        v[2 * j + 1] = t.y;
+      }
+      const uint2 c = reinterpret_cast<const uint2*>(mine)[60];
+      cbytes = c.x;
+      hint = c.y;
+    } else {
+      tpq_load(io, rec, v, cbytes, hint);
+    }
     State st;
     double b6[6], G[21];
-    PrepCommit commit{ prep + rec * kPrepSize, 0u, 0.0 };
+    __shared__ double cols[EARLY ? kEdgeThreads * 36 : 1];  // per thread: f -> grf (12), q (12), tau (12)
+    double* col = cols + threadIdx.x;
+    bool qfin = true;
+    if (EARLY && StageIn<IO>::on) {  // the staged row becomes the prepared record: take the joint angles out first
+#pragma unroll
+      for (int i = 0; i < 12; i++) {
+        const double qi = mine[kQ + i];
+        qfin = qfin && (fabs(qi) <= 1.79769313486231570e308);
+        col[(12 + i) * kEdgeThreads] = qi;
+      }
+    }
+    // staged: the prepared record is put together in this thread's row of shared memory (every pair the block rounds
+    // commit lands there, not in global memory) and leaves in one coalesced copy per record below
+    PrepCommit commit{ StageIn<IO>::on ? const_cast<double*>(mine) : prep + rec * kPrepSize, 0u, 0.0 };
     setup(P, K, v, cbytes, hint, st, b6, G, commit);
     need = commit.key != 0u;
     if (EARLY && !need) {
       // (the pair committed last is the one st holds: start() stops at the first optimal pair)
-      __shared__ double cols[EARLY ? kEdgeThreads * 36 : 1];  // per thread: f -> grf (12), q (12), tau (12)
-      double* col = cols + threadIdx.x;
-      bool qfin = true;
 #pragma unroll
       for (int i = 0; i < 12; i++) {
-        const double qi = tpq_q(io, rec, v, i);
-        qfin = qfin && (fabs(qi) <= 1.79769313486231570e308);
-        col[(12 + i) * kEdgeThreads] = qi;
+        if (!StageIn<IO>::on) {
+          const double qi = tpq_q(io, rec, v, i);
+          qfin = qfin && (fabs(qi) <= 1.79769313486231570e308);
+          col[(12 + i) * kEdgeThreads] = qi;
+        }
         col[i * kEdgeThreads] = st.f[i];
       }
       if (!qfin && st.status == QPB_OK) st.status = QPB_BAD_INPUT;
@@ -280,6 +343,20 @@ tpq_setup_kernel(const __grid_constant__ EdgeParams P, const __grid_constant__ F
   }
   // worklist of the loop pass: one atomic per warp (ticket[2] counts the entries; the loop's last CTA re-arms it)
   const uint32_t m = __ballot_sync(FULL, need);
+  if (StageIn<IO>::on) {
+    // prepared records out: whole (512 B) for the loop's QPs, lever arms and right-hand side (144 B) for the others --
+    // none at all for records an EARLY set-up has finished
+    const int lane = threadIdx.x & 31;
+    const double* stage = stage_dyn + (threadIdx.x >> 5) * 32 * kStageStride;
+    const int64_t base = (int64_t)blockIdx.x * kEdgeThreads + (threadIdx.x & ~31);
+    const int cnt = n - base >= 32 ? 32 : (n > base ? (int)(n - base) : 0);
+    __syncwarp();
+    for (int e = 0; e < cnt; e++) {
+      const int chunks = ((m >> e) & 1u) ? 32 : (EARLY ? 0 : 9);
+      if (lane < chunks)
+        reinterpret_cast<double2*>(prep + (base + e) * kPrepSize)[lane] = reinterpret_cast<const double2*>(stage + e * kStageStride)[lane];
+    }
+  }
   if (m) {
     const int lane = threadIdx.x & 31;
     unsigned long long base = 0;
@@ -297,11 +374,6 @@ tpq_setup_kernel(const __grid_constant__ EdgeParams P, const __grid_constant__ F
 // chain of atomic -> index load -> record load (2 us, a whole loop iteration) as it did when every refill went to
 // global memory on the spot (profiles/r02_ncu_tpq_v4_loop_cfg3_digest.txt: long-scoreboard stalls 1.96 per issue).
 
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 template <int LPQ>
 __global__ void __launch_bounds__(LoopShape<LPQ>::THREADS, LoopShape<LPQ>::MIN_CTAS)
