@@ -181,16 +181,24 @@ int qpb_mpc_batch_host(qpb_mpc_handle* h, int64_t n, const qpb_mpc_rec* h_recs, 
     if (!h->d_out[s]) MPC_CUDA(cudaMalloc(&h->d_out[s], kChunk * sizeof(qpb_mpc_out_rec)));
   }
   // upload / solve / download of successive stages overlap on a ring of streams; the solve dominates by far
-  int slot = 0;
-  for (int64_t lo = 0; lo < n; lo += kChunk, slot = (slot + 1) % kSlots) {
+  int slot = 0, rc = QPB_SUCCESS;
+  cudaError_t ce = cudaSuccess;
+  for (int64_t lo = 0; lo < n && rc == QPB_SUCCESS && ce == cudaSuccess; lo += kChunk, slot = (slot + 1) % kSlots) {
     const int64_t m = n - lo < kChunk ? n - lo : kChunk;
     cudaStream_t st = h->streams[slot];
-    MPC_CUDA(cudaMemcpyAsync(h->d_in[slot], h_recs + lo, m * sizeof(qpb_mpc_rec), cudaMemcpyHostToDevice, st));
-    const int rc = launch_mpc(h, m, h->d_in[slot], h->d_out[slot], st);
-    if (rc != QPB_SUCCESS) return rc;
-    MPC_CUDA(cudaMemcpyAsync(h_out + lo, h->d_out[slot], m * sizeof(qpb_mpc_out_rec), cudaMemcpyDeviceToHost, st));
+    ce = cudaMemcpyAsync(h->d_in[slot], h_recs + lo, m * sizeof(qpb_mpc_rec), cudaMemcpyHostToDevice, st);
+    if (ce != cudaSuccess) break;
+    rc = launch_mpc(h, m, h->d_in[slot], h->d_out[slot], st);
+    if (rc != QPB_SUCCESS) break;
+    ce = cudaMemcpyAsync(h_out + lo, h->d_out[slot], m * sizeof(qpb_mpc_out_rec), cudaMemcpyDeviceToHost, st);
   }
-  for (int s = 0; s < kSlots; s++) MPC_CUDA(cudaStreamSynchronize(h->streams[s]));
+  // never return while an earlier stage may still be copying out of / into the caller's buffers -- also not on an error
+  for (int s = 0; s < kSlots; s++) {
+    const cudaError_t es = cudaStreamSynchronize(h->streams[s]);
+    if (ce == cudaSuccess) ce = es;
+  }
+  if (rc != QPB_SUCCESS) return rc;
+  if (ce != cudaSuccess) return qpb_internal_fail(QPB_ERR_CUDA, std::string("qpb_mpc_batch_host: ") + cudaGetErrorString(ce));
   return QPB_SUCCESS;
 }
 

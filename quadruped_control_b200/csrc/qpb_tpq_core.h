@@ -388,6 +388,7 @@ QPB_HD uint32_t saturated_rows(const FastParams& K, const State& st, uint32_t vi
 #endif
     const uint32_t c = (st.word | viol) >> (6 * i);
     const double fx = st.f[3 * i], fy = st.f[3 * i + 1], fz = st.f[3 * i + 2];
+    (void)fz;  // (mode 2 only)
     uint32_t add = 0u;
     if ((c & 3u) == 0u) add |= hi32(fx) < 0 ? 2u : 1u;
     if ((c & 12u) == 0u) add |= hi32(fy) < 0 ? 8u : 4u;
