@@ -247,10 +247,7 @@ def kernel_path():
         return "balance_qp_kernel<PackedIO>"
     if m == "2":
         return "balance_qp_kernel16<PackedIO>"
-    lpq = os.environ.get("QPB_TPQ_LPQ", "1")
-    if lpq == "1" and os.environ.get("QPB_TPQ_OVERLAP", "1") != "0":  # the default: the finishing pass overlaps the loop's tail
-        return "tpq_setup_kernel<PackedIO, false, true> + tpq_loop_kernel<1, true> + tpq_finish_kernel<PackedIO, 2> (programmatic dependent launch)"
-    return f"tpq_setup_kernel<PackedIO, false> + tpq_loop_kernel<{lpq}> + tpq_finish_kernel<PackedIO, 0>"
+    return f"tpq_setup_kernel<PackedIO, false> + tpq_loop_kernel<{os.environ.get('QPB_TPQ_LPQ', '1')}> + tpq_finish_kernel<PackedIO, false>"
 
 
 def fp64_block(iters, n, step_ms):

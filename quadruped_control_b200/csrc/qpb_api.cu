@@ -84,9 +84,6 @@ struct qpb_handle {
   int qps_per_warp = 2;
   int ctas_per_sm_tpq[5] = {};  // indexed by lanes per QP (1, 2, 4)
   int tpq_lpq = 1;              // lanes per QP of the range-space loop kernel (QPB_TPQ_LPQ=1|2|4 overrides)
-  int tpq_overlap = 1;          // cold three-pass batches: the finishing pass is a programmatic dependent of the loop pass and takes
-                                // its records from a queue of finished QPs, so it fills the SMs the loop's tail leaves idle
-                                // (QPB_TPQ_OVERLAP=0: three serial launches)
   int64_t tpq_min_n = 12288;    // smaller batches take a one-launch kernel: lower latency (QPB_TPQ_MIN_N)
   int64_t tpq_one_max = 1;      // ... up to here the range-space one (tpq_one_kernel), above it the half-warp kernel (QPB_TPQ_ONE_MAX)
   int warm_batches = 0;         // device-resident calls: the records carry warm-start words (qpb_set_warm_batches)
@@ -200,44 +197,24 @@ int launch_balance(qpb_handle* h, const IO& io, int64_t n, int ctas_per_sm, cuda
         unsigned long long* tk = h->d_tickets + 4 * (size_t)slot2;
         const unsigned edge = (unsigned)((m + qpb::tpq::kEdgeThreads - 1) / qpb::tpq::kEdgeThreads);
         const size_t stage_bytes = qpb::tpq::StageIn<IO>::on ? qpb::tpq::kSetupStageBytes : 0;
-        // queue mode (qpb_tpq.cuh, tpq_loop_kernel<1, true>): res is the queue of finished records, all ones = empty
-        const bool queue = !early && lpq == 1 && h->tpq_overlap && h->params.max_iter < (1 << qpb::tpq::kQueueIterBits) - 1;
-        if (queue) QPB_CUDA(cudaMemsetAsync(res, 0xff, (size_t)m * sizeof(double), s));
         if (early)
           qpb::tpq::tpq_setup_kernel<IO, true><<<edge, qpb::tpq::kEdgeThreads, stage_bytes, s>>>(h->edge, h->fast, part, m, prep, res, work, tk);
-        else if (queue)
-          qpb::tpq::tpq_setup_kernel<IO, false, true><<<edge, qpb::tpq::kEdgeThreads, stage_bytes, s>>>(h->edge, h->fast, part, m, prep, res, work, tk);
         else
           qpb::tpq::tpq_setup_kernel<IO, false><<<edge, qpb::tpq::kEdgeThreads, stage_bytes, s>>>(h->edge, h->fast, part, m, prep, res, work, tk);
         const int lthreads = lpq == 1 ? qpb::tpq::LoopShape<1>::THREADS : (lpq == 2 ? qpb::tpq::LoopShape<2>::THREADS : qpb::tpq::LoopShape<4>::THREADS);
         const int64_t want = (m * lpq + lthreads - 1) / lthreads;
         const int64_t cap = (int64_t)h->num_sms * h->ctas_per_sm_tpq[lpq];
         const int grid = (int)(want < cap ? want : cap);
-        if (queue)
-          qpb::tpq::tpq_loop_kernel<1, true><<<grid, lthreads, 0, s>>>(h->fast, prep, res, work, tk);
-        else if (lpq == 1)
+        if (lpq == 1)
           qpb::tpq::tpq_loop_kernel<1><<<grid, lthreads, 0, s>>>(h->fast, prep, res, work, tk);
         else if (lpq == 2)
           qpb::tpq::tpq_loop_kernel<2><<<grid, lthreads, 0, s>>>(h->fast, prep, res, work, tk);
         else
           qpb::tpq::tpq_loop_kernel<4><<<grid, lthreads, 0, s>>>(h->fast, prep, res, work, tk);
-        if (queue) {
-          // programmatic dependent launch: its CTAs may start while the loop kernel is still running
-          cudaLaunchConfig_t cfg = {};
-          cfg.gridDim = dim3(edge);
-          cfg.blockDim = dim3(qpb::tpq::kEdgeThreads);
-          cfg.stream = s;
-          cudaLaunchAttribute attr[1];
-          attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-          attr[0].val.programmaticStreamSerializationAllowed = 1;
-          cfg.attrs = attr;
-          cfg.numAttrs = 1;
-          QPB_CUDA(cudaLaunchKernelEx(&cfg, qpb::tpq::tpq_finish_kernel<IO, 2>, h->edge, h->fast, part, m, (const double*)prep,
-                                      (const double*)res, (const uint32_t*)work, (const unsigned long long*)tk));
-        } else if (early)
-          qpb::tpq::tpq_finish_kernel<IO, 1><<<edge, qpb::tpq::kEdgeThreads, 0, s>>>(h->edge, h->fast, part, m, prep, res, work, tk);
+        if (early)
+          qpb::tpq::tpq_finish_kernel<IO, true><<<edge, qpb::tpq::kEdgeThreads, 0, s>>>(h->edge, h->fast, part, m, prep, res, work, tk);
         else
-          qpb::tpq::tpq_finish_kernel<IO, 0><<<edge, qpb::tpq::kEdgeThreads, 0, s>>>(h->edge, h->fast, part, m, prep, res, work, tk);
+          qpb::tpq::tpq_finish_kernel<IO, false><<<edge, qpb::tpq::kEdgeThreads, 0, s>>>(h->edge, h->fast, part, m, prep, res, work, tk);
         h->launches.fetch_add(3, std::memory_order_relaxed);
         QPB_CUDA(cudaGetLastError());
         if (!scratch) QPB_CUDA(cudaFreeAsync(prep, s));
@@ -537,6 +514,17 @@ extern "C" {
 
 int qpb_version(void) { return QPB_VERSION; }
 
+#ifdef QPB_TPQ_TIMELINE
+// developer build only (not declared in qpb200.h): per-CTA start / end stamps of the last loop and finishing passes
+int qpb_debug_timeline(unsigned long long* out /* [4][8192] */) {
+  QPB_CUDA(cudaDeviceSynchronize());
+  QPB_CUDA(cudaMemcpyFromSymbol(out, qpb::tpq::g_tl, sizeof(unsigned long long) * 4 * 8192));
+  static unsigned long long zero[4 * 8192];
+  QPB_CUDA(cudaMemcpyToSymbol(qpb::tpq::g_tl, zero, sizeof(zero)));
+  return QPB_SUCCESS;
+}
+#endif
+
 const char* qpb_last_error(void) { return g_last_error.c_str(); }
 
 int qpb_default_params(qpb_params* p) {
@@ -637,8 +625,6 @@ int qpb_create(const qpb_params* params, int device, qpb_handle** out) {
     e = cudaFuncSetAttribute(qpb::tpq::tpq_setup_kernel<qpb::PackedIO, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qpb::tpq::kSetupStageBytes);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(qpb::tpq::tpq_setup_kernel<qpb::PackedIO, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qpb::tpq::kSetupStageBytes);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(qpb::tpq::tpq_setup_kernel<qpb::PackedIO, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qpb::tpq::kSetupStageBytes);
   }
   if (e == cudaSuccess) {  // keep freed scratch in the stream-ordered pool instead of returning it to the OS after every call
     cudaMemPool_t pool;
@@ -672,7 +658,6 @@ int qpb_create(const qpb_params* params, int device, qpb_handle** out) {
     const int v = std::atoi(env);
     if (v == 1 || v == 2 || v == 4) h->tpq_lpq = v;
   }
-  if (const char* env = std::getenv("QPB_TPQ_OVERLAP")) h->tpq_overlap = std::atoi(env) != 0;
   if (const char* env = std::getenv("QPB_TPQ_MIN_N")) {
     const long long v = std::atoll(env);
     if (v >= 0) h->tpq_min_n = v;

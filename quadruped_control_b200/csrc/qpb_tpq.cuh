@@ -30,6 +30,19 @@ namespace tpq {
 
 constexpr int kEdgeThreads = 128;   // set-up / finishing kernels
 
+#ifdef QPB_TPQ_TIMELINE
+// developer build only (tools/timeline.py): when every CTA of the loop and finishing passes started and ended (ns, %globaltimer)
+__device__ unsigned long long g_tl[4][8192];  // loop start, loop end, finish start, finish end -- by blockIdx.x
+__device__ __forceinline__ unsigned long long tl_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define QPB_TL(k) do { if (threadIdx.x == 0 && blockIdx.x < 8192) g_tl[k][blockIdx.x] = tl_now(); } while (0)
+#else
+#define QPB_TL(k) do { } while (0)
+#endif
+
 // minimum CTAs per SM = the register cap (65536 / (128 threads * MIN_CTAS)); overridable for experiments
 #ifndef QPB_TPQ_MINCTAS_1
 #define QPB_TPQ_MINCTAS_1 2  // 255 registers
@@ -105,17 +118,6 @@ __device__ __forceinline__ double pack_meta(uint32_t word, uint32_t stance, int 
   const uint32_t lo = word | (stance << 24) | ((uint32_t)status << 28);
   const uint32_t hi = ((uint32_t)iters & 0xffffu) | ((key & 31u) << 16) | ((key >> 31) << 21);
   return __hiloint2double((int)hi, (int)lo);
-}
-
-// Queue of finished records (the overlapped finishing pass, below): one 64-bit entry per record, in the order the records
-// become final.  low word as in pack_meta (working set | stance | status); high word: record number within the chunk (20
-// bits) | working-set changes (11 bits); bit 63 clear.  The queue starts out as all ones: an entry with bit 63 set has
-// not been written yet.  One 8-byte store publishes everything the finishing pass needs of a record, so no fence.
-constexpr int kQueueIterBits = 11, kQueueRecBits = 20;
-__device__ __forceinline__ unsigned long long queue_entry(uint32_t word, uint32_t stance, int status, int iters, uint32_t rec) {
-  const uint32_t lo = word | (stance << 24) | ((uint32_t)status << 28);
-  const uint32_t it = (uint32_t)iters < (1u << kQueueIterBits) - 1u ? (uint32_t)iters : (1u << kQueueIterBits) - 1u;
-  return ((unsigned long long)(rec | (it << kQueueRecBits)) << 32) | lo;
 }
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
@@ -268,16 +270,12 @@ constexpr size_t kSetupStageBytes = (size_t)kEdgeThreads * kStageStride * sizeof
 // tick's working sets -- is finished right here (its forces ARE the minimiser on the final faces from one fresh solve):
 // epilogue, result record, no scratch traffic; only the others get a prepared record and a place in the worklist, and
 // the finishing pass then walks the worklist instead of the batch (tpq_finish_kernel<IO, true>).
-// QUEUE: res is the queue of the overlapped finishing pass (tpq_finish_kernel<IO, 2>) instead of an array of result words.
-template <class IO, bool EARLY, bool QUEUE = false>
+template <class IO, bool EARLY>
 __global__ void __launch_bounds__(kEdgeThreads, QPB_TPQ_EDGE_MINCTAS)
 tpq_setup_kernel(const __grid_constant__ EdgeParams P, const __grid_constant__ FastParams K, IO io, int64_t n, double* __restrict__ prep,
                  double* __restrict__ res, uint32_t* __restrict__ work, unsigned long long* __restrict__ ticket) {
-  static_assert(!(EARLY && QUEUE), "an early-finish set-up has its own finishing pass");
   const int64_t rec = (int64_t)blockIdx.x * kEdgeThreads + threadIdx.x;
   bool need = false;  // this record goes through the active-set loop (its starting pair is not optimal yet)
-  uint32_t qlo = 0u;  // QUEUE: low word and iteration count of this record's result word
-  int qit = 0;
   extern __shared__ __align__(16) double stage_dyn[];
   const double* mine = nullptr;  // this thread's staged record
   if (StageIn<IO>::on) {
@@ -353,23 +351,7 @@ tpq_setup_kernel(const __grid_constant__ EdgeParams P, const __grid_constant__ F
       for (int i = 0; i < 6; i++) o[kPrepR / 2 + i] = make_double2(st.r[2 * i], st.r[2 * i + 1]);
 #pragma unroll
       for (int i = 0; i < 3; i++) o[kPrepB / 2 + i] = make_double2(b6[2 * i], b6[2 * i + 1]);
-      if (!QUEUE) res[rec] = commit.meta;  // the result word: final as it stands unless the loop pass takes the record
-      qlo = (uint32_t)__double2loint(commit.meta);
-      qit = __double2hiint(commit.meta) & 0xffff;
-    }
-  }
-  if (QUEUE) {
-    // records that are final after the set-up go on the queue of the finishing pass (one atomic per warp; ticket[3] is the
-    // tail of the queue, re-armed by the loop's last CTA); the others get there when the loop retires them
-    const uint32_t mq = __ballot_sync(FULL, rec < n && !need);
-    if (mq) {
-      const int lane = threadIdx.x & 31, first = __ffs(mq) - 1;
-      unsigned long long base = 0;
-      if (lane == first) base = atomicAdd(ticket + 3, (unsigned long long)__popc(mq));
-      base = __shfl_sync(FULL, base, first);
-      if (rec < n && !need)
-        reinterpret_cast<unsigned long long*>(res)[base + __popc(mq & ((1u << lane) - 1u))] =
-            queue_entry(qlo & 0xffffffu, (qlo >> 24) & 15u, (int)((qlo >> 28) & 3u), qit, (uint32_t)rec);
+      res[rec] = commit.meta;  // the result word: final as it stands unless the loop pass takes the record
     }
   }
   // worklist of the loop pass: one atomic per warp (ticket[2] counts the entries; the loop's last CTA re-arms it)
@@ -406,21 +388,13 @@ tpq_setup_kernel(const __grid_constant__ EdgeParams P, const __grid_constant__ F
 // global memory on the spot (profiles/r02_ncu_tpq_v4_loop_cfg3_digest.txt: long-scoreboard stalls 1.96 per issue).
 
 
-//
-// QUEUE: the finishing pass overlaps this one.  The loop pass ends with a long tail -- a few QPs need 25-30 working-set
-// changes, most need under ten, so for the last third of the pass most SMs have run out of work (config 2: issue slots
-// 40 % busy while a warp is resident, 23 % over the whole pass).  The finishing pass is therefore launched as a
-// programmatic dependent of this kernel (every CTA signals launch_dependents at once, so its CTAs move in as soon as
-// CTAs of this kernel leave) and takes its records from a queue instead of waiting for the whole pass: `res` is then
-// that queue, a retiring QP appends its entry (queue_entry(); tail = ticket[3]) and tpq_finish_kernel<IO, 2> polls
-// entry i until it is there.  No deadlock: the dependent kernel cannot start before every CTA of this one is resident.
-template <int LPQ, bool QUEUE = false>
+template <int LPQ>
 __global__ void __launch_bounds__(LoopShape<LPQ>::THREADS, LoopShape<LPQ>::MIN_CTAS)
 tpq_loop_kernel(const __grid_constant__ FastParams K, const double* __restrict__ prep, double* __restrict__ res,
                 const uint32_t* __restrict__ work, unsigned long long* __restrict__ ticket) {
-  if (QUEUE) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   constexpr int LPL = 4 / LPQ, NS = 32 / LPQ;  // legs per lane, QP slots per warp
   constexpr int STAGE = LoopShape<LPQ>::STAGE, kLoopThreads = LoopShape<LPQ>::THREADS;
+  QPB_TL(0);
   __shared__ double side_all[(kLoopThreads / LPQ) * kSideSize];
   __shared__ __align__(16) double stage_all[(kLoopThreads / 32) * STAGE * kPrepSize];
   const int lane = threadIdx.x & 31;
@@ -475,19 +449,7 @@ tpq_loop_kernel(const __grid_constant__ FastParams K, const double* __restrict__
     const uint32_t busy = __ballot_sync(FULL, have && !ln.done) & leaders;
     if (NS - __popc(busy) >= kRefill || busy == 0u) {
       // retire: a finished QP hands its final working set and iteration count to the finishing pass
-      if (QUEUE) {
-        const uint32_t mr = __ballot_sync(FULL, have && ln.done && j == 0);
-        if (mr) {  // one atomic per warp for the places on the queue
-          const int first = __ffs(mr) - 1;
-          unsigned long long b = 0;
-          if (lane == first) b = atomicAdd(ticket + 3, (unsigned long long)__popc(mr));
-          b = __shfl_sync(FULL, b, first);
-          if (have && ln.done && j == 0)
-            reinterpret_cast<unsigned long long*>(res)[b + __popc(mr & ((1u << lane) - 1u))] =
-                queue_entry(ln.word, ln.stance, ln.status, ln.iters, (uint32_t)rec);
-        }
-        if (have && ln.done) have = false;
-      } else if (have && ln.done) {
+      if (have && ln.done) {
         if (j == 0) res[rec] = pack_meta(ln.word, ln.stance, ln.status, ln.iters, 0u);
         have = false;
       }
@@ -538,10 +500,11 @@ tpq_loop_kernel(const __grid_constant__ FastParams K, const double* __restrict__
   // The last CTA out re-arms the work counter: the launch is self-contained, so the same counter slot serves graph
   // replays and later launches without a memset (ticket[0] = work counter, ticket[1] = CTAs finished).
   __syncthreads();
+  QPB_TL(1);
   if (threadIdx.x == 0) {
     __threadfence();
     if (atomicAdd(ticket + 1, 1ULL) == (unsigned long long)gridDim.x - 1ULL) {
-      ticket[3] = QUEUE ? 0ULL : (unsigned long long)n;  // for a finishing pass that walks the worklist / the queue's tail re-armed
+      ticket[3] = (unsigned long long)n;  // for a finishing pass that walks the worklist
       ticket[0] = 0ULL;
       ticket[1] = 0ULL;
       ticket[2] = 0ULL;  // the worklist counter the set-up pass filled
@@ -553,50 +516,28 @@ tpq_loop_kernel(const __grid_constant__ FastParams K, const double* __restrict__
 // ---- pass 3: polish + epilogue, one thread per record -------------------------------------------------------------------
 // LIST: only the records of the worklist (ticket[3] entries, published by the loop pass) -- the others were finished by
 // tpq_setup_kernel<IO, true>.
-// MODE 0: every record of the batch, by index.  MODE 1 (LIST): only the records of the worklist (ticket[3] entries,
-// published by the loop pass) -- the others were finished by tpq_setup_kernel<IO, true>.  MODE 2 (QUEUE): launched as a
-// programmatic dependent of tpq_loop_kernel<1, true>, i.e. while that kernel is still running; thread i waits for entry i
-// of the queue of finished records (written by the set-up pass, which is complete by then, or by a retiring QP of the
-// loop pass) and finishes that record.  Entries are consumed in the order they were produced, so only the threads at the
-// very end of the grid ever wait for the loop's longest QPs.
-template <class IO, int MODE>
+template <class IO, bool LIST>
 __global__ void __launch_bounds__(kEdgeThreads, QPB_TPQ_FINISH_MINCTAS)
 tpq_finish_kernel(const __grid_constant__ EdgeParams P, const __grid_constant__ FastParams K, IO io, int64_t n,
-                  const double* __restrict__ prep, const double* res, const uint32_t* __restrict__ work,
+                  const double* __restrict__ prep, const double* __restrict__ res, const uint32_t* __restrict__ work,
                   const unsigned long long* __restrict__ ticket) {
   int64_t rec = (int64_t)blockIdx.x * kEdgeThreads + threadIdx.x;
-  if (MODE == 1) {
+  QPB_TL(2);
+  if (LIST) {
     if (rec >= (int64_t)__ldg(ticket + 3)) return;
     rec = (int64_t)__ldg(work + rec);
   } else if (rec >= n) {
     return;
   }
+  const double* e = prep + rec * kPrepSize;
   State st;
   double b6[6];
-  uint32_t lo;
-  if (MODE == 2) {
-    const volatile unsigned long long* q = reinterpret_cast<const volatile unsigned long long*>(res) + rec;
-    unsigned long long ent = *q;
-    unsigned ns = 64, spins = 0;
-    while ((long long)ent < 0) {  // not there yet: its QP is still in the loop pass
-      __nanosleep(ns);
-      if (ns < 2048) ns *= 2;
-      if (++spins > (1u << 20)) asm volatile("trap;");  // > 2 s: never with a live loop kernel -- fail loudly, do not hang
-      ent = *q;
-    }
-    lo = (uint32_t)ent;
-    const uint32_t hi = (uint32_t)(ent >> 32);
-    rec = (int64_t)(hi & ((1u << kQueueRecBits) - 1u));
-    st.iters = (int)(hi >> kQueueRecBits);
-  } else {
-    const double w = __ldg(res + rec);
-    lo = (uint32_t)__double2loint(w);
-    st.iters = __double2hiint(w) & 0xffff;
-  }
-  const double* e = prep + rec * kPrepSize;
+  const double w = __ldg(res + rec);
+  const uint32_t lo = (uint32_t)__double2loint(w);
   st.word = lo & 0xffffffu;
   st.stance = (lo >> 24) & 15u;
   st.status = (int)((lo >> 28) & 3u);
+  st.iters = __double2hiint(w) & 0xffff;
 #pragma unroll
   for (int i = 0; i < 6; i++) {
     const double2 t = __ldg(reinterpret_cast<const double2*>(e + kPrepR) + i);
@@ -620,6 +561,7 @@ tpq_finish_kernel(const __grid_constant__ EdgeParams P, const __grid_constant__ 
   polish(K, st, b6);  // the minimiser on the final faces, from scratch
   finish<4>(P, R, q, st, grf, tau);
   tpq_store(io, rec, grf, tau, st.status, st.iters, st.word | 0x80000000u);
+  QPB_TL(3);
 }
 
 // ---- small batches: the three passes in ONE launch, one thread per record -------------------------------------------

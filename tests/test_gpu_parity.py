@@ -503,58 +503,6 @@ def test_both_kernel_mappings(built, params06, qps_per_warp, monkeypatch):
     solver.close()
 
 
-def test_overlapped_finishing_pass_gives_the_same_records(built, params06, monkeypatch):
-    """Default for cold three-pass batches: tpq_finish_kernel<IO, 2> is launched as a programmatic dependent of
-    tpq_loop_kernel<1, true> and takes its records from a queue of finished QPs while the loop's long QPs are still
-    running.  Only the ORDER in which records are finished changes: every output record must equal, bit for bit, what
-    three serial launches (QPB_TPQ_OVERLAP=0) write -- device-resident, through the host pipeline, at the iteration
-    limit, with bad inputs, for ragged sizes, in back-to-back calls on one stream and replayed from a CUDA graph."""
-    torch = _torch()
-    S = states.generate_states(150001, 608, profile="stress", masks="mixed")
-    S["contact"][:4096] = ((np.arange(4096)[:, None] % 16 >> np.arange(4)) & 1)
-    S["w"][77, 2] = np.nan
-    S["q"][13000, 5] = np.inf
-    p5 = params06.copy()
-    p5.max_iter = 5
-    n = 70001
-    d_in = torch.from_numpy(S[:n].view(np.uint8).reshape(-1).copy()).cuda()
-    d_out = torch.zeros(n * 256, dtype=torch.uint8, device="cuda")
-    monkeypatch.setenv("QPB_TPQ_OVERLAP", "0")
-    plain, plain5 = lib.BalanceSolver(params06), lib.BalanceSolver(p5)
-    want, want5 = plain.control_host(S), plain5.control_host(S)
-    plain.close(), plain5.close()
-    _compare(want, oracle.control_batch(params06, S, NCPU), 1e-7)
-    assert want["status"][77] == 2 and want["status"][13000] == 2 and (want5["status"] == 1).any()
-    monkeypatch.delenv("QPB_TPQ_OVERLAP")
-    solver, solver5 = lib.BalanceSolver(params06), lib.BalanceSolver(p5)
-    l0 = solver.launches
-    for lo in (0, 40000, 80000):  # back to back on one stream: every call has its own queue and ticket words
-        solver.control_packed(d_in if lo == 0 else torch.from_numpy(S[lo:lo + n].view(np.uint8).reshape(-1).copy()).cuda(), d_out, n)
-        torch.cuda.synchronize()
-        assert d_out.cpu().numpy().view(OUT_DTYPE).tobytes() == want[lo:lo + n].tobytes(), lo
-    assert solver.launches - l0 == 9
-    assert solver.control_host(S).tobytes() == want.tobytes()
-    assert solver5.control_host(S).tobytes() == want5.tobytes()
-    for m in (12288, 12289, 20000):
-        assert solver.control_host(S[:m]).tobytes() == want[:m].tobytes(), m
-    side = torch.cuda.Stream()
-    side.wait_stream(torch.cuda.current_stream())
-    with torch.cuda.stream(side):
-        solver.control_packed(d_in, d_out, n, side.cuda_stream)
-    side.synchronize()
-    graph = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(graph, stream=side):
-        solver.control_packed(d_in, d_out, n, side.cuda_stream)
-    for lo in (0, 80000, 0):
-        d_in.copy_(torch.from_numpy(S[lo:lo + n].view(np.uint8).reshape(-1).copy()).cuda())
-        d_out.zero_()
-        graph.replay()
-        torch.cuda.synchronize()
-        assert d_out.cpu().numpy().view(OUT_DTYPE).tobytes() == want[lo:lo + n].tobytes(), lo
-    del graph
-    solver.close(), solver5.close()
-
-
 def test_degenerate_and_extreme_parameter_regimes(built):
     """Active-set corner cases: pyramid apex (fzmin = 0, many linearly dependent rows), fzmin == fzmax,
     tiny and large friction, heavy robot saturating fzmax, strong regulariser."""
