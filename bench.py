@@ -391,6 +391,29 @@ def secondary_block(solver, params, rank, world, local_rank, dev, dist, barrier)
         entry["max_rel_grf_err_vs_oracle"] = float((np.abs(res[::stride]["grf_body"] - ref["grf_body"]).max(axis=1) /
                                                     np.maximum(np.abs(ref["grf_body"]).max(axis=1), 1.0)).max())
     out["cfg2_warm_tick"] = entry
+    if world > 1:
+        # SURVEY.md 8e, optional: a single consumer wants every shard's results -- one NCCL all-gather of the 200-B result
+        # records (forces, torques, status, iteration count: the first 200 bytes of qpb_out_rec) over NVLink / NVSwitch,
+        # timed by itself.  Not part of the hot path (no QP waits for another rank) and not in `value`.
+        try:
+            from quadruped_control_b200.sharding import gather_outputs
+
+            local = d_out.view(n, OUT_DTYPE.itemsize)[:, :200].contiguous()
+            whole = torch.empty(world * local.numel(), dtype=torch.uint8, device=dev)
+            ms = timed(lambda: gather_outputs(local, dist, whole), 5)
+            sums = torch.stack([local.sum(dtype=torch.int64), torch.zeros((), dtype=torch.int64, device=dev)])
+            dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+            mine = whole[rank * local.numel():(rank + 1) * local.numel()]
+            ok = bool(torch.equal(mine, local.reshape(-1))) and int(whole.sum(dtype=torch.int64)) == int(sums[0])
+            recv = (world - 1) * local.numel()
+            out["allgather_outputs"] = {
+                "what": "torch.distributed.all_gather_into_tensor (NCCL) of 200-B result records, cfg2 shard of every rank -> every rank",
+                "bytes_received_per_rank": recv, "ms_per_call": ms, "calls": 5, "gbs_received_per_rank": recv / (ms * 1e-3) / 1e9,
+                "nvlink_peak_gbs_per_direction": 900.0, "frac": recv / (ms * 1e-3) / 1e9 / 900.0,
+                "peak_source": "nominal NVLink 5 figure (no measured peer bandwidth in MEASURED_PEAKS.json)",
+                "gathered_equals_shards": ok}
+        except Exception as exc:  # never lose the bench line to the optional leg
+            out["allgather_outputs"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
     del d_in, d_out, S
     # cfg4: the 10-step convex-MPC QP
     mp = default_mpc_params(MU)

@@ -16,7 +16,7 @@ for N in ${NLIST:-1 2 4 8}; do
 import json,sys
 try:
     d=json.loads([l for l in open(sys.argv[1]).read().splitlines() if l.startswith('{')][-1]); e=d['e2e']
-    print(f"N={d['n_gpus']}: value {d['value']:.3e}  e2e {e['value']:.3e} (sync {e['sync_call_value']:.3e})  pcie bound {e['pcie_bound_qps']:.3e} = {e['pcie_bound_gbs']:.0f} GB/s  frac {e['pcie_frac']:.2f}  secondary "+", ".join(f"{k} {v['value']:.3e}" for k,v in (d.get('secondary') or {}).items()))
+    print(f"N={d['n_gpus']}: value {d['value']:.3e}  e2e {e['value']:.3e} (sync {e['sync_call_value']:.3e})  pcie bound {e['pcie_bound_qps']:.3e} = {e['pcie_bound_gbs']:.0f} GB/s  frac {e['pcie_frac']:.2f}  secondary "+", ".join(f"{k} {v['value']:.3e}" for k,v in (d.get('secondary') or {}).items() if 'value' in v), (d.get('secondary') or {}).get('allgather_outputs'))
 except Exception as ex:
     print(sys.argv[1], 'ERR', ex)
 PY
