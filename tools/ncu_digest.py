@@ -70,7 +70,10 @@ for r in csv.reader(io.StringIO(src)):
     op = tk[1] if tk and tk[0].startswith("@") else (tk[0] if tk else "?")
     ops[op.split(".")[0]] += inst
 tot = sum(per.values()); ts = sum(samp.values())
-print(f"\nwarp instructions executed / QP: {tot/nq:.1f}   (stall samples {ts})")
+# (tot sums the source view, which lists an instruction of an inlined function under every file of its inline stack that has
+# line information -- 5-20 % above the hardware counter smsp__inst_executed.sum printed with the headline metrics, which is the
+# figure the documents quote; shares per function are what this table is for)
+print(f"\nwarp instructions executed / QP: {tot/nq:.1f} summed over the source view (hardware count: smsp__inst_executed.sum / QPs, above)   (stall samples {ts})")
 print("  inst/QP  inst%  stall%  lanes  function")
 for fn, c in per.most_common(40):
     if c / nq >= 1.0:
