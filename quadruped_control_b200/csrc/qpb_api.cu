@@ -66,8 +66,6 @@ constexpr int64_t kMaxRecordsPerLaunch = (int64_t)1 << 31;  // the kernels index
 constexpr uint32_t kTicketSlots = 4096;  // ring of {work counter, CTAs finished} pairs; the kernels re-arm their own pair
 constexpr int64_t kSmallCall = 128;      // host calls up to this many robots go through one pinned, mapped staging block
 constexpr int64_t kTpqChunk = (int64_t)1 << 20;  // records per set-up / loop / finish triple (512 MiB of scratch)
-// scratch of the three-pass path beside the prepared record: result word, place on the worklist, place on the second worklist
-constexpr size_t kTpqSideBytes = sizeof(double) + 2 * sizeof(uint32_t);
 constexpr size_t kSmallFlagsOff = (size_t)kSmallCall * 1536;  // states + results + swing records (or the kinematics arrays)
 constexpr size_t kSmallBytes = kSmallFlagsOff + (size_t)kSmallCall * sizeof(uint32_t);  // + one completion word per record
 
@@ -84,11 +82,8 @@ struct qpb_handle {
   // 1 = balance_qp_kernel (one warp per QP, north_star's literal mapping).  QPB_QPS_PER_WARP=1|2|32 in the environment
   // at qpb_create time overrides the choice (32 is refused when the parameters do not qualify).
   int qps_per_warp = 2;
-  int ctas_per_sm_tpq[5] = {};  // indexed by lanes per QP (1, 2, 4); [0]: the four-lane build of the second loop launch
+  int ctas_per_sm_tpq[5] = {};  // indexed by lanes per QP (1, 2, 4)
   int tpq_lpq = 1;              // lanes per QP of the range-space loop kernel (QPB_TPQ_LPQ=1|2|4 overrides)
-  int tpq_hand_cap = 0;         // > 0: the one-thread-per-QP loop hands QPs that have spent this many working-set changes on to a
-                                // second loop launch at four lanes per QP (QPB_TPQ_HAND; qpb_tpq.cuh, tpq_loop_kernel<1, true>)
-  int tpq_hand_tail = 1;        // that second launch: the 255-register build (1) or the occupancy build of QPB_TPQ_LPQ=4 (0) (QPB_TPQ_HAND_TAIL)
   int64_t tpq_min_n = 12288;    // smaller batches take a one-launch kernel: lower latency (QPB_TPQ_MIN_N)
   int64_t tpq_one_max = 1;      // ... up to here the range-space one (tpq_one_kernel), above it the half-warp kernel (QPB_TPQ_ONE_MAX)
   int warm_batches = 0;         // device-resident calls: the records carry warm-start words (qpb_set_warm_batches)
@@ -194,10 +189,9 @@ int launch_balance(qpb_handle* h, const IO& io, int64_t n, int ctas_per_sm, cuda
         double* prep = scratch;  // m prepared records, m result words, the worklist of the loop pass (m record indices)
         const size_t prep_bytes = (size_t)m * qpb::tpq::kPrepSize * sizeof(double);
         if (!scratch)  // (the host pipeline brings its own: one block per stage slot, n <= kHostChunkMax)
-          QPB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&prep), prep_bytes + (size_t)m * kTpqSideBytes, s));
+          QPB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&prep), prep_bytes + (size_t)m * (sizeof(double) + sizeof(uint32_t)), s));
         double* res = prep + (size_t)m * qpb::tpq::kPrepSize;
         uint32_t* work = reinterpret_cast<uint32_t*>(res + m);
-        uint32_t* work2 = work + m;  // QPs the first loop launch hands on to the second
         const uint32_t slot2 = first_chain ? slot : h->ticket_slot.fetch_add(1, std::memory_order_relaxed) % kTicketSlots;
         first_chain = false;
         unsigned long long* tk = h->d_tickets + 4 * (size_t)slot2;
@@ -211,20 +205,7 @@ int launch_balance(qpb_handle* h, const IO& io, int64_t n, int ctas_per_sm, cuda
         const int64_t want = (m * lpq + lthreads - 1) / lthreads;
         const int64_t cap = (int64_t)h->num_sms * h->ctas_per_sm_tpq[lpq];
         const int grid = (int)(want < cap ? want : cap);
-        const bool hand = lpq == 1 && h->tpq_hand_cap > 0;
-        if (hand) {
-          // long QPs go on to a second launch at four lanes per QP (its grid cannot know how many there are: CTAs that
-          // find the second worklist empty leave at once)
-          unsigned long long* tk2 = h->d_tickets + 4 * (size_t)(h->ticket_slot.fetch_add(1, std::memory_order_relaxed) % kTicketSlots);
-          qpb::tpq::tpq_loop_kernel<1, true><<<grid, lthreads, 0, s>>>(h->fast, prep, res, work, tk, h->tpq_hand_cap, work2, tk2);
-          const int t4 = qpb::tpq::LoopShape<4>::THREADS;
-          const int64_t want4 = (m * 4 + t4 - 1) / t4, cap4 = (int64_t)h->num_sms * (h->tpq_hand_tail ? h->ctas_per_sm_tpq[0] : h->ctas_per_sm_tpq[4]);
-          if (h->tpq_hand_tail)
-            qpb::tpq::tpq_loop_kernel<4, false, true><<<(int)(want4 < cap4 ? want4 : cap4), t4, 0, s>>>(h->fast, prep, res, work2, tk2);
-          else
-            qpb::tpq::tpq_loop_kernel<4><<<(int)(want4 < cap4 ? want4 : cap4), t4, 0, s>>>(h->fast, prep, res, work2, tk2);
-          h->launches.fetch_add(1, std::memory_order_relaxed);
-        } else if (lpq == 1)
+        if (lpq == 1)
           qpb::tpq::tpq_loop_kernel<1><<<grid, lthreads, 0, s>>>(h->fast, prep, res, work, tk);
         else if (lpq == 2)
           qpb::tpq::tpq_loop_kernel<2><<<grid, lthreads, 0, s>>>(h->fast, prep, res, work, tk);
@@ -437,7 +418,7 @@ int host_pipeline(qpb_handle* h, int64_t n, const qpb_state_rec* h_states, const
     if (wire && !h->d_win[s]) QPB_CUDA(cudaMalloc(&h->d_win[s], kHostChunkMax * sizeof(qpb_wire_state)));
     if (wire && !h->d_wout[s]) QPB_CUDA(cudaMalloc(&h->d_wout[s], kHostChunkMax * sizeof(qpb_wire_out)));
     if (range_space && !h->d_scratch[s])
-      QPB_CUDA(cudaMalloc(&h->d_scratch[s], kHostChunkMax * (qpb::tpq::kPrepSize * sizeof(double) + kTpqSideBytes)));
+      QPB_CUDA(cudaMalloc(&h->d_scratch[s], kHostChunkMax * (qpb::tpq::kPrepSize * sizeof(double) + sizeof(double) + sizeof(uint32_t))));
   }
   // Stages of records are uploaded, solved and downloaded on a ring of streams, so the copy engines and the SMs overlap.
   // One-launch kernels: stage sizes halve towards the end of the batch so the last kernel + download (the part that
@@ -640,7 +621,6 @@ int qpb_create(const qpb_params* params, int device, qpb_handle** out) {
   if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->ctas_per_sm_tpq[1], qpb::tpq::tpq_loop_kernel<1>, qpb::tpq::LoopShape<1>::THREADS, 0);
   if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->ctas_per_sm_tpq[2], qpb::tpq::tpq_loop_kernel<2>, qpb::tpq::LoopShape<2>::THREADS, 0);
   if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->ctas_per_sm_tpq[4], qpb::tpq::tpq_loop_kernel<4>, qpb::tpq::LoopShape<4>::THREADS, 0);
-  if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->ctas_per_sm_tpq[0], qpb::tpq::tpq_loop_kernel<4, false, true>, qpb::tpq::LoopShape<4>::THREADS, 0);
   if (e == cudaSuccess && qpb::tpq::StageIn<qpb::PackedIO>::on) {
     e = cudaFuncSetAttribute(qpb::tpq::tpq_setup_kernel<qpb::PackedIO, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qpb::tpq::kSetupStageBytes);
     if (e == cudaSuccess)
@@ -678,11 +658,6 @@ int qpb_create(const qpb_params* params, int device, qpb_handle** out) {
     const int v = std::atoi(env);
     if (v == 1 || v == 2 || v == 4) h->tpq_lpq = v;
   }
-  if (const char* env = std::getenv("QPB_TPQ_HAND")) {
-    const int v = std::atoi(env);
-    if (v >= 0 && v < 65536) h->tpq_hand_cap = v;
-  }
-  if (const char* env = std::getenv("QPB_TPQ_HAND_TAIL")) h->tpq_hand_tail = std::atoi(env) != 0;
   if (const char* env = std::getenv("QPB_TPQ_MIN_N")) {
     const long long v = std::atoll(env);
     if (v >= 0) h->tpq_min_n = v;

@@ -97,10 +97,8 @@ __device__ __forceinline__ void group_min_ratio(double& ub, double& rb, int& kb)
 
 // One working-set change for every QP the warp holds, then the choice of the next row (or the end of the solve: nothing
 // is violated any more).  Every QP enters with its row already chosen -- the first one by the set-up pass.
-// Returns whether a NEW row has just been chosen (nothing of the previous one is pending: the state of the QP is then
-// f, u, G, the working set and that row -- exactly what a prepared record holds).
 template <int LPQ>
-__device__ __forceinline__ bool iterate_group(const FastParams& K, Lane<4 / LPQ>& ln, int j, double* side) {
+__device__ __forceinline__ void iterate_group(const FastParams& K, Lane<4 / LPQ>& ln, int j, double* side) {
   constexpr int LPL = 4 / LPQ;
   StepTmp<LPL> T;
   double ub, rb;
@@ -112,7 +110,6 @@ __device__ __forceinline__ bool iterate_group(const FastParams& K, Lane<4 / LPQ>
   bool fresh;
   const double slack = group_sum<LPQ>(select_commit<LPL>(K, ln, j, best, fresh));
   if (fresh) ln.sp = slack;
-  return fresh;
 }
 
 // meta word of a prepared record.  low: working set (24) | stance (4) | status (2).  high: working-set changes so far
@@ -121,23 +118,6 @@ __device__ __forceinline__ double pack_meta(uint32_t word, uint32_t stance, int 
   const uint32_t lo = word | (stance << 24) | ((uint32_t)status << 28);
   const uint32_t hi = ((uint32_t)iters & 0xffffu) | ((key & 31u) << 16) | ((key >> 31) << 21);
   return __hiloint2double((int)hi, (int)lo);
-}
-
-// A QP that has just chosen its next row, back into its prepared record (the lever arms and the right-hand side are
-// still there): the loop kernel's refill reads it exactly as it reads a record of the set-up pass.
-template <int LPL>
-__device__ __forceinline__ void hand_on(const Lane<LPL>& ln, const double* side, double* e) {
-  static_assert(LPL == 4, "a lane that holds all four legs");
-  double2* o = reinterpret_cast<double2*>(e);
-#pragma unroll
-  for (int i = 0; i < 6; i++) {
-    o[kPrepF / 2 + i] = make_double2(ln.f[2 * i], ln.f[2 * i + 1]);
-    o[kPrepU / 2 + i] = make_double2(ln.u[2 * i], ln.u[2 * i + 1]);
-  }
-#pragma unroll
-  for (int i = 0; i < 10; i++) o[kPrepG / 2 + i] = make_double2(side[kSideG + 2 * i], side[kSideG + 2 * i + 1]);
-  const uint32_t key = 0x80000000u | (ln.pc == 2u ? 16u : 0u) | (uint32_t)ln.p;
-  o[kPrepG / 2 + 10] = make_double2(side[kSideG + 20], pack_meta(ln.word, ln.stance, ln.status, ln.iters, key));
 }
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
@@ -408,24 +388,10 @@ tpq_setup_kernel(const __grid_constant__ EdgeParams P, const __grid_constant__ F
 // global memory on the spot (profiles/r02_ncu_tpq_v4_loop_cfg3_digest.txt: long-scoreboard stalls 1.96 per issue).
 
 
-//
-// HAND (one thread per QP only): long QPs are handed on.  Most QPs of a cold batch end within a few working-set changes,
-// a few need 25-30 (config 2: 8 % take more than ten trips) -- and once the worklist has run dry the pass lasts as long
-// as its longest QP, iterated on by ONE lane of a warp whose other lanes have nothing left to do.  So a QP that has
-// spent hand_cap changes and has just chosen its next row is written back into its prepared record (f, u, G, working
-// set, that row: the record is again what the set-up pass would have written for a QP standing there) and its number
-// goes on a second worklist (work2, counted in ticket2[2]); a second launch of this kernel at FOUR lanes per QP -- about
-// half the instructions per trip on the critical path of a QP, and one QP keeps four lanes busy instead of one -- takes
-// the loop up from there.  Same arithmetic, same iterates: one, two and four lanes per QP only share out the legs
-// (tests/test_tpq_host.py::test_handing_a_qp_on_changes_nothing, tests/test_gpu_parity.py).
-// TAIL: the build for that second launch -- few QPs, every one of them on the critical path of the batch, so it is
-// compiled for 255 registers (no spills) instead of occupancy.
-template <int LPQ, bool HAND = false, bool TAIL = false>
-__global__ void __launch_bounds__(LoopShape<LPQ>::THREADS, TAIL ? 2 : LoopShape<LPQ>::MIN_CTAS)
-tpq_loop_kernel(const __grid_constant__ FastParams K, double* prep, double* __restrict__ res,
-                const uint32_t* __restrict__ work, unsigned long long* __restrict__ ticket, int hand_cap = 0,
-                uint32_t* __restrict__ work2 = nullptr, unsigned long long* __restrict__ ticket2 = nullptr) {
-  static_assert(!HAND || LPQ == 1, "only the one-thread-per-QP loop hands QPs on");
+template <int LPQ>
+__global__ void __launch_bounds__(LoopShape<LPQ>::THREADS, LoopShape<LPQ>::MIN_CTAS)
+tpq_loop_kernel(const __grid_constant__ FastParams K, const double* __restrict__ prep, double* __restrict__ res,
+                const uint32_t* __restrict__ work, unsigned long long* __restrict__ ticket) {
   constexpr int LPL = 4 / LPQ, NS = 32 / LPQ;  // legs per lane, QP slots per warp
   constexpr int STAGE = LoopShape<LPQ>::STAGE, kLoopThreads = LoopShape<LPQ>::THREADS;
   QPB_TL(0);
@@ -528,24 +494,8 @@ tpq_loop_kernel(const __grid_constant__ FastParams K, double* prep, double* __re
         continue;
       }
     }
-    const bool fresh = iterate_group<LPQ>(K, ln, j, side);
+    iterate_group<LPQ>(K, ln, j, side);
     __syncwarp();  // G written by the first lane of a QP is read by its other lanes in the next round
-    if constexpr (HAND) {
-      const bool out = have && !ln.done && fresh && ln.iters >= hand_cap;
-      const uint32_t mo = __ballot_sync(FULL, out);
-      if (mo) {  // one atomic per warp for the places on the second worklist
-        const int first = __ffs(mo) - 1;
-        unsigned long long b = 0;
-        if (lane == first) b = atomicAdd(ticket2 + 2, (unsigned long long)__popc(mo));
-        b = __shfl_sync(FULL, b, first);
-        if (out) {
-          hand_on<LPL>(ln, side, prep + rec * kPrepSize);
-          work2[b + __popc(mo & ((1u << lane) - 1u))] = (uint32_t)rec;
-          have = false;
-          ln.done = true;
-        }
-      }
-    }
   }
   // The last CTA out re-arms the work counter: the launch is self-contained, so the same counter slot serves graph
   // replays and later launches without a memset (ticket[0] = work counter, ticket[1] = CTAs finished).

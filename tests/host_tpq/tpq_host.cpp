@@ -10,12 +10,8 @@
 
 using namespace qpb::tpq;
 
-// hand_cap > 0 (LPQ = 1): the kernel's hand-on -- a QP that has spent hand_cap working-set changes and has just chosen
-// its next row leaves the loop; its state goes into `handed` in the layout of a prepared record (what hand_on() in
-// qpb_tpq.cuh writes: f, u, G, working set, iteration count, that row) and true is returned.
 template <int LPQ>
-static bool solve_loop(const FastParams& K, State& st, const double* G0, uint32_t key, int hand_cap = 0, double* handed = nullptr,
-                       uint32_t* handed_key = nullptr) {
+static void solve_loop(const FastParams& K, State& st, const double* G0, uint32_t key) {
   constexpr int LPL = 4 / LPQ;
   double side[kSideSize] = {};
   std::memcpy(side + kSideG, G0, 21 * sizeof(double));
@@ -60,37 +56,14 @@ static bool solve_loop(const FastParams& K, State& st, const double* G0, uint32_
     for (int j = 0; j < LPQ; j++) s2 += select_commit(K, ln[j], j, best, fresh[j]);
     for (int j = 0; j < LPQ; j++)
       if (fresh[j]) ln[j].sp = s2;
-    if (LPQ == 1 && hand_cap > 0 && !ln[0].done && fresh[0] && ln[0].iters >= hand_cap) {
-      for (int i = 0; i < 3 * LPL; i++) {
-        handed[kPrepF + i] = ln[0].f[i];
-        handed[kPrepU + i] = ln[0].u[i];
-      }
-      std::memcpy(handed + kPrepG, G, 21 * sizeof(double));
-      *handed_key = 0x80000000u | (ln[0].pc == 2u ? 16u : 0u) | (uint32_t)ln[0].p;
-      st.word = ln[0].word;
-      st.status = ln[0].status;
-      st.iters = ln[0].iters;
-      return true;
-    }
   }
   st.word = ln[0].word;
   st.status = ln[0].status;
   st.iters = ln[0].iters;
-  return false;
 }
 
-extern "C" int tpq_host_control_batch_hand(const qpb_params* P, const qpb_state_rec* in, int64_t n, qpb_out_rec* out, int lpq,
-                                           int do_polish, int hand_cap, int64_t* handed_count);
 extern "C" int tpq_host_control_batch(const qpb_params* P, const qpb_state_rec* in, int64_t n, qpb_out_rec* out,
                                       int lpq /* lanes per QP: 1, 2 or 4 */, int do_polish) {
-  return tpq_host_control_batch_hand(P, in, n, out, lpq, do_polish, 0, nullptr);
-}
-
-// hand_cap > 0: one lane per QP up to hand_cap working-set changes, the rest of the loop at four lanes per QP from the
-// handed-on record (the two launches of the kernel path under QPB_TPQ_HAND); *handed_count = QPs that were handed on.
-extern "C" int tpq_host_control_batch_hand(const qpb_params* P, const qpb_state_rec* in, int64_t n, qpb_out_rec* out, int lpq,
-                                           int do_polish, int hand_cap, int64_t* handed_count) {
-  int64_t handed_n = 0;
   FastParams K;
   if (!make_fast_params(*P, K)) return -1;
   for (int64_t i = 0; i < n; i++) {
@@ -110,17 +83,7 @@ extern "C" int tpq_host_control_batch_hand(const qpb_params* P, const qpb_state_
     st = keep;  // the loop starts from the last dual-feasible pair the set-up committed
     std::memcpy(G, Gkeep, sizeof(G));
     if (st.status == QPB_OK && key != 0u) {  // the set-up's pair is not optimal yet: the loop (the kernel's worklist)
-      if (hand_cap > 0) {
-        double e[kPrepSize] = {};
-        uint32_t key2 = 0;
-        if (solve_loop<1>(K, st, G, key, hand_cap, e, &key2)) {
-          handed_n++;
-          // the second launch reads f, u, G from the record; working set, status and count travel in its meta word
-          std::memcpy(st.f, e + kPrepF, sizeof(st.f));
-          std::memcpy(st.u, e + kPrepU, sizeof(st.u));
-          solve_loop<4>(K, st, e + kPrepG, key2);
-        }
-      } else if (lpq == 4) solve_loop<4>(K, st, G, key);
+      if (lpq == 4) solve_loop<4>(K, st, G, key);
       else if (lpq == 2) solve_loop<2>(K, st, G, key);
       else solve_loop<1>(K, st, G, key);
     }
@@ -135,6 +98,5 @@ extern "C" int tpq_host_control_batch_hand(const qpb_params* P, const qpb_state_
     const uint32_t word = st.word | 0x80000000u;
     std::memcpy(out[i].pad, &word, 4);
   }
-  if (handed_count) *handed_count = handed_n;
   return 0;
 }

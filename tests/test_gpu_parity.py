@@ -503,80 +503,6 @@ def test_both_kernel_mappings(built, params06, qps_per_warp, monkeypatch):
     solver.close()
 
 
-def _same_solves(got, want, tol=1e-9):
-    """Two kernel paths that run the same iterates: equal statuses, results equal to rounding, and -- bar a handful of QPs
-    where the instantiations round a near-tie differently -- equal working sets and iteration counts."""
-    assert np.array_equal(got["status"], want["status"])
-    assert rel_err(got["grf_body"], want["grf_body"]) <= tol and rel_err(got["tau"], want["tau"]) <= tol
-    same = (got["iters"] == want["iters"]) & (got["pad"][:, :4] == want["pad"][:, :4]).all(axis=1)
-    assert same.mean() >= 0.999, same.mean()
-
-
-@pytest.mark.parametrize("cap,tail", [("1", "1"), ("4", "1"), ("10", "1"), ("4", "0")])
-def test_long_qps_handed_on_to_a_second_loop_launch(built, params06, monkeypatch, cap, tail):
-    """QPB_TPQ_HAND: the one-lane loop writes a QP that has spent `cap` working-set changes back into its prepared record
-    and a second launch of the loop kernel at four lanes per QP takes it up (tpq_loop_kernel<1, true> -> <4>).  Same
-    iterates (tests/test_tpq_host.py checks that to the bit on the host build): statuses, working sets, iteration counts
-    and results must be those of the single-launch loop -- cold, warm-started, at the iteration limit, and when the call
-    is replayed from a CUDA graph."""
-    torch = _torch()
-    monkeypatch.setenv("QPB_TPQ_MIN_N", "0")
-    S = states.generate_states(40001, 607, profile="stress", masks="mixed")
-    S["contact"][:4096] = ((np.arange(4096)[:, None] % 16 >> np.arange(4)) & 1)
-    S["w"][77, 2] = np.nan
-    p5 = params06.copy()
-    p5.max_iter = 5
-    n = 30000
-    d_in = torch.from_numpy(S[:n].view(np.uint8).reshape(-1).copy()).cuda()
-    d_out = torch.zeros(n * 256, dtype=torch.uint8, device="cuda")
-    monkeypatch.setenv("QPB_TPQ_HAND", "0")
-    plain, plain5 = lib.BalanceSolver(params06), lib.BalanceSolver(p5)
-    want, want5 = plain.control_host(S), plain5.control_host(S)
-    l0 = plain.launches
-    plain.control_packed(d_in, d_out, n)
-    torch.cuda.synchronize()
-    assert plain.launches - l0 == 3
-    W = S.copy()
-    W["pad"][:, :4] = want["pad"][:, :4]
-    W["x"] += 0.01
-    want_w = plain.control_host(W)
-    plain.close(), plain5.close()
-    ref = oracle.control_batch(params06, S, NCPU)
-    _compare(want, ref, 1e-7)
-    assert (want["iters"] > int(cap) + 2).sum() > 100  # QPs that will in fact be handed on
-    monkeypatch.setenv("QPB_TPQ_HAND", cap)
-    monkeypatch.setenv("QPB_TPQ_HAND_TAIL", tail)
-    solver, solver5 = lib.BalanceSolver(params06), lib.BalanceSolver(p5)
-    l0 = solver.launches
-    solver.control_packed(d_in, d_out, n)
-    torch.cuda.synchronize()
-    assert solver.launches - l0 == 4  # set-up, loop, second loop, finish
-    _same_solves(d_out.cpu().numpy().view(OUT_DTYPE), want[:n])
-    got = solver.control_host(S)
-    _same_solves(got, want)
-    _compare(got, ref, 1e-7)
-    _same_solves(solver.control_host(W), want_w)
-    got5 = solver5.control_host(S)
-    assert (got5["status"] == 1).any() and (got5["status"] != want5["status"]).mean() <= 1e-3
-    # graph replay: both loop launches re-arm their own ticket words
-    side = torch.cuda.Stream()
-    side.wait_stream(torch.cuda.current_stream())
-    with torch.cuda.stream(side):
-        solver.control_packed(d_in, d_out, n, side.cuda_stream)
-    side.synchronize()
-    graph = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(graph, stream=side):
-        solver.control_packed(d_in, d_out, n, side.cuda_stream)
-    for lo in (0, 10001, 0):
-        d_in.copy_(torch.from_numpy(S[lo:lo + n].view(np.uint8).reshape(-1).copy()).cuda())
-        d_out.zero_()
-        graph.replay()
-        torch.cuda.synchronize()
-        assert d_out.cpu().numpy().view(OUT_DTYPE).tobytes() == got[lo:lo + n].tobytes(), lo
-    del graph
-    solver.close(), solver5.close()
-
-
 def test_degenerate_and_extreme_parameter_regimes(built):
     """Active-set corner cases: pyramid apex (fzmin = 0, many linearly dependent rows), fzmin == fzmax,
     tiny and large friction, heavy robot saturating fzmax, strong regulariser."""

@@ -28,17 +28,10 @@ def host():
         subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", LIB, SRC], check=True)
     L = ctypes.CDLL(LIB)
     L.tpq_host_control_batch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
-    L.tpq_host_control_batch_hand.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int,
-                                              ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int64)]
 
-    def run(params, S, lpq=2, polish=1, hand_cap=0):
+    def run(params, S, lpq=2, polish=1):
         S = np.ascontiguousarray(S)
         out = np.zeros(len(S), dtype=OUT_DTYPE)
-        if hand_cap:
-            handed = ctypes.c_int64(0)
-            rc = L.tpq_host_control_batch_hand(ctypes.byref(params), S.ctypes.data, len(S), out.ctypes.data, lpq, polish, hand_cap,
-                                               ctypes.byref(handed))
-            return rc, out, handed.value
         rc = L.tpq_host_control_batch(ctypes.byref(params), S.ctypes.data, len(S), out.ctypes.data, lpq, polish)
         return rc, out
 
@@ -72,28 +65,6 @@ def test_lanes_per_qp_are_the_same_algorithm(host, params06):
         assert o.tobytes() == outs[0].tobytes()
     _check(host, params06, S, 1e-7, lpq=4)
     _check(host, params06, S, 1e-7, lpq=1)
-
-
-@pytest.mark.parametrize("cap", [1, 3, 8, 12])
-def test_handing_a_qp_on_changes_nothing(host, params06, cap):
-    """The kernel path can hand long QPs on from the one-lane loop to a second launch at four lanes per QP
-    (tpq_loop_kernel<1, true> -> tpq_loop_kernel<4>): the QP is written back in the layout of a prepared record at a point
-    where nothing is pending (its next row just chosen) and taken up from there.  Same iterates, so the results, working
-    sets and iteration counts must be identical to the bit -- whatever the hand-on point."""
-    S = states.generate_states(4000, 20260103, profile="stress", masks="mixed")
-    W = S.copy()
-    ref = host(params06, S, 1)[1]
-    rc, out, handed = host(params06, S, 1, hand_cap=cap)
-    assert rc == 0 and out.tobytes() == ref.tobytes()
-    assert 0 < handed <= (ref["iters"] >= cap).sum()
-    if cap >= 8:
-        assert handed < len(S) // 2
-    # warm-started records (last tick's working sets) rarely reach the cap; those that do are handed on the same way
-    W["pad"][:, :4] = ref["pad"][:, :4]
-    W["x"] += 0.02
-    refw = host(params06, W, 1)[1]
-    rc, outw, _ = host(params06, W, 1, hand_cap=cap)
-    assert rc == 0 and outw.tobytes() == refw.tobytes()
 
 
 def test_core_config1_and_every_contact_mask(host, params06, params08):

@@ -1,6 +1,5 @@
 """One small run of EVERY kernel family for compute-sanitizer (tests/test_sanitizer_gpu.py drives it with memcheck and
-racecheck): the range-space path (set-up / loop / finish, one, two and four lanes per QP, long QPs handed on to a second
-loop launch, cold and warm-started, ragged
+racecheck): the range-space path (set-up / loop / finish, one, two and four lanes per QP, cold and warm-started, ragged
 sizes), the half-warp and one-warp-per-QP kernels, the argument-per-array entry point, the asynchronous host pipeline,
 the whole tick (swing legs), planner / adapters / torque command with both record alignments, the MPC kernel, and the
 single-process multi-device calls.  Batches are a few hundred records: the sanitizer runs kernels ~50x slower."""
@@ -31,11 +30,8 @@ def dev(a, shift=0):
 
 
 ref = None
-# (kernel mapping, lanes per QP of the loop, hand-on of long QPs after that many changes [0: none], build of the second loop launch)
-for mode, lpq, hand, tail in (("32", "1", "0", "1"), ("32", "1", "3", "1"), ("32", "1", "1", "0"), ("32", "2", "0", "1"), ("32", "4", "0", "1"),
-                              ("2", "1", "0", "1"), ("1", "1", "0", "1")):
+for mode, lpq in (("32", "1"), ("32", "2"), ("32", "4"), ("2", "1"), ("1", "1")):
     os.environ["QPB_QPS_PER_WARP"], os.environ["QPB_TPQ_LPQ"] = mode, lpq
-    os.environ["QPB_TPQ_HAND"], os.environ["QPB_TPQ_HAND_TAIL"] = hand, tail
     sol = lib.BalanceSolver(params)
     out = sol.control_host(S)
     assert list(np.nonzero(out["status"])[0]) == [3, 5]
@@ -67,7 +63,7 @@ for mode, lpq, hand, tail in (("32", "1", "0", "1"), ("32", "1", "3", "1"), ("32
     for b in [pin_i] + pin_o:
         b.free()
     sol.close()
-del os.environ["QPB_QPS_PER_WARP"], os.environ["QPB_TPQ_LPQ"], os.environ["QPB_TPQ_HAND"], os.environ["QPB_TPQ_HAND_TAIL"]
+del os.environ["QPB_QPS_PER_WARP"], os.environ["QPB_TPQ_LPQ"]
 
 sol = lib.BalanceSolver(params)
 for m, shift in ((300, 0), (300, 16), (19, 0)):  # record kernels: both alignments, full tiles and the tail
