@@ -423,6 +423,35 @@ def test_full_size_config3_properties(solver06, params06):
     _compare(np.ascontiguousarray(out[idx]), ref)
 
 
+def test_full_size_config5_every_shard(solver06, params06):
+    """BASELINE config 5 (8 388 608 mixed-contact states over 8 GPUs): the eight shards exactly as the ranks of
+    `bench.py --gpus 8` generate them (record r * 1 048 576 + i of stream 20260105 on rank r), solved one after the other
+    on this GPU: every status 0, every returned force inside its friction pyramid and normal-force bounds, swing legs zero,
+    and oracle parity on a strided sample of each shard -- the whole configuration at size, not a prefix of it."""
+    torch = _torch()
+    n, mu, tol = 1048576, 0.6, 1e-6
+    d_out = torch.empty(n * 256, dtype=torch.uint8, device="cuda")
+    worst = 0.0
+    for r in range(8):
+        S = states.generate_states(n, 20260105, lo=r * n, masks="mixed")
+        d_in = torch.from_numpy(S.view(np.uint8).reshape(-1)).cuda()
+        solver06.control_packed(d_in, d_out, n)
+        torch.cuda.synchronize()
+        out = d_out.cpu().numpy().view(OUT_DTYPE)
+        assert (out["status"] == 0).all(), r
+        fw = -np.einsum("nij,nlj->nli", S["Rwb"].reshape(n, 3, 3), out["grf_body"].reshape(n, 4, 3))
+        st = S["contact"] != 0
+        fz = fw[..., 2]
+        assert (np.abs(fw[..., 0]) <= mu * fz + tol)[st].all() and (np.abs(fw[..., 1]) <= mu * fz + tol)[st].all(), r
+        assert (fz[st] >= 10.0 - tol).all() and (fz[st] <= 120.0 + tol).all(), r
+        assert not out["grf_body"].reshape(n, 4, 3)[~st].any() and not out["tau"].reshape(n, 4, 3)[~st].any(), r
+        idx = np.arange(r, n, 257)
+        ref = oracle.control_batch(params06, np.ascontiguousarray(S[idx]), NCPU)
+        worst = max(worst, _compare(np.ascontiguousarray(out[idx]), ref)[0])
+        del d_in, S
+    assert worst <= 1e-7, worst
+
+
 def test_kinematics_entry_points(solver06, params06):
     rng = np.random.default_rng(11)
     n = 1000
