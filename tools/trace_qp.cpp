@@ -34,3 +34,21 @@ extern "C" int trace_one(const qpb_params* P, const qpb_state_rec* in, int verbo
   if (verbose) printf("final word=%06x nact=%d iters=%d\n", ln.word, __builtin_popcount(ln.word), ln.iters);
   return ln.iters;
 }
+
+// working-set changes spent by the set-up pass (block rounds) and in total, for n records, without printing
+extern "C" void trace_counts(const qpb_params* P, const qpb_state_rec* in, int64_t n, int* setup_rounds, int* total) {
+  FastParams K;
+  make_fast_params(*P, K);
+  for (int64_t q = 0; q < n; q++) {
+    const double* rec = reinterpret_cast<const double*>(in + q);
+    uint32_t cbytes;
+    memcpy(&cbytes, in[q].contact, 4);
+    State st, keep;
+    double b6[6], G[21];
+    uint32_t key = 0;
+    auto commit = [&](const State& s, const double (&)[21], uint32_t k) { keep = s; key = k; };
+    setup(*P, K, rec, cbytes, 0u, st, b6, G, commit);
+    setup_rounds[q] = keep.iters;
+    total[q] = key ? trace_one(P, in + q, 0) : keep.iters;
+  }
+}
