@@ -84,6 +84,8 @@ struct qpb_handle {
   int qps_per_warp = 2;
   int ctas_per_sm_tpq[5] = {};  // indexed by lanes per QP (1, 2, 4)
   int tpq_lpq = 1;              // lanes per QP of the range-space loop kernel (QPB_TPQ_LPQ=1|2|4 overrides)
+  int tpq_pdl = 1;              // loop and finishing kernels of the three-pass path as programmatic dependent launches
+                                // (qpb_tpq.cuh, pdl_wait; QPB_TPQ_PDL=0: plain launches)
   int64_t tpq_min_n = 12288;    // smaller batches take a one-launch kernel: lower latency (QPB_TPQ_MIN_N)
   int64_t tpq_one_max = 1;      // ... up to here the range-space one (tpq_one_kernel), above it the half-warp kernel (QPB_TPQ_ONE_MAX)
   int warm_batches = 0;         // device-resident calls: the records carry warm-start words (qpb_set_warm_batches)
@@ -201,20 +203,47 @@ int launch_balance(qpb_handle* h, const IO& io, int64_t n, int ctas_per_sm, cuda
           qpb::tpq::tpq_setup_kernel<IO, true><<<edge, qpb::tpq::kEdgeThreads, stage_bytes, s>>>(h->edge, h->fast, part, m, prep, res, work, tk);
         else
           qpb::tpq::tpq_setup_kernel<IO, false><<<edge, qpb::tpq::kEdgeThreads, stage_bytes, s>>>(h->edge, h->fast, part, m, prep, res, work, tk);
+        // programmatic dependent launches for the second and third pass (not while the stream is being captured: a graph
+        // keeps the plain edges)
+        cudaStreamCaptureStatus cap_status = cudaStreamCaptureStatusNone;
+        const bool pdl = h->tpq_pdl && cudaStreamIsCapturing(s, &cap_status) == cudaSuccess && cap_status == cudaStreamCaptureStatusNone;
+        cudaLaunchAttribute pdl_attr[1];
+        pdl_attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        pdl_attr[0].val.programmaticStreamSerializationAllowed = 1;
+        auto launch_cfg = [&](unsigned grid_x, int threads) {
+          cudaLaunchConfig_t cfg = {};
+          cfg.gridDim = dim3(grid_x);
+          cfg.blockDim = dim3((unsigned)threads);
+          cfg.stream = s;
+          cfg.attrs = pdl_attr;
+          cfg.numAttrs = pdl ? 1 : 0;
+          return cfg;
+        };
         const int lthreads = lpq == 1 ? qpb::tpq::LoopShape<1>::THREADS : (lpq == 2 ? qpb::tpq::LoopShape<2>::THREADS : qpb::tpq::LoopShape<4>::THREADS);
         const int64_t want = (m * lpq + lthreads - 1) / lthreads;
         const int64_t cap = (int64_t)h->num_sms * h->ctas_per_sm_tpq[lpq];
         const int grid = (int)(want < cap ? want : cap);
-        if (lpq == 1)
-          qpb::tpq::tpq_loop_kernel<1><<<grid, lthreads, 0, s>>>(h->fast, prep, res, work, tk);
-        else if (lpq == 2)
-          qpb::tpq::tpq_loop_kernel<2><<<grid, lthreads, 0, s>>>(h->fast, prep, res, work, tk);
-        else
-          qpb::tpq::tpq_loop_kernel<4><<<grid, lthreads, 0, s>>>(h->fast, prep, res, work, tk);
-        if (early)
-          qpb::tpq::tpq_finish_kernel<IO, true><<<edge, qpb::tpq::kEdgeThreads, 0, s>>>(h->edge, h->fast, part, m, prep, res, work, tk);
-        else
-          qpb::tpq::tpq_finish_kernel<IO, false><<<edge, qpb::tpq::kEdgeThreads, 0, s>>>(h->edge, h->fast, part, m, prep, res, work, tk);
+        {
+          const cudaLaunchConfig_t cfg = launch_cfg((unsigned)grid, lthreads);
+          const double* cprep = prep;
+          const uint32_t* cwork = work;
+          if (lpq == 1)
+            QPB_CUDA(cudaLaunchKernelEx(&cfg, qpb::tpq::tpq_loop_kernel<1>, h->fast, cprep, res, cwork, tk));
+          else if (lpq == 2)
+            QPB_CUDA(cudaLaunchKernelEx(&cfg, qpb::tpq::tpq_loop_kernel<2>, h->fast, cprep, res, cwork, tk));
+          else
+            QPB_CUDA(cudaLaunchKernelEx(&cfg, qpb::tpq::tpq_loop_kernel<4>, h->fast, cprep, res, cwork, tk));
+        }
+        {
+          const cudaLaunchConfig_t cfg = launch_cfg(edge, qpb::tpq::kEdgeThreads);
+          const double *cprep = prep, *cres = res;
+          const uint32_t* cwork = work;
+          const unsigned long long* ctk = tk;
+          if (early)
+            QPB_CUDA(cudaLaunchKernelEx(&cfg, qpb::tpq::tpq_finish_kernel<IO, true>, h->edge, h->fast, part, m, cprep, cres, cwork, ctk));
+          else
+            QPB_CUDA(cudaLaunchKernelEx(&cfg, qpb::tpq::tpq_finish_kernel<IO, false>, h->edge, h->fast, part, m, cprep, cres, cwork, ctk));
+        }
         h->launches.fetch_add(3, std::memory_order_relaxed);
         QPB_CUDA(cudaGetLastError());
         if (!scratch) QPB_CUDA(cudaFreeAsync(prep, s));
@@ -658,6 +687,7 @@ int qpb_create(const qpb_params* params, int device, qpb_handle** out) {
     const int v = std::atoi(env);
     if (v == 1 || v == 2 || v == 4) h->tpq_lpq = v;
   }
+  if (const char* env = std::getenv("QPB_TPQ_PDL")) h->tpq_pdl = std::atoi(env) != 0;
   if (const char* env = std::getenv("QPB_TPQ_MIN_N")) {
     const long long v = std::atoll(env);
     if (v >= 0) h->tpq_min_n = v;

@@ -30,6 +30,18 @@ namespace tpq {
 
 constexpr int kEdgeThreads = 128;   // set-up / finishing kernels
 
+// Programmatic dependent launch (sm_90+).  The three passes of a batch are launched back to back on one stream, and between
+// two of them the GPU used to sit idle for 4-8 us (per-CTA timelines, profiles/r02_overlap_ab.txt: loop pass over at 71.7 us,
+// first CTA of the finishing pass at 75.8-79.9 us) -- 6-10 % of a 65 536-record step.  Now the set-up and loop kernels tell the
+// hardware at their very start that their dependents may be SCHEDULED (pdl_release), and the loop and finishing kernels are
+// launched with cudaLaunchAttributeProgrammaticStreamSerialization and begin with pdl_wait(), which returns once the whole
+// preceding grid has completed and its memory operations are visible: their CTAs move onto the SMs as the predecessor's CTAs
+// leave and sit in that wait -- issuing nothing, so the long QPs that end the loop pass are not slowed (unlike a finishing pass
+// that really runs beside them, same file) -- and start the moment the predecessor is done.  Results cannot change: nothing of a
+// predecessor is read before the wait.  Launched without the attribute (stream capture, QPB_TPQ_PDL=0) both are no-ops.
+__device__ __forceinline__ void pdl_release() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 #ifdef QPB_TPQ_TIMELINE
 // developer build only (tools/timeline.py): when every CTA of the loop and finishing passes started and ended (ns, %globaltimer)
 __device__ unsigned long long g_tl[4][8192];  // loop start, loop end, finish start, finish end -- by blockIdx.x
@@ -274,6 +286,7 @@ template <class IO, bool EARLY>
 __global__ void __launch_bounds__(kEdgeThreads, QPB_TPQ_EDGE_MINCTAS)
 tpq_setup_kernel(const __grid_constant__ EdgeParams P, const __grid_constant__ FastParams K, IO io, int64_t n, double* __restrict__ prep,
                  double* __restrict__ res, uint32_t* __restrict__ work, unsigned long long* __restrict__ ticket) {
+  pdl_release();
   const int64_t rec = (int64_t)blockIdx.x * kEdgeThreads + threadIdx.x;
   bool need = false;  // this record goes through the active-set loop (its starting pair is not optimal yet)
   extern __shared__ __align__(16) double stage_dyn[];
@@ -394,6 +407,8 @@ tpq_loop_kernel(const __grid_constant__ FastParams K, const double* __restrict__
                 const uint32_t* __restrict__ work, unsigned long long* __restrict__ ticket) {
   constexpr int LPL = 4 / LPQ, NS = 32 / LPQ;  // legs per lane, QP slots per warp
   constexpr int STAGE = LoopShape<LPQ>::STAGE, kLoopThreads = LoopShape<LPQ>::THREADS;
+  pdl_release();
+  pdl_wait();  // the set-up pass is complete: worklist, prepared records and its counter are visible
   QPB_TL(0);
   __shared__ double side_all[(kLoopThreads / LPQ) * kSideSize];
   __shared__ __align__(16) double stage_all[(kLoopThreads / 32) * STAGE * kPrepSize];
@@ -521,6 +536,7 @@ __global__ void __launch_bounds__(kEdgeThreads, QPB_TPQ_FINISH_MINCTAS)
 tpq_finish_kernel(const __grid_constant__ EdgeParams P, const __grid_constant__ FastParams K, IO io, int64_t n,
                   const double* __restrict__ prep, const double* __restrict__ res, const uint32_t* __restrict__ work,
                   const unsigned long long* __restrict__ ticket) {
+  pdl_wait();  // the loop pass is complete: every result word is final
   int64_t rec = (int64_t)blockIdx.x * kEdgeThreads + threadIdx.x;
   QPB_TL(2);
   if (LIST) {

@@ -532,6 +532,58 @@ def test_both_kernel_mappings(built, params06, qps_per_warp, monkeypatch):
     solver.close()
 
 
+def test_programmatic_dependent_launches_change_nothing(built, params06, monkeypatch):
+    """The loop and finishing kernels of the three-pass path are launched as programmatic dependents of the pass before
+    them (their CTAs are scheduled while the predecessor drains and wait in `griddepcontrol.wait` until it has completed):
+    only the idle time between the passes changes.  Every output byte must equal the plain launches (QPB_TPQ_PDL=0) --
+    device-resident calls back to back on one stream, the host pipeline (two compute streams), warm batches with early
+    finish, and a CUDA-graph replay (captured launches keep plain edges)."""
+    torch = _torch()
+    S = states.generate_states(150001, 609, profile="stress", masks="mixed")
+    S["w"][77, 2] = np.nan
+    n = 70001
+    monkeypatch.setenv("QPB_TPQ_PDL", "0")
+    plain = lib.BalanceSolver(params06)
+    want = plain.control_host(S)
+    W = S.copy()
+    W["pad"][:, :4] = want["pad"][:, :4]
+    W["x"] += 0.01
+    monkeypatch.setenv("QPB_TPQ_WARM_DEFER_MIN", "16384")  # warm batches of this size: three passes with early finish
+    plain_w = lib.BalanceSolver(params06)
+    want_w = plain_w.control_host(W)
+    plain.close(), plain_w.close()
+    monkeypatch.delenv("QPB_TPQ_PDL")
+    solver = lib.BalanceSolver(params06)
+    assert solver.control_host(W).tobytes() == want_w.tobytes()
+    monkeypatch.delenv("QPB_TPQ_WARM_DEFER_MIN")
+    d_out = torch.zeros(n * 256, dtype=torch.uint8, device="cuda")
+    d_ins = [torch.from_numpy(S[lo:lo + n].view(np.uint8).reshape(-1).copy()).cuda() for lo in (0, 40000, 80000)]
+    outs = [torch.zeros_like(d_out) for _ in d_ins]
+    for rep in range(3):  # nine calls queued back to back, no synchronisation in between
+        for d_in, o in zip(d_ins, outs):
+            solver.control_packed(d_in, o, n)
+    torch.cuda.synchronize()
+    for lo, o in zip((0, 40000, 80000), outs):
+        assert o.cpu().numpy().view(OUT_DTYPE).tobytes() == want[lo:lo + n].tobytes(), lo
+    assert solver.control_host(S).tobytes() == want.tobytes()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        solver.control_packed(d_ins[0], d_out, n, side.cuda_stream)
+    side.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=side):
+        solver.control_packed(d_ins[0], d_out, n, side.cuda_stream)
+    for lo in (40000, 0):
+        d_ins[0].copy_(torch.from_numpy(S[lo:lo + n].view(np.uint8).reshape(-1).copy()).cuda())
+        d_out.zero_()
+        graph.replay()
+        torch.cuda.synchronize()
+        assert d_out.cpu().numpy().view(OUT_DTYPE).tobytes() == want[lo:lo + n].tobytes(), lo
+    del graph
+    solver.close()
+
+
 def test_degenerate_and_extreme_parameter_regimes(built):
     """Active-set corner cases: pyramid apex (fzmin = 0, many linearly dependent rows), fzmin == fzmax,
     tiny and large friction, heavy robot saturating fzmax, strong regulariser."""

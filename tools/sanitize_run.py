@@ -30,8 +30,9 @@ def dev(a, shift=0):
 
 
 ref = None
-for mode, lpq in (("32", "1"), ("32", "2"), ("32", "4"), ("2", "1"), ("1", "1")):
-    os.environ["QPB_QPS_PER_WARP"], os.environ["QPB_TPQ_LPQ"] = mode, lpq
+# (kernel mapping, lanes per QP of the loop kernel, programmatic dependent launches of the second and third pass)
+for mode, lpq, pdl in (("32", "1", "1"), ("32", "1", "0"), ("32", "2", "1"), ("32", "4", "1"), ("2", "1", "1"), ("1", "1", "1")):
+    os.environ["QPB_QPS_PER_WARP"], os.environ["QPB_TPQ_LPQ"], os.environ["QPB_TPQ_PDL"] = mode, lpq, pdl
     sol = lib.BalanceSolver(params)
     out = sol.control_host(S)
     assert list(np.nonzero(out["status"])[0]) == [3, 5]
@@ -63,7 +64,7 @@ for mode, lpq in (("32", "1"), ("32", "2"), ("32", "4"), ("2", "1"), ("1", "1"))
     for b in [pin_i] + pin_o:
         b.free()
     sol.close()
-del os.environ["QPB_QPS_PER_WARP"], os.environ["QPB_TPQ_LPQ"]
+del os.environ["QPB_QPS_PER_WARP"], os.environ["QPB_TPQ_LPQ"], os.environ["QPB_TPQ_PDL"]
 
 sol = lib.BalanceSolver(params)
 for m, shift in ((300, 0), (300, 16), (19, 0)):  # record kernels: both alignments, full tiles and the tail
