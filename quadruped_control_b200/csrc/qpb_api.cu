@@ -203,10 +203,13 @@ int launch_balance(qpb_handle* h, const IO& io, int64_t n, int ctas_per_sm, cuda
           qpb::tpq::tpq_setup_kernel<IO, true><<<edge, qpb::tpq::kEdgeThreads, stage_bytes, s>>>(h->edge, h->fast, part, m, prep, res, work, tk);
         else
           qpb::tpq::tpq_setup_kernel<IO, false><<<edge, qpb::tpq::kEdgeThreads, stage_bytes, s>>>(h->edge, h->fast, part, m, prep, res, work, tk);
-        // programmatic dependent launches for the second and third pass (not while the stream is being captured: a graph
-        // keeps the plain edges)
+        // Programmatic dependent launches for the second and third pass of a device-resident call.  Not while the stream is
+        // being captured (a graph keeps the plain edges), and not for the stages of the host pipeline (they bring their own
+        // scratch): there the stages of two compute streams fill each other's idle SMs, and CTAs parked in griddepcontrol.wait
+        // hold the registers the other stream's kernels would have used -- end to end 1.005e8 -> 9.2e7 QP/s with it
+        // (profiles/r02_pdl_ab.txt).
         cudaStreamCaptureStatus cap_status = cudaStreamCaptureStatusNone;
-        const bool pdl = h->tpq_pdl && cudaStreamIsCapturing(s, &cap_status) == cudaSuccess && cap_status == cudaStreamCaptureStatusNone;
+        const bool pdl = h->tpq_pdl && !scratch && cudaStreamIsCapturing(s, &cap_status) == cudaSuccess && cap_status == cudaStreamCaptureStatusNone;
         cudaLaunchAttribute pdl_attr[1];
         pdl_attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         pdl_attr[0].val.programmaticStreamSerializationAllowed = 1;
