@@ -247,7 +247,8 @@ def kernel_path():
         return "balance_qp_kernel<PackedIO>"
     if m == "2":
         return "balance_qp_kernel16<PackedIO>"
-    return f"tpq_setup_kernel<PackedIO, false> + tpq_loop_kernel<{os.environ.get('QPB_TPQ_LPQ', '1')}> + tpq_finish_kernel<PackedIO, false>"
+    pdl = "" if os.environ.get("QPB_TPQ_PDL", "1") == "0" else " (loop and finishing passes: programmatic dependent launches)"
+    return f"tpq_setup_kernel<PackedIO, false> + tpq_loop_kernel<{os.environ.get('QPB_TPQ_LPQ', '1')}> + tpq_finish_kernel<PackedIO, false>{pdl}"
 
 
 def fp64_block(iters, n, step_ms):
