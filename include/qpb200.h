@@ -97,9 +97,11 @@ int qpb_default_params(qpb_params* out);
 
 /* Replaces the BalanceController + QuadrupedKinematics constructors (commander_node.cpp:337-338, 358).
  * Picks the kernels once: W = w*I with fzmin >= 0 (the reference's configuration, commander_node.cpp:289, 305) takes the
- * range-space path (three launches: set-up, active-set loop, polish + epilogue; batches below 4096 records and general
- * W take the one-launch half-warp kernel).  QPB_QPS_PER_WARP=1|2|32, QPB_TPQ_LPQ=1|2|4 and QPB_TPQ_MIN_N in the
- * environment override the choice (experiments, tests).
+ * range-space path (three launches: set-up, active-set loop, polish + epilogue -- for device-resident calls the second and
+ * third are programmatic dependent launches, so the passes follow each other without an idle gap; cold batches below
+ * 12 288 records and general W take the one-launch half-warp kernel, warm-started batches and single robots the one-launch
+ * range-space kernel).  QPB_QPS_PER_WARP=1|2|32, QPB_TPQ_LPQ=1|2|4, QPB_TPQ_MIN_N and QPB_TPQ_PDL=0|1 in the environment
+ * override the choices (experiments, tests).
  * Rejects (QPB_ERR_BAD_PARAMS): non-finite values, mu <= 0, fzmin > fzmax, fzmax < 0,
  * S or W not symmetric positive definite, max_iter < 1, and 2*mu*fzmax > 1e6 (the reference's
  * finite "far" bounds of +-1e6, balance_controller.cpp:296-297, are provably inactive below that
